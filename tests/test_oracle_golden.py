@@ -1,0 +1,112 @@
+"""Pins oracle/ff_oracle.py against the golden vectors that tests/golden/make_golden.py produced by
+running the unmodified reference (CPU fp32).  CPU-only."""
+import numpy as np
+import pytest
+
+from oracle import ff_oracle as O
+from tests import helpers as H
+
+TOL = 2e-6   # oracle vs reference, relative to the largest magnitude (both fp32 on CPU)
+
+
+@pytest.mark.parametrize('name', H.field_cases())
+def test_field_forward_and_grads(name):
+    g = H.golden('field_' + name)
+    fo = O.FieldOracle(H.oracle_spec(g), H.oracle_params(g))
+    feats, coeff = fo.get_coding(g['x'])
+    assert feats.shape == g['feats'].shape
+    assert H.rel_err(feats, g['feats']) < TOL, name
+    assert H.rel_err(coeff, g['coeff']) < TOL, name
+    y = O.mlp_forward(H._layers(g, 'param.linear_mat'), feats)
+    assert H.rel_err(y, g['linear_mat_out']) < 2e-5
+    if any(k.startswith('grad.') for k in g):
+        grads = fo.get_coding_bwd(g['x'], g['G'])
+        for kind in ('coeffs', 'basises'):
+            for i, gr in enumerate(grads[kind]):
+                key = f'grad.{kind}.{i}'
+                if key in g:
+                    assert gr.shape == g[key].shape
+                    assert H.rel_err(gr, g[key]) < 1e-5, (name, key)
+                elif isinstance(gr, list):     # 'mlp' factor types: per-layer (gW, gb)
+                    for l, (gW, gb) in enumerate(gr):
+                        assert H.rel_err(gW, g[f'{key}.backbone.{l}.weight']) < 2e-5, (name, key, l)
+                        if gb is not None:
+                            assert H.rel_err(gb, g[f'{key}.backbone.{l}.bias']) < 2e-5, (name, key, l)
+
+
+def test_mlps():
+    g = H.golden('mlp')
+    for tag in ('lm_nerf', 'lm_sdf', 'mlpC', 'deep'):
+        i, o, L, hdim, pe = g[f'{tag}.cfg']
+        layers = H._layers(g, f'{tag}.param')
+        y, cache = O.mlp_forward(layers, g[f'{tag}.x'], pe=int(pe), want_cache=True)
+        assert H.rel_err(y, g[f'{tag}.y']) < 1e-5
+        gx, grads = O.mlp_backward(layers, cache, g[f'{tag}.G'])
+        assert H.rel_err(gx, g[f'{tag}.gx']) < 1e-5
+        for l, (gW, gb) in enumerate(grads):
+            assert H.rel_err(gW, g[f'{tag}.grad.backbone.{l}.weight']) < 1e-5
+            if gb is not None:
+                assert H.rel_err(gb, g[f'{tag}.grad.backbone.{l}.bias']) < 1e-5
+    layers = H._layers(g, 'rm.param')
+    y, cache = O.render_mlp_forward(layers, g['rm.vd'], g['rm.feat'], want_cache=True)
+    assert H.rel_err(y, g['rm.y']) < 1e-5
+    gf, grads = O.render_mlp_backward(layers, cache, g['rm.G'])
+    assert H.rel_err(gf, g['rm.gfeat']) < 1e-5
+    for l, (gW, gb) in enumerate(grads):
+        assert H.rel_err(gW, g[f'rm.grad.mlp.{l}.weight']) < 1e-5
+
+
+def test_sampler_bit_exact():
+    g = H.golden('sampler_nerf')
+    pts, z, inner = O.sample_point(g['aabb'], g['stepSize'], g['rays'][:, :3], g['rays'][:, 3:], 443, g['jitter'])
+    assert np.array_equal(np.packbits(inner), g['inner_train'])
+    assert np.array_equal(inner.sum(-1), g['counts_train'])
+    assert np.array_equal(z[:, 0], g['z_train_first']) and np.array_equal(z[:, -1], g['z_train_last'])
+    assert np.allclose(pts.astype(np.float64).sum((0, 1)), g['pts_train_sum'], rtol=1e-9)
+    pts, z, inner = O.sample_point(g['aabb'], g['stepSize'], g['rays'][:, :3], g['rays'][:, 3:], int(g['nSamples']), None)
+    assert np.array_equal(np.packbits(inner), g['inner_eval'])
+    assert z[0, -1] == g['z_eval_last']
+
+
+def _render_oracle(g):
+    spec = H.oracle_spec(g)
+    fo = O.FieldOracle(spec, H.oracle_params(g))
+    rspec = dict(aabb=g['fact.aabb'], stepSize=g['fact.stepSize'], distance_scale=25.0, density_shift=-10.0,
+                 fea2denseAct='softplus', rayMarch_weight_thres=1e-3, view_pe=6, fea_pe=2)
+    mlps = dict(linear_mat=H._layers(g, 'param.linear_mat'), renderModule=H._layers(g, 'param.renderModule'))
+    alpha = dict(volume=g['alpha_volume'], aabb=g['alpha_aabb']) if 'alpha_volume' in g else None
+    return O.RenderOracle(fo, rspec, mlps, alpha)
+
+
+@pytest.mark.parametrize('name', ['train', 'train_alpha', 'eval_alpha'])
+def test_render_forward_backward(name):
+    g = H.golden('render_' + name)
+    ro = _render_oracle(g)
+    jitter = g['jitter'] if bool(g['is_train']) else None
+    out = ro.forward(g['rays'], int(g['N_samples']), jitter, white_bg=True, want_cache=True)
+    # bit-exact decisions
+    assert np.array_equal(np.packbits(out['ray_valid']), g['ray_valid'])
+    assert int(out['ray_valid'].sum()) == int(g['n_valid'])
+    assert np.array_equal(out['z'], g['z'])
+    assert H.rel_err(out['sigma'], g['sigma']) < 2e-5
+    assert H.rel_err(out['weight'], g['weight']) < 2e-5
+    app_ref = np.unpackbits(g['app_mask'])[:out['app_mask'].size].reshape(out['app_mask'].shape).astype(bool)
+    band = np.abs(g['weight'] - 1e-3) < 1e-7
+    assert np.array_equal(out['app_mask'][~band], app_ref[~band])
+    assert H.rel_err(out['rgb_map'], g['rgb_map']) < 1e-5
+    assert H.rel_err(out['depth_map'], g['depth_map']) < 1e-5
+    assert H.rel_err(out['coeffs'], g['coeffs']) < 1e-6
+    loss, g_rgb = O.mse_loss_and_grad(out['rgb_map'], g['target'])
+    assert abs(float(loss) - float(g['loss'])) < 1e-6
+    grads = ro.backward(out['cache'], g_rgb)
+    for kind in ('coeffs', 'basises'):
+        for i, gr in enumerate(grads[kind]):
+            assert H.rel_err(gr, g[f'grad.{kind}.{i}']) < 2e-4, (kind, i)
+    for l, (gW, gb) in enumerate(grads['linear_mat']):
+        assert H.rel_err(gW, g[f'grad.linear_mat.backbone.{l}.weight']) < 2e-4
+        if gb is not None:
+            assert H.rel_err(gb, g[f'grad.linear_mat.backbone.{l}.bias']) < 2e-4
+    for l, (gW, gb) in enumerate(grads['renderModule']):
+        assert H.rel_err(gW, g[f'grad.renderModule.mlp.{l}.weight']) < 2e-4
+        if gb is not None:
+            assert H.rel_err(gb, g[f'grad.renderModule.mlp.{l}.bias']) < 2e-4
