@@ -1,0 +1,272 @@
+// composite.cu — per-ray emission-absorption composite over the COMPACTED sample list, forward and backward.
+// Replaces basis2density (FactorFields.py:639-643), raw2alpha (:82-88), the weight-threshold mask (:879-881)
+// and the accumulation (:887-896) — dense [rays, samples] tensors + cumprod + index_put in the reference.
+// Invalid samples have sigma = 0 -> alpha = 0 -> a transmittance factor of exactly 1.0f in fp32
+// ((1 - 0) + 1e-10 == 1), so running the recurrence over the valid samples only is exact.
+// One warp per ray; transmittance by a multiplicative warp scan with a carried prefix.
+#include "ffb_common.cuh"
+#include "ffb_math.h"
+
+namespace ffb {
+
+__device__ __forceinline__ float density_act(const ffb_composite_desc& D, float f) {
+  const float x = FFB_ADD(f, D.density_shift);
+  return D.softplus ? softplus_f(x) : fmaxf(x, 0.0f);
+}
+__device__ __forceinline__ float density_act_grad(const ffb_composite_desc& D, float f) {
+  const float x = FFB_ADD(f, D.density_shift);
+  if (D.softplus) return x > 20.0f ? 1.0f : sigmoid_f(x);
+  return x > 0.0f ? 1.0f : 0.0f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) composite_weights_kernel(ffb_composite_desc D, const float* __restrict__ feat0, int ld_feat,
+                                                                const float* __restrict__ dist, const int32_t* __restrict__ offsets,
+                                                                int64_t R, float* __restrict__ sigma, float* __restrict__ trans,
+                                                                float* __restrict__ weight, int32_t* __restrict__ app_counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const int64_t beg = offsets[r], end = offsets[r + 1];
+    float carry = 1.0f;
+    int napp = 0;
+    for (int64_t c0 = beg; c0 < end; c0 += 32) {
+      const int64_t i = c0 + lane;
+      const bool act = i < end;
+      float sg = 0.0f, alpha = 0.0f, fac = 1.0f;
+      if (act) {
+        sg = density_act(D, feat0[i * ld_feat]);
+        const float delta = FFB_MUL(dist[i], D.distance_scale);
+        alpha = FFB_SUB(1.0f, expf(-FFB_MUL(sg, delta)));
+        fac = FFB_ADD(FFB_SUB(1.0f, alpha), 1e-10f);
+      }
+      float p = fac;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float y = __shfl_up_sync(0xffffffffu, p, o);
+        if (lane >= o) p *= y;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, p, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry * excl;
+      const float w = alpha * T;
+      carry *= __shfl_sync(0xffffffffu, p, 31);
+      if (act) {
+        sigma[i] = sg;
+        trans[i] = T;
+        weight[i] = w;
+      }
+      napp += __popc(__ballot_sync(0xffffffffu, act && w > D.weight_thres));
+    }
+    if (lane == 0) app_counts[r] = napp;
+  }
+}
+
+__global__ void __launch_bounds__(256) composite_app_fill_kernel(const float* __restrict__ weight, float thres,
+                                                                 const int32_t* __restrict__ offsets,
+                                                                 const int32_t* __restrict__ app_offsets, int64_t R,
+                                                                 int32_t* __restrict__ app_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const int64_t beg = offsets[r], end = offsets[r + 1];
+    int64_t base = app_offsets[r];
+    for (int64_t c0 = beg; c0 < end; c0 += 32) {
+      const int64_t i = c0 + lane;
+      const bool f = i < end && weight[i] > thres;
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (f) app_idx[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+      base += __popc(m);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) composite_accum_kernel(ffb_composite_desc D, const float* __restrict__ weight,
+                                                              const float* __restrict__ z, const float* __restrict__ rgb,
+                                                              const int32_t* __restrict__ offsets, const int32_t* __restrict__ app_offsets,
+                                                              int64_t R, float* __restrict__ rgb_map, float* __restrict__ pre_clamp,
+                                                              float* __restrict__ acc_out, float* __restrict__ depth) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const int64_t beg = offsets[r], end = offsets[r + 1];
+    int64_t abase = app_offsets[r];
+    float acc = 0.0f, dep = 0.0f, c0s = 0.0f, c1s = 0.0f, c2s = 0.0f;
+    for (int64_t c0 = beg; c0 < end; c0 += 32) {
+      const int64_t i = c0 + lane;
+      const bool act = i < end;
+      const float w = act ? weight[i] : 0.0f;
+      const bool f = act && w > D.weight_thres;
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (act) {
+        acc += w;
+        if (z) dep += w * z[i];
+      }
+      if (f) {
+        const int64_t j = abase + __popc(m & ((1u << lane) - 1u));
+        c0s += w * rgb[j * 3 + 0];
+        c1s += w * rgb[j * 3 + 1];
+        c2s += w * rgb[j * 3 + 2];
+      }
+      abase += __popc(m);
+    }
+    acc = warp_sum(acc);
+    dep = warp_sum(dep);
+    c0s = warp_sum(c0s);
+    c1s = warp_sum(c1s);
+    c2s = warp_sum(c2s);
+    if (lane == 0) {
+      float c[3] = {c0s, c1s, c2s};
+      for (int k = 0; k < 3; ++k) {
+        float v = c[k];
+        if (D.white_bg) v = v + (1.0f - acc);
+        if (pre_clamp) pre_clamp[r * 3 + k] = v;
+        rgb_map[r * 3 + k] = fminf(fmaxf(v, 0.0f), 1.0f);
+      }
+      if (acc_out) acc_out[r] = acc;
+      if (depth) depth[r] = dep;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) composite_bwd_kernel(ffb_composite_desc D, const float* __restrict__ g_rgb_map,
+                                                            const float* __restrict__ pre_clamp, const float* __restrict__ feat0, int ld_feat,
+                                                            const float* __restrict__ dist, const float* __restrict__ sigma,
+                                                            const float* __restrict__ trans, const float* __restrict__ weight,
+                                                            const float* __restrict__ rgb, const int32_t* __restrict__ offsets,
+                                                            const int32_t* __restrict__ app_offsets, int64_t R, float* __restrict__ g_rgb,
+                                                            float* __restrict__ g_feat0, int ld_g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const int64_t beg = offsets[r], end = offsets[r + 1];
+    if (beg >= end) continue;
+    float g[3];
+    for (int k = 0; k < 3; ++k) {
+      const float pc = pre_clamp[r * 3 + k];
+      g[k] = (pc >= 0.0f && pc <= 1.0f) ? g_rgb_map[r * 3 + k] : 0.0f;   // clamp(0,1) backward
+    }
+    const float gsum = D.white_bg ? (g[0] + g[1] + g[2]) : 0.0f;
+    int64_t aend = app_offsets[r + 1];   // one past the last shaded sample of this ray
+    float suffix = 0.0f;                 // sum_{k > chunk} g_w_k * w_k
+    const int64_t nchunks = (end - beg + 31) / 32;
+    for (int64_t ch = nchunks - 1; ch >= 0; --ch) {
+      const int64_t i = beg + ch * 32 + lane;
+      const bool act = i < end;
+      const float w = act ? weight[i] : 0.0f;
+      const bool f = act && w > D.weight_thres;
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      float gw = -gsum;
+      if (f) {
+        const unsigned upper = (lane == 31) ? 0u : (m & ~((2u << lane) - 1u));
+        const int64_t j = aend - 1 - __popc(upper);
+        const float c0 = rgb[j * 3 + 0], c1 = rgb[j * 3 + 1], c2 = rgb[j * 3 + 2];
+        gw += g[0] * c0 + g[1] * c1 + g[2] * c2;
+        g_rgb[j * 3 + 0] = w * g[0];
+        g_rgb[j * 3 + 1] = w * g[1];
+        g_rgb[j * 3 + 2] = w * g[2];
+      }
+      aend -= __popc(m);
+      const float gww = act ? gw * w : 0.0f;
+      // reverse inclusive scan over lanes
+      float s = gww;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float y = __shfl_down_sync(0xffffffffu, s, o);
+        if (lane + o < 32) s += y;
+      }
+      const float after = suffix + (s - gww);   // sum over samples after i
+      suffix += __shfl_sync(0xffffffffu, s, 0);
+      if (act) {
+        const float sg = sigma[i];
+        const float delta = FFB_MUL(dist[i], D.distance_scale);
+        const float e = expf(-FFB_MUL(sg, delta));          // 1 - alpha
+        const float fac = FFB_ADD(FFB_SUB(1.0f, FFB_SUB(1.0f, e)), 1e-10f);
+        const float g_alpha = gw * trans[i] - after / fac;
+        const float g_sigma = g_alpha * e * delta;
+        g_feat0[i * ld_g] = g_sigma * density_act_grad(D, feat0[i * ld_feat]);
+      }
+    }
+  }
+}
+
+__global__ void density_alpha_kernel(ffb_composite_desc D, const float* __restrict__ feat0, int ld_feat, float length, int64_t n,
+                                     const int32_t* __restrict__ n_dev, float* __restrict__ alpha) {
+  n = resolve_n(n, n_dev);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float sg = density_act(D, feat0[i * ld_feat]);
+    alpha[i] = FFB_SUB(1.0f, expf(-FFB_MUL(sg, length)));
+  }
+}
+
+}  // namespace ffb
+
+using namespace ffb;
+
+extern "C" {
+
+int ffb_composite_weights(const ffb_composite_desc* h_desc, const float* feat0, int32_t ld_feat, const float* dist,
+                          const int32_t* offsets, int64_t R, float* sigma, float* trans, float* weight, int32_t* app_counts,
+                          void* stream) {
+  FFB_REQUIRE(h_desc && feat0 && dist && offsets && sigma && trans && weight && app_counts && ld_feat >= 1, "bad argument");
+  if (R <= 0) return FFB_OK;
+  composite_weights_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, feat0, ld_feat, dist, offsets, R,
+                                                                                                sigma, trans, weight, app_counts);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_composite_app_fill(const float* weight, float weight_thres, const int32_t* offsets, const int32_t* app_offsets, int64_t R,
+                           int32_t* app_idx, void* stream) {
+  FFB_REQUIRE(weight && offsets && app_offsets && app_idx, "null argument");
+  if (R <= 0) return FFB_OK;
+  composite_app_fill_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(weight, weight_thres, offsets, app_offsets,
+                                                                                                 R, app_idx);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_composite_accum(const ffb_composite_desc* h_desc, const float* weight, const float* z, const float* rgb,
+                        const int32_t* offsets, const int32_t* app_offsets, int64_t R, float* rgb_map, float* pre_clamp, float* acc,
+                        float* depth, void* stream) {
+  FFB_REQUIRE(h_desc && weight && rgb && offsets && app_offsets && rgb_map, "null argument");
+  if (R <= 0) return FFB_OK;
+  composite_accum_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, weight, z, rgb, offsets, app_offsets, R,
+                                                                                              rgb_map, pre_clamp, acc, depth);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_composite_bwd(const ffb_composite_desc* h_desc, const float* g_rgb_map, const float* pre_clamp, const float* feat0,
+                      int32_t ld_feat, const float* dist, const float* sigma, const float* trans, const float* weight,
+                      const float* rgb, const int32_t* offsets, const int32_t* app_offsets, int64_t R, float* g_rgb, float* g_feat0,
+                      int32_t ld_g, void* stream) {
+  FFB_REQUIRE(h_desc && g_rgb_map && pre_clamp && feat0 && dist && sigma && trans && weight && rgb && offsets && app_offsets && g_rgb &&
+                  g_feat0,
+              "null argument");
+  if (R <= 0) return FFB_OK;
+  composite_bwd_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(
+      *h_desc, g_rgb_map, pre_clamp, feat0, ld_feat, dist, sigma, trans, weight, rgb, offsets, app_offsets, R, g_rgb, g_feat0, ld_g);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_density_alpha(const ffb_composite_desc* h_desc, const float* feat0, int32_t ld_feat, float length, int64_t n,
+                      const int32_t* n_dev, float* alpha, void* stream) {
+  FFB_REQUIRE(h_desc && feat0 && alpha && ld_feat >= 1, "bad argument");
+  if (n <= 0) return FFB_OK;
+  density_alpha_kernel<<<blocks_for(n, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, feat0, ld_feat, length, n, n_dev, alpha);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+}  // extern "C"

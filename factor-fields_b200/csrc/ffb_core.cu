@@ -1,0 +1,43 @@
+// ffb_core.cu — error state, device info, launch counter.
+#include <stdarg.h>
+#include <string.h>
+#include "ffb_common.cuh"
+
+namespace ffb {
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+}  // namespace ffb
+
+extern "C" {
+const char* ffb_last_error(void) { return ffb::g_err; }
+int ffb_abi_version(void) { return FFB_ABI_VERSION; }
+uint64_t ffb_launch_count(void) { return ffb::g_launches.load(); }
+
+int ffb_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  FFB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  FFB_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm) *sm = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  return FFB_OK;
+}
+}

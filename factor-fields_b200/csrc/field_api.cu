@@ -1,0 +1,24 @@
+// field_api.cu — public field-query entry points: dispatch between the specialised grid x grid kernels
+// (field_fast.cu) and the descriptor-driven generic kernels (field_generic.cu).
+#include "ffb_common.cuh"
+
+extern "C" {
+int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff,
+                          float* basis_out, void* stream);
+int ffb_field_generic_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
+                          const float* g_coeff, float* const* h_grads, void* stream);
+int ffb_field_fast_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, void* stream);
+int ffb_field_fast_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                       float* const* h_grads, void* stream);
+
+int ffb_field_query_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, void* stream) {
+  if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_fwd(f, x, n, n_dev, feats, coeff, stream);
+  return ffb_field_generic_fwd(f, x, n, n_dev, feats, coeff, nullptr, stream);
+}
+
+int ffb_field_query_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                        float* const* h_grads, void* stream) {
+  if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
+  return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
+}
+}

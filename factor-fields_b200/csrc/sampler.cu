@@ -1,0 +1,301 @@
+// sampler.cu — ray sampling + alpha-mask stream compaction.
+// Replaces FactorFields.sample_point (FactorFields.py:586-602), AlphaGridMask.sample_alpha (:103-110) and
+// the boolean-mask gathers of forward (:864-867, :874) — which in the reference materialise dense
+// [rays, samples, 3] tensors, call nonzero()/index() and sync the host on `.any()`.
+//
+// Design: one warp per ray.  Pass 1 counts valid samples per ray with warp ballots, a device-wide
+// exclusive scan turns counts into offsets, pass 2 recomputes the (cheap) positions and writes the
+// compacted list in row-major (ray, sample) order — the order torch boolean-mask indexing produces, so
+// indices compare bit-exactly.  All decision arithmetic is the unfused fp32 sequence of ffb_math.h.
+#include "ffb_common.cuh"
+#include "ffb_math.h"
+
+namespace ffb {
+
+struct RaySetup {
+  float o[3], d[3];
+  float tmin;
+};
+
+__device__ __forceinline__ bool sample_valid(const ffb_sampler_desc& D, const RaySetup& r, int s, float jit, bool train, float p[3],
+                                             float* t_out) {
+  const float t = sample_t(r.tmin, D.step_size, s, jit, train);
+  if (t_out) *t_out = t;
+  bool ok = sample_pos(r.o, r.d, t, D.aabb_min, D.aabb_max, p);
+  if (ok && D.alpha_volume) ok = alpha_lookup(D.alpha_volume, D.alpha_size, D.alpha_aabb_min, D.alpha_inv_size, p) > D.alpha_thres;
+  return ok;
+}
+
+__device__ __forceinline__ void load_ray(const float* __restrict__ rays, int64_t r, RaySetup& rs) {
+  for (int k = 0; k < 3; ++k) {
+    rs.o[k] = rays[r * 6 + k];
+    rs.d[k] = rays[r * 6 + 3 + k];
+  }
+}
+
+__global__ void __launch_bounds__(256) sample_count_kernel(ffb_sampler_desc D, const float* __restrict__ rays,
+                                                           const float* __restrict__ jitter, int64_t R, int32_t* __restrict__ counts,
+                                                           float* __restrict__ tmin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    RaySetup rs;
+    load_ray(rays, r, rs);
+    rs.tmin = ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max);
+    const bool train = jitter != nullptr;
+    const float jit = train ? jitter[r] : 0.0f;
+    int cnt = 0;
+    for (int s0 = 0; s0 < D.n_samples; s0 += 32) {
+      const int s = s0 + lane;
+      float p[3];
+      const bool ok = s < D.n_samples && sample_valid(D, rs, s, jit, train, p, nullptr);
+      cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) {
+      counts[r] = cnt;
+      if (tmin) tmin[r] = rs.tmin;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sample_fill_kernel(ffb_sampler_desc D, const float* __restrict__ rays,
+                                                          const float* __restrict__ jitter, const float* __restrict__ tmin,
+                                                          const int32_t* __restrict__ offsets, int64_t R, int64_t cap,
+                                                          float* __restrict__ xyz, int32_t* __restrict__ ray_id,
+                                                          int32_t* __restrict__ sample_id, float* __restrict__ z,
+                                                          float* __restrict__ dist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    RaySetup rs;
+    load_ray(rays, r, rs);
+    rs.tmin = tmin ? tmin[r] : ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max);
+    const bool train = jitter != nullptr;
+    const float jit = train ? jitter[r] : 0.0f;
+    int64_t base = offsets[r];
+    for (int s0 = 0; s0 < D.n_samples; s0 += 32) {
+      const int s = s0 + lane;
+      float p[3], t = 0.0f;
+      const bool ok = s < D.n_samples && sample_valid(D, rs, s, jit, train, p, &t);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int64_t i = base + __popc(m & ((1u << lane) - 1u));
+        if (i < cap) {
+          xyz[i * 3 + 0] = p[0];
+          xyz[i * 3 + 1] = p[1];
+          xyz[i * 3 + 2] = p[2];
+          if (ray_id) ray_id[i] = (int32_t)r;
+          if (sample_id) sample_id[i] = s;
+          if (z) z[i] = t;
+          if (dist) {
+            // dists = cat(z[1:] - z[:-1], 0)  (FactorFields.py:861)
+            const float tn = sample_t(rs.tmin, D.step_size, s + 1, jit, train);
+            dist[i] = (s + 1 < D.n_samples) ? FFB_SUB(tn, t) : 0.0f;
+          }
+        }
+      }
+      base += __popc(m);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sample_dense_kernel(ffb_sampler_desc D, const float* __restrict__ rays,
+                                                           const float* __restrict__ jitter, int64_t R, uint8_t* __restrict__ mask,
+                                                           float* __restrict__ z) {
+  const int64_t total = R * D.n_samples;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / D.n_samples;
+    const int s = (int)(t % D.n_samples);
+    RaySetup rs;
+    load_ray(rays, r, rs);
+    rs.tmin = ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max);
+    const bool train = jitter != nullptr;
+    float p[3], tt;
+    const bool ok = sample_valid(D, rs, s, train ? jitter[r] : 0.0f, train, p, &tt);
+    mask[t] = ok ? 1 : 0;
+    if (z) z[t] = tt;
+  }
+}
+
+__global__ void alpha_sample_kernel(ffb_sampler_desc D, const float* __restrict__ xyz, int64_t n, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p[3] = {xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2]};
+    out[i] = alpha_lookup(D.alpha_volume, D.alpha_size, D.alpha_aabb_min, D.alpha_inv_size, p);
+  }
+}
+
+// ---- exclusive scan (single pass, decoupled look-back over 1024-element tiles) -----------------
+constexpr int SCAN_T = 256, SCAN_PER = 4, SCAN_TILE = SCAN_T * SCAN_PER;
+
+__global__ void __launch_bounds__(SCAN_T) scan_tiles_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
+                                                            unsigned long long* __restrict__ tile_state /* zeroed */,
+                                                            unsigned int* __restrict__ ticket) {
+  __shared__ int warp_sums[SCAN_T / 32];
+  __shared__ long long s_prefix;
+  __shared__ unsigned s_tile;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);   // dynamic tile id => forward-progress safe look-back
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const int64_t base = (int64_t)tile * SCAN_TILE + threadIdx.x * SCAN_PER;
+  int v[SCAN_PER];
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_PER; ++j) {
+    v[j] = (base + j < n) ? in[base + j] : 0;
+    sum += v[j];
+  }
+  // block exclusive scan of `sum`
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int ws = lane < SCAN_T / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < SCAN_T / 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= o) ws += y;
+    }
+    if (lane < SCAN_T / 32) warp_sums[lane] = ws;
+  }
+  __syncthreads();
+  const int warp_off = wid ? warp_sums[wid - 1] : 0;
+  const int excl = warp_off + inc - sum;
+  const int tile_total = warp_sums[SCAN_T / 32 - 1];
+  // state word: bits 62..63 flag (1 = aggregate, 2 = inclusive prefix), low bits value
+  if (threadIdx.x == 0) {
+    long long prefix = 0;
+    if (tile == 0) {
+      atomicExch(&tile_state[0], (2ull << 62) | (unsigned long long)(unsigned)tile_total);
+    } else {
+      atomicExch(&tile_state[tile], (1ull << 62) | (unsigned long long)(unsigned)tile_total);
+      long long run = 0;
+      int look = (int)tile - 1;
+      while (true) {
+        unsigned long long st = atomicAdd(&tile_state[look], 0ull);
+        unsigned flag = (unsigned)(st >> 62);
+        if (flag == 0) continue;
+        run += (long long)(st & 0x3fffffffffffffffull);
+        if (flag == 2) break;
+        --look;
+      }
+      prefix = run;
+      atomicExch(&tile_state[tile], (2ull << 62) | (unsigned long long)(prefix + tile_total));
+    }
+    s_prefix = prefix;
+  }
+  __syncthreads();
+  int run = (int)s_prefix + excl;
+#pragma unroll
+  for (int j = 0; j < SCAN_PER; ++j) {
+    if (base + j < n) out[base + j] = run;
+    run += v[j];
+  }
+  // total at out[n]
+  if (base <= n - 1 && n - 1 < base + SCAN_PER) out[n] = run;
+}
+
+}  // namespace ffb
+
+using namespace ffb;
+
+static int check_sampler(const ffb_sampler_desc* d) {
+  FFB_REQUIRE(d, "null descriptor");
+  FFB_REQUIRE(d->n_samples > 0, "n_samples must be positive");
+  if (d->alpha_volume) FFB_REQUIRE(d->alpha_size[0] > 0 && d->alpha_size[1] > 0 && d->alpha_size[2] > 0, "bad alpha volume size");
+  return FFB_OK;
+}
+
+extern "C" {
+
+int ffb_sample_count(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter, int64_t R, int32_t* counts, float* tmin,
+                     void* stream) {
+  int rc = check_sampler(h_desc);
+  if (rc) return rc;
+  FFB_REQUIRE(rays && counts, "null argument");
+  if (R <= 0) return FFB_OK;
+  sample_count_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, rays, jitter, R, counts, tmin);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t R, void* stream) {
+  FFB_REQUIRE(counts && offsets, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (R <= 0) {
+    FFB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int32_t), s));
+    return FFB_OK;
+  }
+  const int64_t tiles = (R + SCAN_TILE - 1) / SCAN_TILE;
+  unsigned long long* state = nullptr;
+  FFB_CUDA(cudaMallocAsync(&state, sizeof(unsigned long long) * (tiles + 1), s));
+  FFB_CUDA(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (tiles + 1), s));
+  scan_tiles_kernel<<<(unsigned)tiles, SCAN_T, 0, s>>>(counts, offsets, R, state, reinterpret_cast<unsigned int*>(state + tiles));
+  FFB_LAUNCHED();
+  FFB_CUDA(cudaFreeAsync(state, s));
+  return FFB_OK;
+}
+
+int ffb_sample_fill(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter, const float* tmin, const int32_t* offsets,
+                    int64_t R, int64_t cap, float* xyz, int32_t* ray_id, int32_t* sample_id, float* z, float* dist, void* stream) {
+  int rc = check_sampler(h_desc);
+  if (rc) return rc;
+  FFB_REQUIRE(rays && offsets && xyz, "null argument");
+  if (R <= 0) return FFB_OK;
+  sample_fill_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, rays, jitter, tmin, offsets, R, cap, xyz,
+                                                                                          ray_id, sample_id, z, dist);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_sample_dense(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter, int64_t R, uint8_t* mask, float* z,
+                     void* stream) {
+  int rc = check_sampler(h_desc);
+  if (rc) return rc;
+  FFB_REQUIRE(rays && mask, "null argument");
+  if (R <= 0) return FFB_OK;
+  sample_dense_kernel<<<blocks_for(R * h_desc->n_samples, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, rays, jitter, R, mask, z);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_alpha_sample(const ffb_sampler_desc* h_desc, const float* xyz, int64_t n, float* out, void* stream) {
+  FFB_REQUIRE(h_desc && h_desc->alpha_volume && xyz && out, "null argument / no alpha volume");
+  if (n <= 0) return FFB_OK;
+  alpha_sample_kernel<<<blocks_for(n, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, xyz, n, out);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_sample_dense_host(const ffb_sampler_desc* h_desc, const float* h_rays, const float* h_jitter, int64_t R, uint8_t* h_mask,
+                          float* h_z) {
+  int rc = check_sampler(h_desc);
+  if (rc) return rc;
+  FFB_REQUIRE(h_rays && h_mask, "null argument");
+  if (R <= 0) return FFB_OK;
+  const int64_t S = h_desc->n_samples;
+  float *d_rays = nullptr, *d_jit = nullptr, *d_z = nullptr;
+  uint8_t* d_mask = nullptr;
+  cudaStream_t s = nullptr;
+  FFB_CUDA(cudaMalloc(&d_rays, sizeof(float) * R * 6));
+  FFB_CUDA(cudaMalloc(&d_mask, R * S));
+  if (h_jitter) FFB_CUDA(cudaMalloc(&d_jit, sizeof(float) * R));
+  if (h_z) FFB_CUDA(cudaMalloc(&d_z, sizeof(float) * R * S));
+  FFB_CUDA(cudaMemcpyAsync(d_rays, h_rays, sizeof(float) * R * 6, cudaMemcpyHostToDevice, s));
+  if (h_jitter) FFB_CUDA(cudaMemcpyAsync(d_jit, h_jitter, sizeof(float) * R, cudaMemcpyHostToDevice, s));
+  rc = ffb_sample_dense(h_desc, d_rays, d_jit, R, d_mask, d_z, s);
+  if (rc == FFB_OK) rc = check_cuda(cudaMemcpyAsync(h_mask, d_mask, R * S, cudaMemcpyDeviceToHost, s), "D2H mask");
+  if (rc == FFB_OK && h_z) rc = check_cuda(cudaMemcpyAsync(h_z, d_z, sizeof(float) * R * S, cudaMemcpyDeviceToHost, s), "D2H z");
+  if (rc == FFB_OK) rc = check_cuda(cudaStreamSynchronize(s), "sync");
+  cudaFree(d_rays); cudaFree(d_mask); cudaFree(d_jit); cudaFree(d_z);
+  return rc;
+}
+
+}  // extern "C"

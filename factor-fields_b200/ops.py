@@ -1,0 +1,529 @@
+"""Autograd-aware wrappers around the libffb200.so entry points.
+
+Each class below is the counterpart of a block of ATen ops in the reference (cited per class).  All
+compute is in the CUDA library; torch supplies device memory, the current stream and the autograd
+graph so that unmodified caller code (`loss.backward()`, `torch.optim.Adam`) keeps working.
+"""
+import ctypes as C
+
+import torch
+
+from . import native as nv
+
+_ACT = {'none': 0, 'relu': 1, 'sigmoid': 2}
+
+
+def _dev_check(t):
+    if not t.is_cuda:
+        raise RuntimeError('ffb200 ops need CUDA tensors: there is no CPU path (the oracle under oracle/ is test-only)')
+
+
+def _empty(shape, like, dtype=torch.float32):
+    return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# Field plan: host-side description of get_coeff / get_basis (FactorFields.py:425-516) as gather ops.
+# --------------------------------------------------------------------------------------------------
+class FieldPlan:
+    """Owns an ffb_field_t handle.  `tensors[i]` is the factor tensor op i samples (None for none)."""
+
+    def __init__(self, desc, tensors, perm, width):
+        self.desc, self.tensors, self.perm, self.width = desc, tensors, perm, width
+        self.handle = C.c_void_p()
+        nv.check(nv.lib().ffb_field_create(C.byref(desc), C.byref(self.handle)))
+        self.ptrs = [t.data_ptr() if t is not None else 0 for t in tensors]
+
+    def stale(self):
+        return any((t.data_ptr() if t is not None else 0) != p for t, p in zip(self.tensors, self.ptrs))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                nv.lib().ffb_field_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class PlanBuilder:
+    def __init__(self, xdim, in_dim, aabb, mapping, freq):
+        d = nv.FieldDesc()
+        d.xdim, d.in_dim = xdim, in_dim
+        lo, hi = aabb[0].tolist(), aabb[1].tolist()
+        for k in range(len(lo)):
+            d.aabb_min[k], d.aabb_max[k] = lo[k], hi[k]
+        d.mapping = nv.MAP_IDS[mapping]
+        fl = freq.tolist() if freq is not None else []
+        if len(fl) > nv.MAX_FREQ:
+            raise RuntimeError(f'ffb200: at most {nv.MAX_FREQ} frequency bands are supported')
+        d.n_freq = len(fl)
+        for i, f in enumerate(fl):
+            d.freq[i] = f
+        self.d = d
+        self.tensors = []
+        self.perm = None
+
+    def op(self, tensor, src, space, level=0, align=False, border=False, nearest=False, cst=(0.0, 0.0, 0.0)):
+        """tensor [1, C, *spatial] channels-last; src: per grid_sample coordinate (x=W first) the x column or -1."""
+        d = self.d
+        if d.n_ops >= nv.MAX_OPS:
+            raise RuntimeError('ffb200: too many gather ops in one field')
+        o = d.ops[d.n_ops]
+        o.data = nv.texel_ptr(tensor)
+        o.grad = 0
+        o.C = tensor.shape[1]
+        spatial = list(tensor.shape[2:])[::-1]  # W, H, (D)
+        o.nd = len(spatial)
+        if len(src) != o.nd:
+            raise RuntimeError('ffb200: gather op coordinate count does not match the tensor rank')
+        for k in range(o.nd):
+            o.size[k], o.src[k], o.cst[k] = spatial[k], src[k], cst[k]
+        o.space, o.level, o.align_corners, o.border, o.nearest = space, level, int(align), int(border), int(nearest)
+        self.tensors.append(tensor)
+        d.n_ops += 1
+        return d.n_ops - 1
+
+    def term(self, which, ops, col):
+        d = self.d
+        n = d.n_cterms if which == 'c' else d.n_bterms
+        if n >= nv.MAX_TERMS:
+            raise RuntimeError('ffb200: too many terms in one field')
+        t = (d.cterms if which == 'c' else d.bterms)[n]
+        t.n_ops = len(ops)
+        for i, o in enumerate(ops):
+            t.op[i] = o
+        t.col = col
+        if which == 'c':
+            d.n_cterms += 1
+        else:
+            d.n_bterms += 1
+
+    def finish(self, coeff_width, basis_width, basis_is_x=False, perm=None, device=None):
+        d = self.d
+        d.coeff_width, d.basis_width, d.basis_is_x = coeff_width, basis_width, int(basis_is_x)
+        if perm is not None:
+            self.perm = torch.as_tensor(perm, dtype=torch.int32, device=device).contiguous()
+            d.basis_perm = self.perm.data_ptr()
+        else:
+            d.basis_perm = 0
+        return FieldPlan(d, self.tensors, self.perm, basis_width if basis_width > 0 else coeff_width)
+
+
+class FieldQuery(torch.autograd.Function):
+    """get_coding / get_coeff / get_basis (FactorFields.py:425-533) + the autograd of F.grid_sample w.r.t. the
+    factor tensors (the reference never needs d/dx)."""
+
+    @staticmethod
+    def forward(ctx, plan, x, *tensors):
+        _dev_check(x)
+        x = x.contiguous().float()
+        n = x.shape[0]
+        feats = _empty((n, plan.width), x)
+        coeff = _empty((n, plan.width), x)
+        if n > 0:
+            nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(feats), nv.ptr(coeff), nv.stream()))
+        ctx.plan = plan
+        ctx.save_for_backward(x)
+        ctx.mark_non_differentiable()
+        return feats, coeff
+
+    @staticmethod
+    def backward(ctx, g_feats, g_coeff):
+        plan = ctx.plan
+        (x,) = ctx.saved_tensors
+        n = x.shape[0]
+        # one gradient tensor per distinct factor tensor (an op list may reference a tensor once only)
+        grads = []
+        arr = (C.c_void_p * nv.MAX_OPS)()
+        for i, t in enumerate(plan.tensors):
+            if ctx.needs_input_grad[2 + i]:
+                g = torch.zeros_like(t)  # preserve_format keeps the channels-last strides
+                grads.append(g)
+                arr[i] = g.data_ptr()
+            else:
+                grads.append(None)
+                arr[i] = 0
+        if n > 0 and any(g is not None for g in grads):
+            gf = g_feats.contiguous() if g_feats is not None else None
+            gc = g_coeff.contiguous() if g_coeff is not None else None
+            nv.check(nv.lib().ffb_field_query_bwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(gf, allow_none=True),
+                                                  nv.ptr(gc, allow_none=True), arr, nv.stream()))
+        return (None, None, *grads)
+
+
+def grid_mapping(positions, freq_bands, aabb, basis_mapping='sawtooth'):
+    """FactorFields.py:11-33.  positions [..., d] -> [..., d, F] ([..., d, 2F] for 'trigonometric')."""
+    _dev_check(positions)
+    shp = positions.shape
+    d = shp[-1]
+    x = positions.reshape(-1, d).contiguous().float()
+    F = freq_bands.numel()
+    Fo = 2 * F if basis_mapping == 'trigonometric' else F
+    out = _empty((x.shape[0], d, Fo), x)
+    lo = (C.c_float * 3)(*aabb[0].tolist())
+    hi = (C.c_float * 3)(*aabb[1].tolist())
+    fr = (C.c_float * F)(*freq_bands.tolist())
+    nv.check(nv.lib().ffb_grid_mapping(nv.ptr(x), C.c_int64(x.shape[0]), d, lo, hi, fr, F, nv.MAP_IDS[basis_mapping], nv.ptr(out),
+                                       nv.stream()))
+    return out.reshape(*shp, Fo)
+
+
+# --------------------------------------------------------------------------------------------------
+# MLPs
+# --------------------------------------------------------------------------------------------------
+def _linear_fwd(x, W, b, act):
+    n, K = x.shape
+    M = W.shape[0]
+    y = _empty((n, M), x)
+    if n > 0:
+        nv.check(nv.lib().ffb_linear_fwd(nv.ptr(x), nv.ptr(W), nv.ptr(b, allow_none=True), nv.ptr(y), C.c_int64(n), None, K, M, act,
+                                         nv.stream()))
+    return y
+
+
+def _mlp_backward(acts, layers, acts_kind, g_out, need_input_grad, param_needs):
+    """acts[l] = input of layer l, acts[l+1] = its (activated) output.  -> (g_input | None, [gW, gb, ...])"""
+    lib = nv.lib()
+    g = g_out.contiguous()
+    n = g.shape[0]
+    grads = [None] * len(layers)
+    for l in range(len(layers) - 1, -1, -1):
+        W, b = layers[l]
+        M, K = W.shape
+        act = acts_kind[l]
+        y = acts[l + 1]
+        gW = torch.zeros_like(W) if param_needs[l][0] else None
+        gb = torch.zeros_like(b) if (b is not None and param_needs[l][1]) else None
+        if n > 0 and gW is not None:
+            nv.check(lib.ffb_linear_bwd_weight_act(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), act, nv.ptr(acts[l]), nv.ptr(gW),
+                                                   nv.ptr(gb, allow_none=True), C.c_int64(n), None, K, M, nv.stream()))
+        grads[l] = (gW, gb)
+        if l > 0 or need_input_grad:
+            gx = _empty((n, K), g)
+            if n > 0:
+                nv.check(lib.ffb_linear_bwd_input(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), nv.ptr(W), nv.ptr(gx), C.c_int64(n), None,
+                                                  K, M, act, nv.stream()))
+            g = gx
+        else:
+            g = None
+    return g, grads
+
+
+def _split_params(params, has_bias):
+    layers, i = [], 0
+    for hb in has_bias:
+        W = params[i]
+        b = params[i + 1] if hb else None
+        i += 2 if hb else 1
+        layers.append((W, b))
+    return layers
+
+
+class MLPFunction(torch.autograd.Function):
+    """MLPMixer.forward (FactorFields.py:144-159): optional PE concat, Linear+ReLU ..., bias-free last layer."""
+
+    @staticmethod
+    def forward(ctx, x, pe, has_bias, *params):
+        _dev_check(x)
+        x = x.contiguous().float()
+        layers = _split_params(params, has_bias)
+        n, D = x.shape
+        h = x
+        if pe > 0:
+            h = _empty((n, D + 2 * D * pe), x)
+            if n > 0:
+                nv.check(nv.lib().ffb_pe_concat_fwd(nv.ptr(x), nv.ptr(h), C.c_int64(n), None, D, pe, nv.stream()))
+        acts = [h]
+        kinds = []
+        for l, (W, b) in enumerate(layers):
+            act = 1 if l != len(layers) - 1 else 0
+            kinds.append(act)
+            h = _linear_fwd(h, W, b, act)
+            acts.append(h)
+        ctx.pe, ctx.has_bias, ctx.kinds = pe, has_bias, kinds
+        ctx.save_for_backward(x, *acts, *params)
+        ctx.n_acts = len(acts)
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        x = saved[0]
+        acts = list(saved[1:1 + ctx.n_acts])
+        params = saved[1 + ctx.n_acts:]
+        layers = _split_params(params, ctx.has_bias)
+        needs = ctx.needs_input_grad[3:]
+        pn, i = [], 0
+        for hb in ctx.has_bias:
+            pn.append((needs[i], needs[i + 1] if hb else False))
+            i += 2 if hb else 1
+        gin, grads = _mlp_backward(acts, layers, ctx.kinds, g, ctx.needs_input_grad[0], pn)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.pe > 0:
+                n, D = x.shape
+                gx = _empty((n, D), x)
+                if n > 0:
+                    nv.check(nv.lib().ffb_pe_concat_bwd(nv.ptr(x), nv.ptr(gin), nv.ptr(gx), C.c_int64(n), None, D, ctx.pe, nv.stream()))
+            else:
+                gx = gin
+        flat = []
+        for (gW, gb), hb in zip(grads, ctx.has_bias):
+            flat.append(gW)
+            if hb:
+                flat.append(gb)
+        return (gx, None, None, *flat)
+
+
+# --------------------------------------------------------------------------------------------------
+# Sampling + compaction (no gradient)
+# --------------------------------------------------------------------------------------------------
+def make_sampler_desc(aabb, step_size, n_samples, alpha=None, alpha_thres=0.5):
+    d = nv.SamplerDesc()
+    lo, hi = aabb[0].tolist(), aabb[1].tolist()
+    for k in range(3):
+        d.aabb_min[k], d.aabb_max[k] = lo[k], hi[k]
+    d.step_size = float(step_size)
+    d.n_samples = int(n_samples)
+    if alpha is not None:
+        d.alpha_volume = alpha.volume_u8.data_ptr()
+        D, H, W = alpha.volume_u8.shape
+        d.alpha_size[0], d.alpha_size[1], d.alpha_size[2] = W, H, D
+        alo, ainv = alpha.aabb[0].tolist(), alpha.invgridSize.tolist()
+        for k in range(3):
+            d.alpha_aabb_min[k], d.alpha_inv_size[k] = alo[k], ainv[k]
+        d.alpha_thres = alpha_thres
+    else:
+        d.alpha_volume = 0
+    return d
+
+
+def exclusive_scan(counts):
+    R = counts.shape[0]
+    out = _empty((R + 1,), counts, torch.int32)
+    nv.check(nv.lib().ffb_exclusive_scan_i32(nv.i32p(counts), nv.i32p(out), C.c_int64(R), nv.stream()))
+    return out
+
+
+@torch.no_grad()
+def sample_compact(desc, rays, jitter):
+    """-> dict(xyz [Nv,3], ray_id, sample_id, z, dist, offsets [R+1], n_valid int).  One host read of Nv."""
+    _dev_check(rays)
+    lib = nv.lib()
+    rays = rays.contiguous().float()
+    R = rays.shape[0]
+    counts = _empty((R,), rays, torch.int32)
+    tmin = _empty((R,), rays)
+    jp = nv.ptr(jitter, allow_none=True)
+    nv.check(lib.ffb_sample_count(C.byref(desc), nv.ptr(rays), jp, C.c_int64(R), nv.i32p(counts), nv.ptr(tmin), nv.stream()))
+    offsets = exclusive_scan(counts)
+    nvld = int(offsets[R].item())
+    xyz = _empty((nvld, 3), rays)
+    ray_id = _empty((nvld,), rays, torch.int32)
+    sample_id = _empty((nvld,), rays, torch.int32)
+    z = _empty((nvld,), rays)
+    dist = _empty((nvld,), rays)
+    if nvld > 0:
+        nv.check(lib.ffb_sample_fill(C.byref(desc), nv.ptr(rays), jp, nv.ptr(tmin), nv.i32p(offsets), C.c_int64(R), C.c_int64(nvld),
+                                     nv.ptr(xyz), nv.i32p(ray_id), nv.i32p(sample_id), nv.ptr(z), nv.ptr(dist), nv.stream()))
+    return dict(xyz=xyz, ray_id=ray_id, sample_id=sample_id, z=z, dist=dist, offsets=offsets, counts=counts, n_valid=nvld, rays=rays)
+
+
+@torch.no_grad()
+def sample_dense(desc, rays, jitter, want_z=True):
+    _dev_check(rays)
+    rays = rays.contiguous().float()
+    R, S = rays.shape[0], desc.n_samples
+    mask = _empty((R, S), rays, torch.uint8)
+    z = _empty((R, S), rays) if want_z else None
+    nv.check(nv.lib().ffb_sample_dense(C.byref(desc), nv.ptr(rays), nv.ptr(jitter, allow_none=True), C.c_int64(R),
+                                       nv.ptr(mask, torch.uint8), nv.ptr(z, allow_none=True), nv.stream()))
+    return mask.bool(), z
+
+
+# --------------------------------------------------------------------------------------------------
+# Composite + appearance MLP
+# --------------------------------------------------------------------------------------------------
+def make_composite_desc(density_shift, fea2denseAct, distance_scale, weight_thres, white_bg):
+    d = nv.CompositeDesc()
+    d.density_shift = float(density_shift)
+    d.softplus = 1 if fea2denseAct == 'softplus' else 0
+    d.distance_scale = float(distance_scale)
+    d.weight_thres = float(weight_thres)
+    d.white_bg = int(bool(white_bg))
+    return d
+
+
+class RenderComposite(torch.autograd.Function):
+    """FactorFields.forward from `sigma[ray_valid] = ...` to `rgb_map.clamp` (FactorFields.py:876-896): density
+    activation, raw2alpha, weight-threshold compaction, MLPRender_Fea on the shaded samples, accumulation."""
+
+    @staticmethod
+    def forward(ctx, feat, samp, cdesc, view_pe, fea_pe, has_bias, *params):
+        lib = nv.lib()
+        feat = feat.contiguous()
+        Nv, ld = feat.shape
+        rays, offsets = samp['rays'], samp['offsets']
+        R = rays.shape[0]
+        sigma, trans, weight = _empty((Nv,), feat), _empty((Nv,), feat), _empty((Nv,), feat)
+        app_counts = _empty((R,), feat, torch.int32)
+        nv.check(lib.ffb_composite_weights(C.byref(cdesc), nv.ptr(feat), ld, nv.ptr(samp['dist']), nv.i32p(offsets), C.c_int64(R),
+                                           nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight), nv.i32p(app_counts), nv.stream()))
+        app_offsets = exclusive_scan(app_counts)
+        Na = int(app_offsets[R].item())
+        app_idx = _empty((Na,), feat, torch.int32)
+        layers = _split_params(params, has_bias)
+        Cf = ld - 1
+        Win = 3 + Cf + 6 * view_pe + 2 * fea_pe * Cf
+        acts, kinds = [], []
+        if Na > 0:
+            nv.check(lib.ffb_composite_app_fill(nv.ptr(weight), C.c_float(cdesc.weight_thres), nv.i32p(offsets), nv.i32p(app_offsets),
+                                                C.c_int64(R), nv.i32p(app_idx), nv.stream()))
+            inp = _empty((Na, Win), feat)
+            nv.check(lib.ffb_render_input_fwd(nv.ptr(feat), ld, nv.ptr(rays), nv.i32p(samp['ray_id']), nv.i32p(app_idx), nv.ptr(inp),
+                                              C.c_int64(Na), None, Cf, view_pe, fea_pe, nv.stream()))
+            h = inp
+            acts.append(h)
+            for l, (W, b) in enumerate(layers):
+                act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
+                kinds.append(act)
+                h = _linear_fwd(h, W, b, act)
+                acts.append(h)
+            rgb = h
+        else:
+            rgb = _empty((0, 3), feat)
+        rgb_map, pre_clamp = _empty((R, 3), feat), _empty((R, 3), feat)
+        acc, depth = _empty((R,), feat), _empty((R,), feat)
+        nv.check(lib.ffb_composite_accum(C.byref(cdesc), nv.ptr(weight), nv.ptr(samp['z']), nv.ptr(rgb), nv.i32p(offsets),
+                                         nv.i32p(app_offsets), C.c_int64(R), nv.ptr(rgb_map), nv.ptr(pre_clamp), nv.ptr(acc),
+                                         nv.ptr(depth), nv.stream()))
+        ctx.cdesc, ctx.samp, ctx.has_bias, ctx.kinds = cdesc, samp, has_bias, kinds
+        ctx.view_pe, ctx.fea_pe, ctx.n_acts, ctx.Na = view_pe, fea_pe, len(acts), Na
+        ctx.save_for_backward(feat, sigma, trans, weight, rgb, app_offsets, app_idx, pre_clamp, *acts, *params)
+        ctx.mark_non_differentiable(depth, acc, weight, app_idx)
+        ctx.aux = dict(n_app=Na)
+        return rgb_map, depth, acc, weight, app_idx
+
+    @staticmethod
+    def backward(ctx, g_rgb_map, *_unused):
+        lib = nv.lib()
+        saved = ctx.saved_tensors
+        feat, sigma, trans, weight, rgb, app_offsets, app_idx, pre_clamp = saved[:8]
+        acts = list(saved[8:8 + ctx.n_acts])
+        params = saved[8 + ctx.n_acts:]
+        samp, cdesc = ctx.samp, ctx.cdesc
+        Nv, ld = feat.shape
+        R = samp['rays'].shape[0]
+        Na = ctx.Na
+        g_feat = torch.zeros_like(feat)
+        g_rgb = _empty((Na, 3), feat)
+        g_rgb_map = g_rgb_map.contiguous()
+        if Nv > 0:
+            nv.check(lib.ffb_composite_bwd(C.byref(cdesc), nv.ptr(g_rgb_map), nv.ptr(pre_clamp), nv.ptr(feat), ld, nv.ptr(samp['dist']),
+                                           nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight), nv.ptr(rgb), nv.i32p(samp['offsets']),
+                                           nv.i32p(app_offsets), C.c_int64(R), nv.ptr(g_rgb), nv.ptr(g_feat), ld, nv.stream()))
+        layers = _split_params(params, ctx.has_bias)
+        needs = ctx.needs_input_grad[6:]
+        pn, i = [], 0
+        for hb in ctx.has_bias:
+            pn.append((needs[i], needs[i + 1] if hb else False))
+            i += 2 if hb else 1
+        flat = []
+        if Na > 0:
+            g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn)
+            Cf = ld - 1
+            nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(Na), None, Cf,
+                                              ctx.view_pe, ctx.fea_pe, nv.stream()))
+            for (gW, gb), hb in zip(grads, ctx.has_bias):
+                flat.append(gW)
+                if hb:
+                    flat.append(gb)
+        else:
+            for (W, b), hb, (nw, nb) in zip(layers, ctx.has_bias, pn):
+                flat.append(torch.zeros_like(W) if nw else None)
+                if hb:
+                    flat.append(torch.zeros_like(b) if nb else None)
+        return (g_feat, None, None, None, None, None, *flat)
+
+
+class RenderMLP(torch.autograd.Function):
+    """MLPRender_Fea.forward (FactorFields.py:188-203) for callers that use the module directly."""
+
+    @staticmethod
+    def forward(ctx, viewdirs, features, view_pe, fea_pe, has_bias, *params):
+        _dev_check(features)
+        lib = nv.lib()
+        n, Cf = features.shape
+        # pack [unused, features] so the shared input-assembly kernel (which skips the density column) can be used
+        feat = torch.cat([torch.zeros_like(features[:, :1]), features], -1).contiguous()
+        rays = torch.cat([torch.zeros_like(viewdirs), viewdirs], -1).contiguous()
+        Win = 3 + Cf + 6 * view_pe + 2 * fea_pe * Cf
+        inp = _empty((n, Win), features)
+        if n > 0:
+            nv.check(lib.ffb_render_input_fwd(nv.ptr(feat), Cf + 1, nv.ptr(rays), None, None, nv.ptr(inp), C.c_int64(n), None, Cf, view_pe,
+                                              fea_pe, nv.stream()))
+        layers = _split_params(params, has_bias)
+        acts, kinds, h = [inp], [], inp
+        for l, (W, b) in enumerate(layers):
+            act = 1 if l != len(layers) - 1 else 2
+            kinds.append(act)
+            h = _linear_fwd(h, W, b, act)
+            acts.append(h)
+        ctx.has_bias, ctx.kinds, ctx.n_acts, ctx.view_pe, ctx.fea_pe = has_bias, kinds, len(acts), view_pe, fea_pe
+        ctx.save_for_backward(feat, *acts, *params)
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        feat = saved[0]
+        acts = list(saved[1:1 + ctx.n_acts])
+        params = saved[1 + ctx.n_acts:]
+        layers = _split_params(params, ctx.has_bias)
+        needs = ctx.needs_input_grad[5:]
+        pn, i = [], 0
+        for hb in ctx.has_bias:
+            pn.append((needs[i], needs[i + 1] if hb else False))
+            i += 2 if hb else 1
+        g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g, True, pn)
+        n, ld = feat.shape
+        g_feat = torch.zeros_like(feat)
+        if n > 0:
+            nv.check(nv.lib().ffb_render_input_bwd(nv.ptr(feat), ld, None, nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(n), None, ld - 1,
+                                                   ctx.view_pe, ctx.fea_pe, nv.stream()))
+        flat = []
+        for (gW, gb), hb in zip(grads, ctx.has_bias):
+            flat.append(gW)
+            if hb:
+                flat.append(gb)
+        return (None, g_feat[:, 1:], None, None, None, *flat)
+
+
+@torch.no_grad()
+def density_alpha(cdesc, feat, length):
+    n, ld = feat.shape
+    out = _empty((n,), feat)
+    if n > 0:
+        nv.check(nv.lib().ffb_density_alpha(C.byref(cdesc), nv.ptr(feat.contiguous()), ld, C.c_float(float(length)), C.c_int64(n), None,
+                                            nv.ptr(out), nv.stream()))
+    return out
+
+
+@torch.no_grad()
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """In-place fused Adam on the raw storage (any memory format, as long as p/g/m/v share it)."""
+    n = p.numel()
+    nv.check(nv.lib().ffb_adam_step(C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(m.data_ptr()), C.c_void_p(v.data_ptr()),
+                                    C.c_int64(n), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps), int(step),
+                                    C.c_float(grad_scale), nv.stream()))
+
+
+@torch.no_grad()
+def mse_fwd_bwd(pred, target, g_scale=1.0):
+    """-> (loss [1] device tensor, g_pred)"""
+    pred, target = pred.contiguous(), target.contiguous()
+    loss = torch.zeros(1, device=pred.device)
+    g = torch.empty_like(pred)
+    nv.check(nv.lib().ffb_mse_fwd_bwd(nv.ptr(pred), nv.ptr(target), C.c_int64(pred.numel()), C.c_float(g_scale), nv.ptr(loss), nv.ptr(g),
+                                      nv.stream()))
+    return loss, g

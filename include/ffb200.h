@@ -1,0 +1,252 @@
+/* ffb200.h — C ABI of libffb200.so: the B200 (sm_100a) query-and-render hot path of Factor Fields.
+ *
+ * The reference (autonomousvision/factor-fields) is pure Python/PyTorch and has no FFI of its own;
+ * the interface each entry point replaces is therefore a *Python call site* of the reference, cited
+ * as file:line (paths relative to the reference checkout).  The Python host in
+ * factor-fields_b200/ binds these symbols with ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  Unless a parameter is named `h_*`, every
+ *    pointer is a DEVICE pointer on the current CUDA device; `stream` is a cudaStream_t passed as
+ *    void* (NULL = legacy default stream).  Nothing synchronises the stream except the functions
+ *    whose name ends in `_host`.
+ *  - all functions return 0 on success, a negative FFB_E* code otherwise; ffb_last_error() returns a
+ *    thread-local message.  There is NO CPU fallback: without a CUDA device every compute entry
+ *    point fails with FFB_ECUDA.
+ *  - factor tensors are CHANNELS-LAST: a reference parameter of logical shape [1,C,(D,)H,W]
+ *    (FactorFields.py:315,408) is stored as [(D,)H,W,C] — exactly torch's channels_last(_3d) memory
+ *    format of the same logical tensor, so state_dict shapes are unchanged.
+ *  - "n, n_dev": `n` is the row count (or an upper bound used to size the launch); if `n_dev` is
+ *    non-NULL the kernel reads the actual count from device memory (min(*n_dev, n)) so that
+ *    data-dependent sizes never need a host round trip.
+ */
+#ifndef FFB200_H
+#define FFB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB_ABI_VERSION 1
+#define FFB_OK 0
+#define FFB_EINVAL (-1)
+#define FFB_ECUDA (-2)
+#define FFB_ENOMEM (-3)
+
+#define FFB_MAX_OPS 64
+#define FFB_MAX_TERMS 40
+#define FFB_MAX_FREQ 16
+#define FFB_MAX_LAYERS 10
+
+/* basis_mapping, FactorFields.py:11-33 */
+enum { FFB_MAP_SAWTOOTH = 0, FFB_MAP_TRIANGLE = 1, FFB_MAP_SINC = 2, FFB_MAP_TRIG = 3, FFB_MAP_X = 4 };
+
+const char* ffb_last_error(void);
+int ffb_abi_version(void);
+/* Number of kernels launched by this library in this process (bench.py's gpu_launches). */
+uint64_t ffb_launch_count(void);
+int ffb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Field query: get_coeff / get_basis / get_coding (FactorFields.py:425-533) and their autograd.
+ *
+ * One ffb_gather_op == one F.grid_sample call site (:433,439,446-450,458,489,495,502-508).
+ * A term is the channel-wise product of 1..3 gathers (cp factors, :446-450,:501-508) written to
+ * `col .. col+C-1` of the coefficient row or of the concatenated basis row (:513).  The final row is
+ * feats[perm[q]] = basis_cat[q] * coeff[perm[q]]  (:514-515 re-ordering for vm, :527 product).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ffb_gather_op {
+  const float* data;    /* channels-last texels [S2][S1][S0][C] */
+  float* grad;          /* same layout; NULL = no gradient for this tensor (fix-grid, frozen) */
+  int32_t C;
+  int32_t nd;           /* spatial dims sampled: 1, 2 or 3 */
+  int32_t size[3];      /* S0 (fastest; grid_sample's x / W), S1 (y / H), S2 (z / D) */
+  int32_t src[3];       /* coordinate column feeding each dim; -1 = constant cst[k] */
+  float cst[3];
+  int32_t space;        /* 0: normalize_coord(x) (:635-637)   1: grid_mapping(x)[..., level] (:481) */
+  int32_t level;
+  int32_t align_corners;
+  int32_t border;       /* 1: padding_mode='border', 0: zeros */
+  int32_t nearest;      /* 1: mode='nearest', 0: (bi/tri)linear */
+} ffb_gather_op;
+
+typedef struct ffb_term {
+  int32_t n_ops;
+  int32_t op[3];
+  int32_t col;
+} ffb_term;
+
+typedef struct ffb_field_desc {
+  int32_t xdim;                 /* columns of x (in_dim, +1 in 'images' mode :469-470) */
+  int32_t in_dim;               /* dims fed to grid_mapping */
+  float aabb_min[3], aabb_max[3];
+  int32_t mapping;              /* FFB_MAP_* */
+  int32_t n_freq;
+  float freq[FFB_MAX_FREQ];     /* self.freq_bands */
+  int32_t n_ops;
+  ffb_gather_op ops[FFB_MAX_OPS];
+  int32_t n_cterms, n_bterms;
+  ffb_term cterms[FFB_MAX_TERMS], bterms[FFB_MAX_TERMS];
+  int32_t coeff_width;          /* 0 = coeff_type 'none' */
+  int32_t basis_width;          /* 0 = basis_type 'none' */
+  int32_t basis_is_x;           /* basis_type 'x' (:510-511): basis row = mapped coordinates */
+  const int32_t* basis_perm;    /* device [basis_width] or NULL (identity) */
+} ffb_field_desc;
+
+typedef struct ffb_field* ffb_field_t;
+
+/* Uploads a copy of the descriptor (h_desc is HOST memory).  Texel pointers must stay valid. */
+int ffb_field_create(const ffb_field_desc* h_desc, ffb_field_t* out);
+int ffb_field_destroy(ffb_field_t f);
+/* get_coding (:523-533): x [n, xdim] -> feats [n, W], coeff [n, W] (either may be NULL). */
+int ffb_field_query_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
+                        float* feats, float* coeff, void* stream);
+/* autograd of get_coding: scatter-adds d(sum feats*g_feats + coeff*g_coeff) into the gradient tensors
+ * (not zeroed here).  h_grads: HOST array of n_ops device pointers (NULL entry = no gradient for that
+ * tensor), or NULL to use ops[i].grad of the descriptor.  g_coeff may be NULL. */
+int ffb_field_query_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
+                        const float* g_feats, const float* g_coeff, float* const* h_grads, void* stream);
+/* grid_mapping (:11-33) on its own: x [n, in_dim] -> out [n, in_dim, F] (trig: [n, in_dim, 2F]). */
+int ffb_grid_mapping(const float* x, int64_t n, int32_t in_dim, const float* h_aabb_min,
+                     const float* h_aabb_max, const float* h_freq, int32_t n_freq, int32_t mapping,
+                     float* out, void* stream);
+
+/* Specialised fast path for grid x grid fields (nerf.yaml / sdf.yaml / image.yaml shapes).
+ * Same semantics as ffb_field_query_fwd/bwd; returns FFB_EINVAL if the descriptor is not eligible. */
+int ffb_field_fast_eligible(ffb_field_t f);
+int ffb_field_fast_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,
+                       float* coeff, void* stream);
+int ffb_field_fast_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
+                       const float* g_feats, const float* g_coeff, float* const* h_grads, void* stream);
+/* The descriptor-driven generic kernels, callable directly (parity tests compare both paths).
+ * basis_out: optional [n, W] copy of the (re-ordered) basis row. */
+int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,
+                          float* coeff, float* basis_out, void* stream);
+int ffb_field_generic_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
+                          const float* g_feats, const float* g_coeff, float* const* h_grads, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layers: nn.Linear call sites of MLPMixer (:153-156) and MLPRender_Fea (:197-200).
+ * Row-major: x [n,K], W [M,K] (torch layout), y [n,M].
+ * ------------------------------------------------------------------------------------------- */
+/* y = act(x W^T + b); act: 0 none, 1 relu, 2 sigmoid.  b may be NULL. */
+int ffb_linear_fwd(const float* x, const float* W, const float* b, float* y, int64_t n,
+                   const int32_t* n_dev, int32_t K, int32_t M, int32_t act, void* stream);
+/* gx = (gy .* act'(y)) W, where y is the saved forward OUTPUT of the layer and act the activation that
+ * produced it (mask applied on the fly; gy is not modified).  act == 0: y may be NULL. */
+int ffb_linear_bwd_input(float* gy, const float* y, const float* W, float* gx, int64_t n,
+                         const int32_t* n_dev, int32_t K, int32_t M, int32_t act, void* stream);
+/* gW += (gy .* act'(y))^T x ; gb += sum_rows (gy .* act'(y)).  gb may be NULL.  Not zeroed here. */
+int ffb_linear_bwd_weight_act(const float* gy, const float* y, int32_t act, const float* x, float* gW,
+                              float* gb, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
+                              void* stream);
+int ffb_linear_bwd_weight(const float* gy, const float* x, float* gW, float* gb, int64_t n,
+                          const int32_t* n_dev, int32_t K, int32_t M, void* stream);
+
+/* positional_encoding (:74-79) appended to the input: out [n, D + 2*D*pe] = [x, sin, cos]. */
+int ffb_pe_concat_fwd(const float* x, float* out, int64_t n, const int32_t* n_dev, int32_t D,
+                      int32_t pe, void* stream);
+/* gx [n,D] = g[:, :D] + dPE */
+int ffb_pe_concat_bwd(const float* x, const float* g, float* gx, int64_t n, const int32_t* n_dev,
+                      int32_t D, int32_t pe, void* stream);
+/* MLPRender_Fea input assembly (:190-196) with gather: for row j, i = app_idx ? app_idx[j] : j,
+ * features = feat[i, 1:1+C] (row stride ld_feat), viewdir = rays[ray_id ? ray_id[i] : i, 3:6]
+ * (row stride 6) -> out [n, 3 + C + 6*viewpe + 2*feape*C]. */
+int ffb_render_input_fwd(const float* feat, int32_t ld_feat, const float* rays, const int32_t* ray_id,
+                         const int32_t* app_idx, float* out, int64_t n, const int32_t* n_dev,
+                         int32_t C, int32_t viewpe, int32_t feape, void* stream);
+/* scatter of the gradient back: g_feat[i, 1:1+C] += d(features) (rows are unique -> plain add). */
+int ffb_render_input_bwd(const float* feat, int32_t ld_feat, const int32_t* app_idx, const float* g_in,
+                         float* g_feat, int64_t n, const int32_t* n_dev, int32_t C, int32_t viewpe,
+                         int32_t feape, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ray sampling + alpha-mask stream compaction: sample_point (:586-602), AlphaGridMask.sample_alpha
+ * (:103-110) and the boolean-mask indexing of forward (:864-867,874).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ffb_sampler_desc {
+  float aabb_min[3], aabb_max[3];
+  float step_size;              /* self.stepSize (:697), an fp32 value */
+  int32_t n_samples;
+  const uint8_t* alpha_volume;  /* [D][H][W] 0/1, or NULL (self.alphaMask is None) */
+  int32_t alpha_size[3];        /* W, H, D */
+  float alpha_aabb_min[3];
+  float alpha_inv_size[3];      /* AlphaGridMask.invgridSize (:98) */
+  float alpha_thres;            /* > thres keeps the sample: 0.5 in forward (:866), 0 in filtering (:833) */
+} ffb_sampler_desc;
+
+/* Pass 1: counts[r] = number of valid samples of ray r; tmin[r] = entry distance.
+ * jitter [R] (is_train, :593-595) or NULL. rays [R,6]. */
+int ffb_sample_count(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter,
+                     int64_t R, int32_t* counts, float* tmin, void* stream);
+/* Exclusive prefix sum: offsets [R+1]; offsets[R] = total. */
+int ffb_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t R, void* stream);
+/* Pass 2: compacted, row-major (ray, sample) order — identical to torch boolean-mask indexing.
+ * xyz [Nv,3], ray_id [Nv], sample_id [Nv], z [Nv] (interpx), dist [Nv] (:861; last sample 0). */
+int ffb_sample_fill(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter,
+                    const float* tmin, const int32_t* offsets, int64_t R, int64_t cap, float* xyz,
+                    int32_t* ray_id, int32_t* sample_id, float* z, float* dist, void* stream);
+/* Dense variant used by parity tests / filtering_rays: mask [R, S] (uint8), z [R,S] or NULL. */
+int ffb_sample_dense(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter, int64_t R,
+                     uint8_t* mask, float* z, void* stream);
+/* sample_alpha (:103-110) for arbitrary points: out [n] float. */
+int ffb_alpha_sample(const ffb_sampler_desc* h_desc, const float* xyz, int64_t n, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Volume-rendering composite: basis2density (:639-643), raw2alpha (:82-88), weight threshold
+ * (:879-881), accumulation (:887-896) — over the COMPACTED sample list.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ffb_composite_desc {
+  float density_shift;          /* cfg.renderer.density_shift */
+  int32_t softplus;             /* 1: softplus, 0: relu (fea2denseAct) */
+  float distance_scale;
+  float weight_thres;           /* rayMarch_weight_thres */
+  int32_t white_bg;
+} ffb_composite_desc;
+
+/* Phase A, per ray: sigma, alpha, T, weight for each valid sample; app_counts[r] = #(weight>thres).
+ * feat0 = density feature with row stride ld_feat (feat[:,0] of linear_mat's output). */
+int ffb_composite_weights(const ffb_composite_desc* h_desc, const float* feat0, int32_t ld_feat,
+                          const float* dist, const int32_t* offsets, int64_t R, float* sigma,
+                          float* trans, float* weight, int32_t* app_counts, void* stream);
+/* app_idx [Na]: indices (into the valid list) of shaded samples, in order. */
+int ffb_composite_app_fill(const float* weight, float weight_thres, const int32_t* offsets,
+                           const int32_t* app_offsets, int64_t R, int32_t* app_idx, void* stream);
+/* Phase B: rgb_map [R,3] (clamped), acc [R], depth [R]; rgb [Na,3] in app order. pre_clamp [R,3]. */
+int ffb_composite_accum(const ffb_composite_desc* h_desc, const float* weight, const float* z,
+                        const float* rgb, const int32_t* offsets, const int32_t* app_offsets, int64_t R,
+                        float* rgb_map, float* pre_clamp, float* acc, float* depth, void* stream);
+/* Backward: g_rgb_map [R,3] -> g_rgb [Na,3], g_feat0 (row stride ld_g; d loss / d density feature). */
+int ffb_composite_bwd(const ffb_composite_desc* h_desc, const float* g_rgb_map, const float* pre_clamp,
+                      const float* feat0, int32_t ld_feat, const float* dist, const float* sigma,
+                      const float* trans, const float* weight, const float* rgb, const int32_t* offsets,
+                      const int32_t* app_offsets, int64_t R, float* g_rgb, float* g_feat0, int32_t ld_g,
+                      void* stream);
+/* compute_alpha (:710-727) tail: alpha[i] = 1 - exp(-basis2density(feat0[i]) * length). */
+int ffb_density_alpha(const ffb_composite_desc* h_desc, const float* feat0, int32_t ld_feat, float length,
+                      int64_t n, const int32_t* n_dev, float* alpha, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Train-step glue: loss (train_per_scene.py:158) and Adam (:124-132,160-162,170-171).
+ * ------------------------------------------------------------------------------------------- */
+/* loss[0] += mean((pred-target)^2) over n elements (loss must be zeroed by the caller);
+ * g_pred = 2 (pred-target)/n * g_scale. */
+int ffb_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float g_scale, float* loss,
+                    float* g_pred, void* stream);
+/* torch.optim.Adam semantics (no amsgrad, no weight decay), fp32; step is 1-based. grad_scale
+ * multiplies g first (1/world after a sum all-reduce). */
+int ffb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry point (the end-to-end boundary: host rays in, host pixels out; includes the
+ * H2D/D2H copies and a stream synchronise).  Mirrors renderer.py:8-27 + FactorFields.py:586-602 for
+ * the sampling stage; used by tests to exercise the C ABI without torch.
+ * ------------------------------------------------------------------------------------------- */
+int ffb_sample_dense_host(const ffb_sampler_desc* h_desc, const float* h_rays, const float* h_jitter,
+                          int64_t R, uint8_t* h_mask, float* h_z);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB200_H */

@@ -1,0 +1,140 @@
+"""GPU parity of the field query (K1) and its scatter-add backward (K2) through the C ABI:
+ - against the golden vectors produced by the unmodified reference,
+ - against the oracle on fresh seeded inputs,
+ - size-independent properties at the BASELINE (nerf.yaml) size.
+Tolerance: north_star asks for 1e-4 relative in fp32; we assert tighter (see TOL_*)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = 2e-5    # features / coefficients, relative to the largest magnitude
+TOL_BWD = 1e-4    # scatter-add gradients (fp32 atomics, order-dependent rounding)
+
+
+@pytest.mark.parametrize('name', H.field_cases())
+def test_field_golden(name):
+    from tests import gpu_helpers as G
+    g = H.golden('field_' + name)
+    cfg, m = G.build_model(g)
+    assert list(m.basis_reso) == list(g['fact.basis_reso']) or np.isnan(np.array(m.basis_reso, float)).any()
+    assert np.array_equal(G.npy(m.freq_bands), g['fact.freq_bands'])
+    assert int(m.n_parameters()) == int(g['fact.n_parameters'])
+    x = G.t(g['x'])
+    feats, coeff = m.get_coding(x)
+    assert H.rel_err(G.npy(feats), g['feats']) < TOL_FWD, name
+    assert H.rel_err(G.npy(coeff), g['coeff']) < TOL_FWD, name
+    y = m.linear_mat(feats)
+    assert H.rel_err(G.npy(y), g['linear_mat_out']) < 1e-4, name
+    params = [(n, p) for n, p in m.named_parameters() if n.startswith('coeffs') or n.startswith('basises')]
+    if params:
+        grads = torch.autograd.grad((feats * G.t(g['G'])).sum(), [p for _, p in params], allow_unused=True)
+        for (n, p), gr in zip(params, grads):
+            ref = g['grad.' + n]
+            got = G.npy(gr) if gr is not None else np.zeros_like(ref)
+            assert got.shape == ref.shape
+            assert H.rel_err(got, ref) < TOL_BWD, (name, n)
+
+
+@pytest.mark.parametrize('name', ['nerf_grid_box', 'image', 'nerf_vm', 'nerf_CP', 'image_set', 'nerf_tria', 'sdf'])
+def test_field_vs_oracle_random(name):
+    """Fresh seeded inputs (incl. points outside the box) at a size the oracle finishes in seconds."""
+    from oracle import ff_oracle as O
+    from tests import gpu_helpers as G
+    g = H.golden('field_' + name)
+    cfg, m = G.build_model(g)
+    rng = np.random.RandomState(123)
+    lo, hi = g['fact.aabb'][0], g['fact.aabb'][1]
+    N = 20000
+    x = (lo - 0.05 * (hi - lo) + rng.rand(N, lo.size) * 1.1 * (hi - lo)).astype(np.float32)
+    if name == 'image':
+        x = np.floor(x) + 0.5
+    if name == 'image_set':
+        x[:, -1] = np.clip(np.floor(x[:, -1]) + 0.5, 0.5, hi[-1] - 0.5)
+    Gm = rng.randn(N, g['feats'].shape[1]).astype(np.float32)
+    fo = O.FieldOracle(H.oracle_spec(g), H.oracle_params(g))
+    f_ref, c_ref = fo.get_coding(x)
+    feats, coeff = m.get_coding(G.t(x))
+    assert H.rel_err(G.npy(feats), f_ref) < TOL_FWD
+    assert H.rel_err(G.npy(coeff), c_ref) < TOL_FWD
+    ref = fo.get_coding_bwd(x, Gm)
+    params = [(n, p) for n, p in m.named_parameters() if n.startswith('coeffs') or n.startswith('basises')]
+    grads = torch.autograd.grad((feats * G.t(Gm)).sum(), [p for _, p in params])
+    for (n, p), gr in zip(params, grads):
+        kind, i = n.split('.')[:2]
+        assert H.rel_err(G.npy(gr), ref[kind][int(i)]) < TOL_BWD, (name, n)
+
+
+def test_get_coeff_get_basis_split():
+    from tests import gpu_helpers as G
+    g = H.golden('field_nerf_vm')
+    cfg, m = G.build_model(g)
+    x = G.t(g['x'])
+    feats, coeff = m.get_coding(x)
+    c = m.get_coeff(x)
+    b = m.get_basis(x)
+    assert torch.equal(c, coeff)
+    assert H.rel_err(G.npy(b * c), G.npy(feats)) < 1e-6
+
+
+def test_grid_mapping_all_modes():
+    from oracle import ff_oracle as O
+    from ffb200.models.FactorFields import grid_mapping
+    rng = np.random.RandomState(5)
+    aabb = np.array([[-1.2, -0.7, -1.0], [1.3, 0.9, 0.8]], np.float32)
+    x = (aabb[0] + rng.rand(5000, 3) * (aabb[1] - aabb[0])).astype(np.float32)
+    freq = np.array([1.9, 3.1, 4.3, 5.4, 6.6, 7.8], np.float32)
+    for mode in ['sawtooth', 'triangle', 'sinc', 'trigonometric', 'x']:
+        ref = O.grid_mapping(x, freq, aabb, mode)
+        got = grid_mapping(torch.from_numpy(x).cuda(), torch.from_numpy(freq).cuda(), torch.from_numpy(aabb).cuda(), mode)
+        got = got.cpu().numpy()
+        assert got.shape == ref.shape
+        if mode in ('sawtooth', 'triangle', 'x'):
+            assert np.array_equal(got, ref), mode      # pure fp32 arithmetic: bit-exact
+        else:
+            assert np.abs(got - ref).max() < 2e-6, mode  # sinf/cosf vs libm
+
+
+def test_full_size_properties():
+    """nerf.yaml at its real size (5.3 M parameters, 1 M queries): linearity in the coefficients, weight-sum
+    checksum of the scatter-add, empty input."""
+    import ffb200
+    from ffb200.models.FactorFields import FactorFields
+    cfg = ffb200.load_cfg('nerf.yaml')
+    cfg.dataset.aabb = [[-1., -1., -1.], [1., 1., 1.]]
+    torch.manual_seed(0)
+    m = FactorFields(cfg, 'cuda')
+    assert m.n_parameters() == 5347600 and m.nSamples == 440
+    with torch.no_grad():
+        m.coeffs[0].add_(0.1 * torch.randn_like(m.coeffs[0]))
+    N = 1 << 20
+    x = (torch.rand(N, 3, device='cuda') * 2 - 1)
+    feats, coeff = m.get_coding(x)
+    assert feats.shape == (N, 18) and torch.isfinite(feats).all()
+    # linearity: doubling the coefficient grid doubles coeff and feats exactly (power of two)
+    with torch.no_grad():
+        m.coeffs[0].mul_(2.0)
+    f2, c2 = m.get_coding(x)
+    assert torch.equal(c2, coeff * 2) and torch.equal(f2, feats * 2)
+    # checksum: trilinear weights of an in-box query sum to 1 (border padding), so
+    # sum(grad_coeff[:, c]) == sum_n g[n, c] * basis[n, c]
+    gmat = torch.randn(N, 18, device='cuda')
+    gc, = torch.autograd.grad((f2 * gmat).sum(), [m.coeffs[0]])
+    basis = m.get_basis(x)
+    lhs = gc.double().sum(dim=(0, 2, 3, 4))
+    rhs = (gmat.double() * basis.double()).sum(0)
+    assert torch.allclose(lhs, rhs, rtol=2e-4, atol=1e-2)
+    # empty input
+    fe, ce = m.get_coding(torch.zeros(0, 3, device='cuda'))
+    assert fe.shape == (0, 18)
+
+
+def test_cpu_tensor_rejected():
+    from tests import gpu_helpers as G
+    g = H.golden('field_nerf_grid')
+    cfg, m = G.build_model(g)
+    with pytest.raises(RuntimeError):
+        m.get_coding(torch.zeros(4, 3))
