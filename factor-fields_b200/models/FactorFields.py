@@ -589,12 +589,17 @@ class FactorFields(torch.nn.Module):
 
     # ---- render parameters (FactorFields.py:693-708) ------------------------------------------------
     def update_renderParams(self, gridSize):
+        # The reference evaluates these few scalars with torch on self.device; a 3-element torch.mean rounds
+        # differently on CUDA and on CPU, and stepSize feeds bit-exact sampling decisions, so they are evaluated
+        # on the host (= the reference's CPU path, which is what the oracle is pinned to).
         self.aabbSize = self.aabb[1] - self.aabb[0]
         self.gridSize = torch.LongTensor(gridSize).to(self.device)
-        units = self.aabbSize / (self.gridSize - 1)
-        self.stepSize = torch.mean(units) * self.cfg.renderer.step_ratio
-        aabbDiag = torch.sqrt(torch.sum(torch.square(self.aabbSize)))
-        self.nSamples = int((aabbDiag / self.stepSize).item()) + 1
+        size_h = self.aabbSize.cpu()
+        units = size_h / (torch.LongTensor(gridSize) - 1)
+        step_h = torch.mean(units) * self.cfg.renderer.step_ratio
+        self.stepSize = step_h.to(self.device)
+        aabbDiag = torch.sqrt(torch.sum(torch.square(size_h)))
+        self.nSamples = int((aabbDiag / step_h).item()) + 1
 
     @torch.no_grad()
     def upsample_volume_grid(self, res_target):
@@ -625,7 +630,7 @@ class FactorFields(torch.nn.Module):
         aabbSize = self.inward_aabb[1] - self.inward_aabb[0]
         units = aabbSize / (torch.LongTensor(gridSize).to(self.device) - 1)
         units_half = 1.0 / (torch.LongTensor(gridSize) - 1) * 0.5
-        stepSize = torch.mean(units)
+        stepSize = torch.mean(units.cpu())   # host evaluation, see update_renderParams
         axes = [torch.linspace(units_half[k], 1 - units_half[k], gridSize[k]) for k in range(3)]
         samples = torch.stack(torch.meshgrid(axes, indexing='ij'), -1).to(self.device)
         dense_xyz = self.inward_aabb[0] * (1 - samples) + self.inward_aabb[1] * samples

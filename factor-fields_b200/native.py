@@ -122,3 +122,39 @@ def texel_ptr(p):
 
 def i32p(t, allow_none=True):
     return ptr(t, torch.int32, allow_none)
+
+
+# ---- optional per-section device timing (bench.py's roofline): CUDA events on the launching stream ----------
+_sections = None
+
+
+def profile_begin():
+    global _sections
+    _sections = {}
+
+
+def profile_end():
+    """-> {name: (total_ms, calls)}; synchronises."""
+    global _sections
+    torch.cuda.synchronize()
+    out = {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _sections.items()}
+    _sections = None
+    return out
+
+
+class section:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _sections is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _sections is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _sections.setdefault(self.name, []).append((self.e0, e1))
+        return False

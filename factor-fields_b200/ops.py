@@ -121,10 +121,11 @@ class FieldQuery(torch.autograd.Function):
         feats = _empty((n, plan.width), x)
         coeff = _empty((n, plan.width), x)
         if n > 0:
-            nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(feats), nv.ptr(coeff), nv.stream()))
+            with nv.section('field_fwd'):
+                nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(feats), nv.ptr(coeff),
+                                                      nv.stream()))
         ctx.plan = plan
         ctx.save_for_backward(x)
-        ctx.mark_non_differentiable()
         return feats, coeff
 
     @staticmethod
@@ -146,8 +147,9 @@ class FieldQuery(torch.autograd.Function):
         if n > 0 and any(g is not None for g in grads):
             gf = g_feats.contiguous() if g_feats is not None else None
             gc = g_coeff.contiguous() if g_coeff is not None else None
-            nv.check(nv.lib().ffb_field_query_bwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(gf, allow_none=True),
-                                                  nv.ptr(gc, allow_none=True), arr, nv.stream()))
+            with nv.section('field_bwd'):
+                nv.check(nv.lib().ffb_field_query_bwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(gf, allow_none=True),
+                                                      nv.ptr(gc, allow_none=True), arr, nv.stream()))
         return (None, None, *grads)
 
 
@@ -235,11 +237,12 @@ class MLPFunction(torch.autograd.Function):
                 nv.check(nv.lib().ffb_pe_concat_fwd(nv.ptr(x), nv.ptr(h), C.c_int64(n), None, D, pe, nv.stream()))
         acts = [h]
         kinds = []
-        for l, (W, b) in enumerate(layers):
-            act = 1 if l != len(layers) - 1 else 0
-            kinds.append(act)
-            h = _linear_fwd(h, W, b, act)
-            acts.append(h)
+        with nv.section('mlp_fwd'):
+            for l, (W, b) in enumerate(layers):
+                act = 1 if l != len(layers) - 1 else 0
+                kinds.append(act)
+                h = _linear_fwd(h, W, b, act)
+                acts.append(h)
         ctx.pe, ctx.has_bias, ctx.kinds = pe, has_bias, kinds
         ctx.save_for_backward(x, *acts, *params)
         ctx.n_acts = len(acts)
@@ -257,7 +260,8 @@ class MLPFunction(torch.autograd.Function):
         for hb in ctx.has_bias:
             pn.append((needs[i], needs[i + 1] if hb else False))
             i += 2 if hb else 1
-        gin, grads = _mlp_backward(acts, layers, ctx.kinds, g, ctx.needs_input_grad[0], pn)
+        with nv.section('mlp_bwd'):
+            gin, grads = _mlp_backward(acts, layers, ctx.kinds, g, ctx.needs_input_grad[0], pn)
         gx = None
         if ctx.needs_input_grad[0]:
             if ctx.pe > 0:
@@ -315,6 +319,8 @@ def sample_compact(desc, rays, jitter):
     counts = _empty((R,), rays, torch.int32)
     tmin = _empty((R,), rays)
     jp = nv.ptr(jitter, allow_none=True)
+    sec = nv.section('sample')
+    sec.__enter__()
     nv.check(lib.ffb_sample_count(C.byref(desc), nv.ptr(rays), jp, C.c_int64(R), nv.i32p(counts), nv.ptr(tmin), nv.stream()))
     offsets = exclusive_scan(counts)
     nvld = int(offsets[R].item())
@@ -326,6 +332,7 @@ def sample_compact(desc, rays, jitter):
     if nvld > 0:
         nv.check(lib.ffb_sample_fill(C.byref(desc), nv.ptr(rays), jp, nv.ptr(tmin), nv.i32p(offsets), C.c_int64(R), C.c_int64(nvld),
                                      nv.ptr(xyz), nv.i32p(ray_id), nv.i32p(sample_id), nv.ptr(z), nv.ptr(dist), nv.stream()))
+    sec.__exit__()
     return dict(xyz=xyz, ray_id=ray_id, sample_id=sample_id, z=z, dist=dist, offsets=offsets, counts=counts, n_valid=nvld, rays=rays)
 
 
@@ -367,11 +374,14 @@ class RenderComposite(torch.autograd.Function):
         R = rays.shape[0]
         sigma, trans, weight = _empty((Nv,), feat), _empty((Nv,), feat), _empty((Nv,), feat)
         app_counts = _empty((R,), feat, torch.int32)
+        sec = nv.section('composite_fwd')
+        sec.__enter__()
         nv.check(lib.ffb_composite_weights(C.byref(cdesc), nv.ptr(feat), ld, nv.ptr(samp['dist']), nv.i32p(offsets), C.c_int64(R),
                                            nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight), nv.i32p(app_counts), nv.stream()))
         app_offsets = exclusive_scan(app_counts)
         Na = int(app_offsets[R].item())
         app_idx = _empty((Na,), feat, torch.int32)
+        sec.__exit__()
         layers = _split_params(params, has_bias)
         Cf = ld - 1
         Win = 3 + Cf + 6 * view_pe + 2 * fea_pe * Cf
@@ -384,11 +394,12 @@ class RenderComposite(torch.autograd.Function):
                                               C.c_int64(Na), None, Cf, view_pe, fea_pe, nv.stream()))
             h = inp
             acts.append(h)
-            for l, (W, b) in enumerate(layers):
-                act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
-                kinds.append(act)
-                h = _linear_fwd(h, W, b, act)
-                acts.append(h)
+            with nv.section('rgbmlp_fwd'):
+                for l, (W, b) in enumerate(layers):
+                    act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
+                    kinds.append(act)
+                    h = _linear_fwd(h, W, b, act)
+                    acts.append(h)
             rgb = h
         else:
             rgb = _empty((0, 3), feat)
@@ -419,9 +430,11 @@ class RenderComposite(torch.autograd.Function):
         g_rgb = _empty((Na, 3), feat)
         g_rgb_map = g_rgb_map.contiguous()
         if Nv > 0:
-            nv.check(lib.ffb_composite_bwd(C.byref(cdesc), nv.ptr(g_rgb_map), nv.ptr(pre_clamp), nv.ptr(feat), ld, nv.ptr(samp['dist']),
-                                           nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight), nv.ptr(rgb), nv.i32p(samp['offsets']),
-                                           nv.i32p(app_offsets), C.c_int64(R), nv.ptr(g_rgb), nv.ptr(g_feat), ld, nv.stream()))
+            with nv.section('composite_bwd'):
+                nv.check(lib.ffb_composite_bwd(C.byref(cdesc), nv.ptr(g_rgb_map), nv.ptr(pre_clamp), nv.ptr(feat), ld,
+                                               nv.ptr(samp['dist']), nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight), nv.ptr(rgb),
+                                               nv.i32p(samp['offsets']), nv.i32p(app_offsets), C.c_int64(R), nv.ptr(g_rgb),
+                                               nv.ptr(g_feat), ld, nv.stream()))
         layers = _split_params(params, ctx.has_bias)
         needs = ctx.needs_input_grad[6:]
         pn, i = [], 0
@@ -430,7 +443,8 @@ class RenderComposite(torch.autograd.Function):
             i += 2 if hb else 1
         flat = []
         if Na > 0:
-            g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn)
+            with nv.section('rgbmlp_bwd'):
+                g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn)
             Cf = ld - 1
             nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(Na), None, Cf,
                                               ctx.view_pe, ctx.fea_pe, nv.stream()))

@@ -1,0 +1,102 @@
+"""ORACLE / CPU BASELINE — test infrastructure, NOT product code.
+
+Restatement of the reference's NeRF train step (grid coefficient x grid basis, bounded scene) with the SAME
+third-party operators the reference calls (torch CPU: F.grid_sample, nn.functional.linear, cumprod, autograd,
+Adam), so that timing it on the host cores reproduces the cost of the reference's CPU path.  The reference itself
+(pure Python) cannot travel to the GPU box; this file is what `bench.py`'s cpu_baseline leg and `--impl reference`
+time ("kind": "port").  Pinned against the golden vectors in tests/test_oracle_golden.py::test_torch_port.
+
+Follows /root/reference/models/FactorFields.py (line numbers cited inline) and train_per_scene.py:149-171.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def grid_mapping_sawtooth(x, freq_bands, aabb):                          # FactorFields.py:11-22
+    scale = max(aabb[1] - aabb[0])[..., None] / freq_bands
+    local = (x - aabb[0])[..., None] % scale
+    return (local / (scale / 2) - 1).clamp(-1., 1.)
+
+
+def positional_encoding(p, freqs):                                         # :74-79
+    fb = (2 ** torch.arange(freqs).float())
+    pts = (p[..., None] * fb).reshape(p.shape[:-1] + (freqs * p.shape[-1],))
+    return torch.cat([torch.sin(pts), torch.cos(pts)], dim=-1)
+
+
+class TorchPort:
+    """state: dict of numpy arrays with the reference's state_dict names (reference layout)."""
+
+    def __init__(self, state, aabb, freq_bands, step_size, rcfg, lr_small=0.001, lr_large=0.02):
+        self.p = {k: torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(v)).float()) for k, v in state.items()}
+        self.aabb = torch.tensor(aabb, dtype=torch.float32)
+        self.freq = torch.tensor(freq_bands, dtype=torch.float32)
+        self.step = torch.tensor(step_size, dtype=torch.float32)
+        self.r = rcfg
+        self.n_basis = len([k for k in state if k.startswith('basises.')])
+        small = [v for k, v in self.p.items() if k.startswith(('linear_mat', 'renderModule'))]
+        large = [v for k, v in self.p.items() if k.startswith(('coeffs', 'basises'))]
+        self.opt = torch.optim.Adam([{'params': small, 'lr': lr_small}, {'params': large, 'lr': lr_large}], betas=(0.9, 0.99))
+
+    def get_coding(self, x):                                               # :425-434, :467-490, :523-527
+        N = x.shape[0]
+        inv = 2.0 / (self.aabb[1] - self.aabb[0])
+        pts = ((x - self.aabb[0]) * inv - 1).view(1, -1, 1, 1, 3)
+        coeff = F.grid_sample(self.p['coeffs.0'], pts, mode='bilinear', align_corners=False, padding_mode='border').view(-1, N).t()
+        xyz = grid_mapping_sawtooth(x, self.freq, self.aabb).view(1, 1, 1, -1, 3, self.freq.numel())
+        bs = [F.grid_sample(self.p[f'basises.{i}'], xyz[..., i], mode='bilinear', align_corners=True).view(-1, N).T
+              for i in range(self.n_basis)]
+        return torch.cat(bs, dim=-1) * coeff, coeff
+
+    def linear_mat(self, h):                                               # :144-159
+        h = F.relu(F.linear(h, self.p['linear_mat.backbone.0.weight'], self.p['linear_mat.backbone.0.bias']))
+        return F.linear(h, self.p['linear_mat.backbone.1.weight'])
+
+    def render_module(self, viewdirs, features):                           # :188-203
+        h = torch.cat([features, viewdirs, positional_encoding(features, self.r['fea_pe']),
+                       positional_encoding(viewdirs, self.r['view_pe'])], dim=-1)
+        h = F.relu(F.linear(h, self.p['renderModule.mlp.0.weight'], self.p['renderModule.mlp.0.bias']))
+        h = F.relu(F.linear(h, self.p['renderModule.mlp.1.weight'], self.p['renderModule.mlp.1.bias']))
+        return torch.sigmoid(F.linear(h, self.p['renderModule.mlp.2.weight']))
+
+    def forward(self, rays, n_samples, jitter=None, white_bg=True):        # :586-602, :843-898
+        o, d = rays[:, :3], rays[:, 3:6]
+        vec = torch.where(d == 0, torch.full_like(d, 1e-6), d)
+        t_min = torch.minimum((self.aabb[1] - o) / vec, (self.aabb[0] - o) / vec).amax(-1).clamp(min=0.05, max=1e3)
+        rng = torch.arange(n_samples)[None].float()
+        if jitter is not None:
+            rng = rng.repeat(o.shape[0], 1) + jitter[:, None]
+        z = t_min[..., None] + self.step * rng
+        pts = o[..., None, :] + d[..., None, :] * z[..., None]
+        valid = ~((self.aabb[0] > pts) | (pts > self.aabb[1])).any(dim=-1)
+        dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), dim=-1)
+        viewdirs = d.view(-1, 1, 3).expand(pts.shape)
+        sigma = torch.zeros(pts.shape[:-1])
+        rgb = torch.zeros((*pts.shape[:2], 3))
+        if valid.any():
+            feats, _ = self.get_coding(pts[valid])
+            feat = self.linear_mat(feats)
+            sigma[valid] = F.softplus(feat[..., 0] + self.r['density_shift'])
+        alpha = 1. - torch.exp(-sigma * dists * self.r['distance_scale'])       # :82-88
+        T = torch.cumprod(torch.cat([torch.ones_like(alpha[..., :1]), 1. - alpha + 1e-10], -1), -1)
+        weight = alpha * T[..., :-1]
+        app = weight > self.r['rayMarch_weight_thres']
+        valid_new = torch.logical_and(valid, app)
+        app_c = valid_new[valid]
+        if app_c.any():
+            rgb[valid_new] = self.render_module(viewdirs[valid_new], feat[app_c, 1:])
+        acc = torch.sum(weight, -1)
+        rgb_map = torch.sum(weight[..., None] * rgb, -2)
+        if white_bg:
+            rgb_map = rgb_map + (1. - acc[..., None])
+        self.stats = dict(n_valid=int(valid.sum()), n_app=int(valid_new.sum()))
+        return rgb_map.clamp(0, 1), torch.sum(weight * z, -1).detach(), valid, weight
+
+    def train_step(self, rays, target, n_samples, jitter):                 # train_per_scene.py:154-162
+        rgb_map, _, _, _ = self.forward(rays, n_samples, jitter)
+        loss = torch.mean((rgb_map - target) ** 2)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return float(loss)

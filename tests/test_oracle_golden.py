@@ -110,3 +110,35 @@ def test_render_forward_backward(name):
         assert H.rel_err(gW, g[f'grad.renderModule.mlp.{l}.weight']) < 2e-4
         if gb is not None:
             assert H.rel_err(gb, g[f'grad.renderModule.mlp.{l}.bias']) < 2e-4
+
+
+def test_torch_port():
+    """oracle/torch_port.py (the CPU-baseline restatement with torch CPU operators) against the reference's golden
+    render vectors: same masks, rgb, loss."""
+    import torch
+    from oracle.torch_port import TorchPort
+    g = H.golden('render_train')
+    state = {k[len('param.'):]: v for k, v in g.items() if k.startswith('param.')}
+    tp = TorchPort(state, g['fact.aabb'], g['fact.freq_bands'], g['fact.stepSize'],
+                   dict(density_shift=-10.0, distance_scale=25.0, rayMarch_weight_thres=1e-3, view_pe=6, fea_pe=2))
+    rgb, depth, valid, weight = tp.forward(torch.from_numpy(g['rays']), int(g['N_samples']), torch.from_numpy(g['jitter']))
+    assert np.array_equal(np.packbits(valid.numpy()), g['ray_valid'])
+    assert H.rel_err(rgb.detach().numpy(), g['rgb_map']) < 1e-6
+    assert H.rel_err(weight.detach().numpy(), g['weight']) < 1e-6
+    loss = torch.mean((rgb - torch.from_numpy(g['target'])) ** 2)
+    assert abs(float(loss.detach()) - float(g['loss'])) < 1e-7
+    gc, = torch.autograd.grad(loss, [tp.p['coeffs.0']])
+    assert H.rel_err(gc.numpy(), g['grad.coeffs.0']) < 1e-5
+
+
+def test_bench_workload_matches_reference_shapes():
+    """bench_workload's hard-coded nerf.yaml facts equal what the product's host logic derives from configs/nerf.yaml."""
+    import bench_workload as W
+    import ffb200
+    from ffb200.models.FactorFields import field_shapes
+    cfg = ffb200.load_cfg('nerf.yaml')
+    sh = field_shapes(cfg, W.AABB)
+    assert list(sh['basis_reso']) == W.BASIS_RESO and [int(v) for v in sh['coeff_reso']] == [W.COEFF_RESO] * 3
+    assert np.array_equal(sh['freq_bands'].numpy(), np.array(W.FREQ_BANDS, np.float32))
+    sd = W.make_state()
+    assert sum(v.size for v in sd.values()) == 5347600
