@@ -372,6 +372,15 @@ class RenderComposite(torch.autograd.Function):
         Nv, ld = feat.shape
         rays, offsets = samp['rays'], samp['offsets']
         R = rays.shape[0]
+        if Nv == 0:   # every ray misses the box / the alpha mask: background only (FactorFields.py:887-893 with weight == 0)
+            bg = 1.0 if cdesc.white_bg else 0.0
+            ctx.Na, ctx.empty, ctx.has_bias = 0, True, has_bias
+            ctx.save_for_backward(feat, *params)
+            outs = (torch.full((R, 3), bg, device=feat.device), torch.zeros(R, device=feat.device), torch.zeros(R, device=feat.device),
+                    _empty((0,), feat), _empty((0,), feat, torch.int32))
+            ctx.mark_non_differentiable(*outs[1:])
+            return outs
+        ctx.empty = False
         sigma, trans, weight = _empty((Nv,), feat), _empty((Nv,), feat), _empty((Nv,), feat)
         app_counts = _empty((R,), feat, torch.int32)
         sec = nv.section('composite_fwd')
@@ -419,6 +428,8 @@ class RenderComposite(torch.autograd.Function):
     def backward(ctx, g_rgb_map, *_unused):
         lib = nv.lib()
         saved = ctx.saved_tensors
+        if ctx.empty:
+            return (torch.zeros_like(saved[0]), None, None, None, None, None, *[torch.zeros_like(p) for p in saved[1:]])
         feat, sigma, trans, weight, rgb, app_offsets, app_idx, pre_clamp = saved[:8]
         acts = list(saved[8:8 + ctx.n_acts])
         params = saved[8 + ctx.n_acts:]

@@ -138,3 +138,40 @@ def test_cpu_tensor_rejected():
     cfg, m = G.build_model(g)
     with pytest.raises(RuntimeError):
         m.get_coding(torch.zeros(4, 3))
+
+
+@pytest.mark.parametrize('name', ['nerf_grid_box', 'nerf_nearest', 'nerf_tria', 'nerf_sinc', 'nerf_SL', 'sdf', 'image', 'image_bilinear', 'image_set'])
+def test_fast_path_matches_generic(name):
+    """The specialised grid x grid kernels (field_fast.cu) against the descriptor-driven generic kernels, same inputs."""
+    import ctypes as C
+    from ffb200 import native as nv
+    from tests import gpu_helpers as G
+    g = H.golden('field_' + name)
+    cfg, m = G.build_model(g)
+    plan = m._plan('coding')
+    lib = nv.lib()
+    assert lib.ffb_field_fast_eligible(plan.handle) == 1, name
+    rng = np.random.RandomState(7)
+    lo, hi = g['fact.aabb'][0], g['fact.aabb'][1]
+    N = 50001
+    x = (lo - 0.02 * (hi - lo) + rng.rand(N, lo.size) * 1.04 * (hi - lo)).astype(np.float32)
+    x[:4] = g['x'][:4]
+    if name == 'image':
+        x = np.floor(x) + 0.5
+    xd = G.t(x)
+    W = plan.width
+    out = {k: torch.empty(N, W, device='cuda') for k in ('fg', 'cg', 'ff', 'cf')}
+    nv.check(lib.ffb_field_generic_fwd(plan.handle, nv.ptr(xd), C.c_int64(N), None, nv.ptr(out['fg']), nv.ptr(out['cg']), None, nv.stream()))
+    nv.check(lib.ffb_field_fast_fwd(plan.handle, nv.ptr(xd), C.c_int64(N), None, nv.ptr(out['ff']), nv.ptr(out['cf']), nv.stream()))
+    assert H.rel_err(G.npy(out['ff']), G.npy(out['fg'])) < 2e-6
+    assert H.rel_err(G.npy(out['cf']), G.npy(out['cg'])) < 2e-6
+    gf = torch.randn(N, W, device='cuda')
+    gc = torch.randn(N, W, device='cuda')
+    res = []
+    for fn in (lib.ffb_field_generic_bwd, lib.ffb_field_fast_bwd):
+        grads = [torch.zeros_like(t) for t in plan.tensors]
+        arr = (C.c_void_p * nv.MAX_OPS)(*[gr.data_ptr() for gr in grads])
+        nv.check(fn(plan.handle, nv.ptr(xd), C.c_int64(N), None, nv.ptr(gf), nv.ptr(gc), arr, nv.stream()))
+        res.append(grads)
+    for a, b in zip(*res):
+        assert H.rel_err(G.npy(b), G.npy(a)) < 5e-5
