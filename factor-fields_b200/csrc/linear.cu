@@ -380,7 +380,7 @@ int ffb_linear_bwd_weight_act(const float* gy, const float* y, int32_t act, cons
   wgrad_kernel<<<grid, 256, 0, s>>>(gy, y, act, x, gW, n, n_dev, K, M, rows);
   FFB_LAUNCHED();
   if (gb) {
-    int64_t rpb = 2048;
+    int64_t rpb = 256;
     bgrad_kernel<<<blocks_for(n, (int)rpb), 256, 0, s>>>(gy, y, act, gb, n, n_dev, M, rpb);
     FFB_LAUNCHED();
   }
