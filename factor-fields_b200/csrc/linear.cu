@@ -331,11 +331,20 @@ __global__ void render_input_bwd_kernel(const float* __restrict__ feat, int ld_f
 using namespace ffb;
 
 extern "C" {
+int ffb_linear_tc_eligible(int32_t K, int32_t N);
+int ffb_linear_tc_wgrad_eligible(int32_t K, int32_t M);
+int ffb_linear_tc_fwd(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
+                      int32_t act, void* stream);
+int ffb_linear_tc_bwd_input(const float* gy, const float* y, const float* W, float* gx, int64_t n, const int32_t* n_dev, int32_t K,
+                            int32_t M, int32_t act, void* stream);
+int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const float* x, float* gW, float* gb, int64_t n,
+                             const int32_t* n_dev, int32_t K, int32_t M, void* stream);
 
 int ffb_linear_fwd(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K,
                    int32_t M, int32_t act, void* stream) {
   FFB_REQUIRE(x && W && y && K > 0 && M > 0, "bad argument");
   if (n <= 0) return FFB_OK;
+  if (n >= 1024 && ffb_linear_tc_eligible(K, M)) return ffb_linear_tc_fwd(x, W, b, y, n, n_dev, K, M, act, stream);
   cudaStream_t s = (cudaStream_t)stream;
   if (M <= 8 && (size_t)(8 * K + 256 * 33) * sizeof(float) <= 96 * 1024) {
     const size_t smem = (size_t)(8 * K + 256 * 33) * sizeof(float);
@@ -357,6 +366,7 @@ int ffb_linear_bwd_input(float* gy, const float* y, const float* W, float* gx, i
                          int32_t M, int32_t act, void* stream) {
   FFB_REQUIRE(gy && W && K > 0 && M > 0 && (act == 0 || y), "bad argument");
   if (n <= 0 || !gx) return FFB_OK;
+  if (n >= 1024 && ffb_linear_tc_eligible(M, K)) return ffb_linear_tc_bwd_input(gy, y, W, gx, n, n_dev, K, M, act, stream);
   cudaStream_t s = (cudaStream_t)stream;
   // gx[n,K] = (gy .* mask)[n,M] * W[M,K] : inner = M, B(kin=m, col=k) = W[m*K + k]
   dim3 grid(blocks_for(n, BM), (K + BN - 1) / BN);
@@ -370,6 +380,7 @@ int ffb_linear_bwd_weight_act(const float* gy, const float* y, int32_t act, cons
                               const int32_t* n_dev, int32_t K, int32_t M, void* stream) {
   FFB_REQUIRE(gy && x && gW && K > 0 && M > 0 && (act == 0 || y), "bad argument");
   if (n <= 0) return FFB_OK;
+  if (n >= 1024 && ffb_linear_tc_wgrad_eligible(K, M)) return ffb_linear_tc_bwd_weight(gy, y, act, x, gW, gb, n, n_dev, K, M, stream);
   cudaStream_t s = (cudaStream_t)stream;
   const int tiles = ((M + BM - 1) / BM) * ((K + BN - 1) / BN);
   int64_t chunks = (4LL * sm_count() + tiles - 1) / tiles;

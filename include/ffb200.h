@@ -143,6 +143,21 @@ int ffb_linear_bwd_weight_act(const float* gy, const float* y, int32_t act, cons
 int ffb_linear_bwd_weight(const float* gy, const float* x, float* gW, float* gb, int64_t n,
                           const int32_t* n_dev, int32_t K, int32_t M, void* stream);
 
+/* Tensor-core (tcgen05.mma, bf16 hi+lo split x3, fp32 accumulation in TMEM) variants of the three layer kernels.
+ * ffb_linear_fwd / _bwd_input / _bwd_weight_act dispatch to them when the shape is eligible and n >= 1024;
+ * ffb_set_tensor_cores(0) forces the exact-fp32 SIMT kernels. */
+int ffb_set_tensor_cores(int enabled);
+int ffb_tensor_cores_enabled(void);
+int ffb_linear_tc_eligible(int32_t K, int32_t N);
+int ffb_linear_tc_wgrad_eligible(int32_t K, int32_t M);
+int ffb_linear_tc_fwd(const float* x, const float* W, const float* b, float* y, int64_t n,
+                      const int32_t* n_dev, int32_t K, int32_t M, int32_t act, void* stream);
+int ffb_linear_tc_bwd_input(const float* gy, const float* y, const float* W, float* gx, int64_t n,
+                            const int32_t* n_dev, int32_t K, int32_t M, int32_t act, void* stream);
+int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const float* x, float* gW,
+                             float* gb, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
+                             void* stream);
+
 /* positional_encoding (:74-79) appended to the input: out [n, D + 2*D*pe] = [x, sin, cos]. */
 int ffb_pe_concat_fwd(const float* x, float* out, int64_t n, const int32_t* n_dev, int32_t D,
                       int32_t pe, void* stream);
