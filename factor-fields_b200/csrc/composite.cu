@@ -238,7 +238,7 @@ int ffb_composite_app_fill(const float* weight, float weight_thres, const int32_
 int ffb_composite_accum(const ffb_composite_desc* h_desc, const float* weight, const float* z, const float* rgb,
                         const int32_t* offsets, const int32_t* app_offsets, int64_t R, float* rgb_map, float* pre_clamp, float* acc,
                         float* depth, void* stream) {
-  FFB_REQUIRE(h_desc && weight && rgb && offsets && app_offsets && rgb_map, "null argument");
+  FFB_REQUIRE(h_desc && weight && offsets && app_offsets && rgb_map, "null argument");   // rgb may be NULL when no sample is shaded
   if (R <= 0) return FFB_OK;
   composite_accum_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, weight, z, rgb, offsets, app_offsets, R,
                                                                                               rgb_map, pre_clamp, acc, depth);
@@ -250,9 +250,8 @@ int ffb_composite_bwd(const ffb_composite_desc* h_desc, const float* g_rgb_map, 
                       int32_t ld_feat, const float* dist, const float* sigma, const float* trans, const float* weight,
                       const float* rgb, const int32_t* offsets, const int32_t* app_offsets, int64_t R, float* g_rgb, float* g_feat0,
                       int32_t ld_g, void* stream) {
-  FFB_REQUIRE(h_desc && g_rgb_map && pre_clamp && feat0 && dist && sigma && trans && weight && rgb && offsets && app_offsets && g_rgb &&
-                  g_feat0,
-              "null argument");
+  FFB_REQUIRE(h_desc && g_rgb_map && pre_clamp && feat0 && dist && sigma && trans && weight && offsets && app_offsets && g_feat0,
+              "null argument");   // rgb / g_rgb may be NULL when no sample is shaded
   if (R <= 0) return FFB_OK;
   composite_bwd_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(
       *h_desc, g_rgb_map, pre_clamp, feat0, ld_feat, dist, sigma, trans, weight, rgb, offsets, app_offsets, R, g_rgb, g_feat0, ld_g);

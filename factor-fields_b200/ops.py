@@ -414,7 +414,7 @@ class RenderComposite(torch.autograd.Function):
             rgb = _empty((0, 3), feat)
         rgb_map, pre_clamp = _empty((R, 3), feat), _empty((R, 3), feat)
         acc, depth = _empty((R,), feat), _empty((R,), feat)
-        nv.check(lib.ffb_composite_accum(C.byref(cdesc), nv.ptr(weight), nv.ptr(samp['z']), nv.ptr(rgb), nv.i32p(offsets),
+        nv.check(lib.ffb_composite_accum(C.byref(cdesc), nv.ptr(weight), nv.ptr(samp['z']), nv.ptr(rgb, allow_none=True) if Na > 0 else None, nv.i32p(offsets),
                                          nv.i32p(app_offsets), C.c_int64(R), nv.ptr(rgb_map), nv.ptr(pre_clamp), nv.ptr(acc),
                                          nv.ptr(depth), nv.stream()))
         ctx.cdesc, ctx.samp, ctx.has_bias, ctx.kinds = cdesc, samp, has_bias, kinds
@@ -443,8 +443,9 @@ class RenderComposite(torch.autograd.Function):
         if Nv > 0:
             with nv.section('composite_bwd'):
                 nv.check(lib.ffb_composite_bwd(C.byref(cdesc), nv.ptr(g_rgb_map), nv.ptr(pre_clamp), nv.ptr(feat), ld,
-                                               nv.ptr(samp['dist']), nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight), nv.ptr(rgb),
-                                               nv.i32p(samp['offsets']), nv.i32p(app_offsets), C.c_int64(R), nv.ptr(g_rgb),
+                                               nv.ptr(samp['dist']), nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight),
+                                               nv.ptr(rgb) if Na > 0 else None,
+                                               nv.i32p(samp['offsets']), nv.i32p(app_offsets), C.c_int64(R), nv.ptr(g_rgb) if Na > 0 else None,
                                                nv.ptr(g_feat), ld, nv.stream()))
         layers = _split_params(params, ctx.has_bias)
         needs = ctx.needs_input_grad[6:]
