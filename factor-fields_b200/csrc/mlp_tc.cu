@@ -104,29 +104,52 @@ __device__ __forceinline__ float tc_act_mask(float y, int act) {
   return 1.0f;
 }
 
+// fp32 -> TERMS bf16 parts (x = p0 + p1 (+ p2) + O(2^-9*TERMS x)), 8 values -> one 16-byte chunk per part
+template <int TERMS>
+__device__ __forceinline__ void splitN(const float x[8], uint4 out[TERMS]) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = x[i];
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16 a = __float2bfloat16_rn(r[2 * i]), b = __float2bfloat16_rn(r[2 * i + 1]);
+      r[2 * i] -= __bfloat162float(a);
+      r[2 * i + 1] -= __bfloat162float(b);
+      __nv_bfloat162 ab = __halves2bfloat162(a, b);
+      w[i] = *reinterpret_cast<uint32_t*>(&ab);
+    }
+    out[t] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // C[n, N] = act_out( (A .* mask(Y))[n, K] * B^T + bias ),   B(j, k) = Bp[j*sbj + k*sbk]   (j < N, k < K)
-// Persistent CTAs; the weight operand is staged once per CTA, 128-row tiles of A per iteration.
+// Persistent CTAs; the weight operand is staged once per CTA (TERMS bf16 parts), A is streamed per 128-row
+// tile in K chunks of KC.  TERMS = 3 (6 MMAs per product, ~fp32 accuracy) for the forward pass, whose output
+// feeds exp() in the compositor; TERMS = 2 (3 MMAs) for gradients.
 // ---------------------------------------------------------------------------------------------------------
+template <int TERMS>
 __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ Y, int act_in,
                                                            const float* __restrict__ Bp, int64_t sbj, int64_t sbk,
                                                            const float* __restrict__ bias, int act_out, float* __restrict__ C,
                                                            int64_t n, const int32_t* __restrict__ n_dev, int K, int N, int Kp, int Np,
-                                                           int tmem_cols) {
+                                                           int KC, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
   n = resolve_n(n, n_dev);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sboK = (uint32_t)(Kp / 8) * 128u;            // bytes between 8-row groups
-  uint8_t* sBhi = smem;
-  uint8_t* sBlo = sBhi + (size_t)Np * Kp * 2;
-  uint8_t* sAhi = sBlo + (size_t)Np * Kp * 2;
-  uint8_t* sAlo = sAhi + (size_t)128 * Kp * 2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sAlo + (size_t)128 * Kp * 2);
+  const uint32_t sboB = (uint32_t)(Kp / 8) * 128u;            // bytes between 8-row groups of the weight operand
+  const uint32_t sboA = (uint32_t)(KC / 8) * 128u;            // ... of one A chunk
+  const size_t szB = (size_t)Np * Kp * 2, szA = (size_t)128 * KC * 2;
+  uint8_t* sB = smem;                                         // [TERMS][Np x Kp]
+  uint8_t* sA = sB + TERMS * szB;                             // [TERMS][128 x KC]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sA + TERMS * szA);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) mbar_init(bar, 1);
-  // stage the weight operand (hi / lo), K-major
   const int kchunks = Kp / 8;
   for (int item = tid; item < Np * kchunks; item += 128) {
     const int j = item % Np, c = item / Np;
@@ -136,11 +159,11 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
       const int k = c * 8 + i;
       x[i] = (j < N && k < K) ? __ldg(Bp + (int64_t)j * sbj + (int64_t)k * sbk) : 0.0f;
     }
-    uint4 hi, lo;
-    split8(x, hi, lo);
-    const uint32_t off = (uint32_t)(j / 8) * sboK + (uint32_t)c * 128u + (uint32_t)(j % 8) * 16u;
-    *reinterpret_cast<uint4*>(sBhi + off) = hi;
-    *reinterpret_cast<uint4*>(sBlo + off) = lo;
+    uint4 parts[TERMS];
+    splitN<TERMS>(x, parts);
+    const uint32_t off = (uint32_t)(j / 8) * sboB + (uint32_t)c * 128u + (uint32_t)(j % 8) * 16u;
+#pragma unroll
+    for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint4*>(sB + t * szB + off) = parts[t];
   }
   tc_fence_before();
   __syncthreads();
@@ -151,44 +174,52 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
   uint32_t phase = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * 128;
-    // ---- stage A tile (hi / lo): item = (row r, 8-wide k chunk c); consecutive threads -> consecutive rows
-    for (int item = tid; item < 128 * kchunks; item += 128) {
-      const int r = item & 127, c = item >> 7;
-      const int64_t row = row0 + r;
-      float x[8];
+    for (int k0 = 0; k0 < Kp; k0 += KC) {
+      const int kc = min(KC, Kp - k0);                        // multiple of 16
+      // ---- stage the A chunk: item = (row r, 8-wide k chunk c); consecutive threads -> consecutive rows
+      for (int item = tid; item < 128 * (kc / 8); item += 128) {
+        const int r = item & 127, c = item >> 7;
+        const int64_t row = row0 + r;
+        float x[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = c * 8 + i;
-        float v = 0.0f;
-        if (row < n && k < K) {
-          v = A[row * K + k];
-          if (Y) v *= tc_act_mask(Y[row * K + k], act_in);
+        for (int i = 0; i < 8; ++i) {
+          const int k = k0 + c * 8 + i;
+          float v = 0.0f;
+          if (row < n && k < K) {
+            v = A[row * K + k];
+            if (Y) v *= tc_act_mask(Y[row * K + k], act_in);
+          }
+          x[i] = v;
         }
-        x[i] = v;
+        uint4 parts[TERMS];
+        splitN<TERMS>(x, parts);
+        const uint32_t off = (uint32_t)(r / 8) * sboA + (uint32_t)c * 128u + (uint32_t)(r % 8) * 16u;
+#pragma unroll
+        for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint4*>(sA + t * szA + off) = parts[t];
       }
-      uint4 hi, lo;
-      split8(x, hi, lo);
-      const uint32_t off = (uint32_t)(r / 8) * sboK + (uint32_t)c * 128u + (uint32_t)(r % 8) * 16u;
-      *reinterpret_cast<uint4*>(sAhi + off) = hi;
-      *reinterpret_cast<uint4*>(sAlo + off) = lo;
-    }
-    proxy_fence();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t aH = smem_u32(sAhi), aL = smem_u32(sAlo), bH = smem_u32(sBhi), bL = smem_u32(sBlo);
-      for (int ks = 0; ks < Kp / 16; ++ks) {
-        const uint32_t o = (uint32_t)ks * 256u;    // two 8-wide k chunks per K=16 slice
-        const uint64_t dAh = make_desc(aH + o, 128, sboK), dAl = make_desc(aL + o, 128, sboK);
-        const uint64_t dBh = make_desc(bH + o, 128, sboK), dBl = make_desc(bL + o, 128, sboK);
-        umma_f16(tmem_d, dAh, dBh, idesc, ks > 0);
-        umma_f16(tmem_d, dAl, dBh, idesc, 1);
-        umma_f16(tmem_d, dAh, dBl, idesc, 1);
+      proxy_fence();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
+        for (int ks = 0; ks < kc / 16; ++ks) {
+          const uint32_t oa = (uint32_t)ks * 256u, ob = (uint32_t)(k0 / 16 + ks) * 256u;   // two 8-wide k chunks per K=16 slice
+          bool first = (k0 == 0 && ks == 0);
+#pragma unroll
+          for (int ta = 0; ta < TERMS; ++ta)
+#pragma unroll
+            for (int tb = 0; tb < TERMS; ++tb) {
+              if (ta + tb >= TERMS) continue;                 // drop the terms below the fp32 rounding level
+              umma_f16(tmem_d, make_desc(aBase + ta * (uint32_t)szA + oa, 128, sboA), make_desc(bBase + tb * (uint32_t)szB + ob, 128, sboB),
+                       idesc, first ? 0u : 1u);
+              first = false;
+            }
+        }
+        umma_commit(bar);     // implies tcgen05.fence::before_thread_sync
       }
-      umma_commit(bar);     // implies tcgen05.fence::before_thread_sync
+      mbar_wait(bar, phase);  // the chunk buffer may be overwritten only after the MMAs have read it
+      phase ^= 1;
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
     tc_fence_after();
     // ---- epilogue: thread <-> row (TMEM lane), 16 columns at a time
     const int64_t row = row0 + warp * 32 + lane;
@@ -216,7 +247,7 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
       }
     }
     tc_fence_before();
-    __syncthreads();        // all TMEM reads + smem reads (MMA done) complete before the next tile overwrites them
+    __syncthreads();        // all TMEM reads complete before the next tile's first MMA overwrites the accumulator
   }
   if (warp == 0) tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
 }
@@ -365,21 +396,34 @@ int ffb_set_tensor_cores(int enabled) {
 }
 int ffb_tensor_cores_enabled(void) { return g_tc_enabled; }
 
-// returns 1 if the (K, N) layer shape fits the tcgen05 forward / input-gradient kernel
-int ffb_linear_tc_eligible(int32_t K, int32_t N) {
-  if (!g_tc_enabled || K < 1 || N < 1) return 0;
+static bool tc_gemm_plan(int K, int N, int terms, int* Kp_, int* Np_, int* KC_, size_t* smem_) {
   const int Kp = (K + 15) / 16 * 16, Np = (N + 15) / 16 * 16;
-  if (Np > 256) return 0;
-  const size_t smem = (size_t)(Np + 128) * Kp * 4 + 64;
-  return smem <= (size_t)max_smem_optin() ? 1 : 0;
+  if (Np > 256) return false;
+  for (int KC = 64; KC >= 16; KC >>= 1) {
+    const int kc = KC < Kp ? KC : Kp;
+    const size_t smem = (size_t)terms * ((size_t)Np * Kp * 2 + (size_t)128 * kc * 2) + 64;
+    if (smem <= (size_t)max_smem_optin()) {
+      *Kp_ = Kp; *Np_ = Np; *KC_ = kc; *smem_ = smem;
+      return true;
+    }
+  }
+  return false;
 }
 
-static int tc_gemm_launch(const float* A, const float* Y, int act_in, const float* Bp, int64_t sbj, int64_t sbk, const float* bias,
-                          int act_out, float* C, int64_t n, const int32_t* n_dev, int K, int N, cudaStream_t s) {
-  const int Kp = (K + 15) / 16 * 16, Np = (N + 15) / 16 * 16;
-  const size_t smem = (size_t)(Np + 128) * Kp * 4 + 64;
+// returns 1 if the (K, N) layer shape fits the tcgen05 forward (3-term) and input-gradient (2-term) kernels
+int ffb_linear_tc_eligible(int32_t K, int32_t N) {
+  if (!g_tc_enabled || K < 1 || N < 1) return 0;
+  int Kp, Np, KC;
+  size_t smem;
+  return tc_gemm_plan(K, N, 3, &Kp, &Np, &KC, &smem) ? 1 : 0;
+}
+
+static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in, const float* Bp, int64_t sbj, int64_t sbk,
+                          const float* bias, int act_out, float* C, int64_t n, const int32_t* n_dev, int K, int N, cudaStream_t s) {
+  int Kp, Np, KC;
+  size_t smem;
+  FFB_REQUIRE(tc_gemm_plan(K, N, terms, &Kp, &Np, &KC, &smem), "layer does not fit in shared memory");
   const int cols = pow2_cols(Np);
-  FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
   int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
   if (per_sm > 512 / cols) per_sm = 512 / cols;
   if (per_sm > 8) per_sm = 8;
@@ -387,7 +431,13 @@ static int tc_gemm_launch(const float* A, const float* Y, int act_in, const floa
   const int64_t tiles = (n + 127) / 128;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > tiles) grid = tiles;
-  tc_gemm_rows_kernel<<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, cols);
+  if (terms == 3) {
+    FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+    tc_gemm_rows_kernel<3><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, cols);
+  } else {
+    FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+    tc_gemm_rows_kernel<2><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, cols);
+  }
   FFB_LAUNCHED();
   return FFB_OK;
 }
@@ -397,7 +447,7 @@ int ffb_linear_tc_fwd(const float* x, const float* W, const float* b, float* y, 
   FFB_REQUIRE(x && W && y, "null argument");
   FFB_REQUIRE(ffb_linear_tc_eligible(K, M), "layer shape not eligible for the tensor-core path");
   if (n <= 0) return FFB_OK;
-  return tc_gemm_launch(x, nullptr, 0, W, K, 1, b, act, y, n, n_dev, K, M, (cudaStream_t)stream);
+  return tc_gemm_launch(3, x, nullptr, 0, W, K, 1, b, act, y, n, n_dev, K, M, (cudaStream_t)stream);
 }
 
 int ffb_linear_tc_bwd_input(const float* gy, const float* y, const float* W, float* gx, int64_t n, const int32_t* n_dev, int32_t K,
@@ -406,7 +456,7 @@ int ffb_linear_tc_bwd_input(const float* gy, const float* y, const float* W, flo
   FFB_REQUIRE(ffb_linear_tc_eligible(M, K), "layer shape not eligible for the tensor-core path");
   if (n <= 0) return FFB_OK;
   // gx[n, K] = (gy .* mask)[n, M] * W[M, K]:  inner dim = M, B(j = k_in, k = m) = W[m*K + j]
-  return tc_gemm_launch(gy, act ? y : nullptr, act, W, 1, K, nullptr, 0, gx, n, n_dev, M, K, (cudaStream_t)stream);
+  return tc_gemm_launch(2, gy, act ? y : nullptr, act, W, 1, K, nullptr, 0, gx, n, n_dev, M, K, (cudaStream_t)stream);
 }
 
 int ffb_linear_tc_wgrad_eligible(int32_t K, int32_t M) {

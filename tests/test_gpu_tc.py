@@ -36,7 +36,7 @@ def test_tc_layers(K, M, act):
     z = x.double() @ W.double().T + b.double()
     ref = z if act == 0 else torch.relu(z) if act == 1 else torch.sigmoid(z)
     err = float((y_tc.double() - ref).abs().max() / ref.abs().max())
-    assert err < 3e-5, ('fwd', K, M, act, err)
+    assert err < 3e-6, ('fwd', K, M, act, err)      # 3-term split: fp32-class accuracy
     # ---- input gradient: gx = (gy .* act'(y)) W
     gy = torch.randn(n, M, device='cuda')
     y = ref.float()
