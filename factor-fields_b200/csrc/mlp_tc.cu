@@ -125,27 +125,56 @@ __device__ __forceinline__ void splitN(const float x[8], uint4 out[TERMS]) {
   }
 }
 
+// Stage a [128 rows x nchunks*8 cols] fp32 block as TERMS bf16 operand copies.  Warp-cooperative: a warp owns an
+// 8-row group at a time; lane = (rr = lane>>2 : row in the group, q = lane&3 : column pair 2q,2q+1 of an 8-wide
+// chunk), so one load instruction touches 8 fully-used 32-byte sectors and one store instruction writes 128
+// contiguous bytes (bank-conflict free).  Element (r, k) lands at
+//     (r/8)*stride_g + (k/8)*stride_c + (r%8)*16 + (k%8)*2        (see the layout table at the top of the file)
+template <int TERMS, class Load>
+__device__ __forceinline__ void stage_block(uint8_t* dst, uint32_t part_bytes, uint32_t stride_g, uint32_t stride_c, int nchunks,
+                                            int warp, int lane, Load load) {
+  const int rr = lane >> 2, q = lane & 3;
+  for (int g = warp; g < 16; g += 4) {
+    const int r = g * 8 + rr;
+    uint8_t* base = dst + (uint32_t)g * stride_g + (uint32_t)rr * 16u + (uint32_t)q * 4u;
+#pragma unroll 4
+    for (int c = 0; c < nchunks; ++c) {
+      float2 v = load(r, c * 8 + 2 * q);
+#pragma unroll
+      for (int t = 0; t < TERMS; ++t) {
+        const __nv_bfloat16 a = __float2bfloat16_rn(v.x), b = __float2bfloat16_rn(v.y);
+        v.x -= __bfloat162float(a);
+        v.y -= __bfloat162float(b);
+        __nv_bfloat162 ab = __halves2bfloat162(a, b);
+        *reinterpret_cast<uint32_t*>(base + (uint32_t)t * part_bytes + (uint32_t)c * stride_c) = *reinterpret_cast<uint32_t*>(&ab);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // C[n, N] = act_out( (A .* mask(Y))[n, K] * B^T + bias ),   B(j, k) = Bp[j*sbj + k*sbk]   (j < N, k < K)
 // Persistent CTAs; the weight operand is staged once per CTA (TERMS bf16 parts), A is streamed per 128-row
 // tile in K chunks of KC.  TERMS = 3 (6 MMAs per product, ~fp32 accuracy) for the forward pass, whose output
-// feeds exp() in the compositor; TERMS = 2 (3 MMAs) for gradients.
+// feeds exp() in the compositor; TERMS = 2 (3 MMAs) for gradients.  The output tile goes TMEM -> registers ->
+// shared memory -> coalesced 16-byte global stores.
 // ---------------------------------------------------------------------------------------------------------
 template <int TERMS>
 __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ Y, int act_in,
                                                            const float* __restrict__ Bp, int64_t sbj, int64_t sbk,
                                                            const float* __restrict__ bias, int act_out, float* __restrict__ C,
                                                            int64_t n, const int32_t* __restrict__ n_dev, int K, int N, int Kp, int Np,
-                                                           int KC, int tmem_cols) {
+                                                           int KC, int CB, uint32_t szU, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
   n = resolve_n(n, n_dev);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sboB = (uint32_t)(Kp / 8) * 128u;            // bytes between 8-row groups of the weight operand
   const uint32_t sboA = (uint32_t)(KC / 8) * 128u;            // ... of one A chunk
-  const size_t szB = (size_t)Np * Kp * 2, szA = (size_t)128 * KC * 2;
+  const uint32_t szB = (uint32_t)Np * Kp * 2, szA = (uint32_t)128 * KC * 2;
   uint8_t* sB = smem;                                         // [TERMS][Np x Kp]
-  uint8_t* sA = sB + TERMS * szB;                             // [TERMS][128 x KC]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sA + TERMS * szA);
+  uint8_t* sA = sB + TERMS * szB;                             // [TERMS][128 x KC], re-used as the fp32 output staging tile
+  float* sE = reinterpret_cast<float*>(sA);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sA + szU);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
@@ -171,32 +200,37 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
   const uint32_t tmem_d = *tmem_slot;
   const uint32_t idesc = make_idesc(Np, 0, 0);
   const int64_t n_tiles = (n + 127) / 128;
+  const bool vec2 = ((K & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 7) == 0) && (!Y || (reinterpret_cast<uintptr_t>(Y) & 7) == 0);
+  const int pitchE = CB + 4;
   uint32_t phase = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * 128;
     for (int k0 = 0; k0 < Kp; k0 += KC) {
       const int kc = min(KC, Kp - k0);                        // multiple of 16
-      // ---- stage the A chunk: item = (row r, 8-wide k chunk c); consecutive threads -> consecutive rows
-      for (int item = tid; item < 128 * (kc / 8); item += 128) {
-        const int r = item & 127, c = item >> 7;
+      stage_block<TERMS>(sA, szA, sboA, 128u, kc / 8, warp, lane, [&](int r, int k) {
         const int64_t row = row0 + r;
-        float x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = k0 + c * 8 + i;
-          float v = 0.0f;
-          if (row < n && k < K) {
-            v = A[row * K + k];
-            if (Y) v *= tc_act_mask(Y[row * K + k], act_in);
+        const int kk = k0 + k;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (row < n && kk < K) {
+          const float* p = A + row * K + kk;
+          if (vec2) {
+            v = *reinterpret_cast<const float2*>(p);
+            if (Y) {
+              const float2 yy = *reinterpret_cast<const float2*>(Y + row * K + kk);
+              v.x *= tc_act_mask(yy.x, act_in);
+              v.y *= tc_act_mask(yy.y, act_in);
+            }
+          } else {
+            v.x = p[0];
+            if (kk + 1 < K) v.y = p[1];
+            if (Y) {
+              v.x *= tc_act_mask(Y[row * K + kk], act_in);
+              if (kk + 1 < K) v.y *= tc_act_mask(Y[row * K + kk + 1], act_in);
+            }
           }
-          x[i] = v;
         }
-        uint4 parts[TERMS];
-        splitN<TERMS>(x, parts);
-        const uint32_t off = (uint32_t)(r / 8) * sboA + (uint32_t)c * 128u + (uint32_t)(r % 8) * 16u;
-#pragma unroll
-        for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint4*>(sA + t * szA + off) = parts[t];
-      }
+        return v;
+      });
       proxy_fence();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncthreads();
       if (tid == 0) {
@@ -210,8 +244,8 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
 #pragma unroll
             for (int tb = 0; tb < TERMS; ++tb) {
               if (ta + tb >= TERMS) continue;                 // drop the terms below the fp32 rounding level
-              umma_f16(tmem_d, make_desc(aBase + ta * (uint32_t)szA + oa, 128, sboA), make_desc(bBase + tb * (uint32_t)szB + ob, 128, sboB),
-                       idesc, first ? 0u : 1u);
+              umma_f16(tmem_d, make_desc(aBase + ta * szA + oa, 128, sboA), make_desc(bBase + tb * szB + ob, 128, sboB), idesc,
+                       first ? 0u : 1u);
               first = false;
             }
         }
@@ -221,33 +255,45 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
       phase ^= 1;
     }
     tc_fence_after();
-    // ---- epilogue: thread <-> row (TMEM lane), 16 columns at a time
-    const int64_t row = row0 + warp * 32 + lane;
+    // ---- epilogue: thread <-> row (TMEM lane); CB columns at a time through shared memory
+    const int rloc = warp * 32 + lane;
     const uint32_t tbase = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < Np; c0 += 16) {
-      float v[16];
-      tmem_ld16(tbase + (uint32_t)c0, v);
-      if (row < n) {
+    for (int cb0 = 0; cb0 < Np; cb0 += CB) {
+      for (int c0 = 0; c0 < CB; c0 += 16) {
+        float v[16];
+        tmem_ld16(tbase + (uint32_t)(cb0 + c0), v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int c = c0 + i;
-          if (c < N) {
-            float o = v[i];
-            if (bias) o += __ldg(bias + c);
-            v[i] = tc_act_fwd(o, act_out);
+          const int c = cb0 + c0 + i;
+          float o = v[i];
+          if (bias && c < N) o += __ldg(bias + c);
+          v[i] = tc_act_fwd(o, act_out);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(sE + rloc * pitchE + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      __syncthreads();
+      const int cb = min(CB, N - cb0);                        // valid columns in this block (may be <= 0 for padding)
+      if (cb > 0) {
+        if ((N & 3) == 0) {
+          const int q4 = cb / 4;
+          for (int idx = tid; idx < 128 * q4; idx += 128) {
+            const int r = idx / q4, c4 = idx % q4;
+            if (row0 + r < n)
+              *reinterpret_cast<float4*>(C + (row0 + r) * N + cb0 + c4 * 4) = *reinterpret_cast<const float4*>(sE + r * pitchE + c4 * 4);
+          }
+        } else {
+          for (int idx = tid; idx < 128 * cb; idx += 128) {
+            const int r = idx / cb, c = idx % cb;
+            if (row0 + r < n) C[(row0 + r) * N + cb0 + c] = sE[r * pitchE + c];
           }
         }
-        float* dst = C + row * N + c0;
-        if ((N & 3) == 0 && c0 + 16 <= N) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-          for (int i = 0; i < 16 && c0 + i < N; ++i) dst[i] = v[i];
-        }
       }
+      __syncthreads();        // sE (= the A chunk buffer) is free again
     }
     tc_fence_before();
-    __syncthreads();        // all TMEM reads complete before the next tile's first MMA overwrites the accumulator
+    __syncthreads();          // all TMEM reads complete before the next tile's first MMA overwrites the accumulator
   }
   if (warp == 0) tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
 }
@@ -255,6 +301,7 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------------------
 // gW[M, K] += (gy .* mask(y))^T x ;  gb[M] += column sums (through an extra all-ones column of x).
 // D[128 (m, zero padded) x Np] accumulates in TMEM over all row tiles of this CTA; one atomic update at the end.
+// Both operands are MN-major (the reduction index = the sample row is the MMA K dimension).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ y, int act,
                                                        const float* __restrict__ x, float* __restrict__ gW, float* __restrict__ gb,
@@ -263,19 +310,16 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
   n = resolve_n(n, n_dev);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t SBO = 16 * 128;                          // bytes between 8-wide MN chunks: 128 rows = 16 k-groups of 128 B
-  uint8_t* sGhi = smem;                                       // [128 m][128 r] MN-major
-  uint8_t* sGlo = sGhi + 128 * 256;
-  uint8_t* sXhi = sGlo + 128 * 256;                           // [Np k][128 r]
-  uint8_t* sXlo = sXhi + (size_t)Np * 256;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sXlo + (size_t)Np * 256);
+  constexpr uint32_t szG = 128 * 256;
+  const uint32_t szX = (uint32_t)Np * 256;
+  uint8_t* sG = smem;                                         // [2][128 m x 128 r]
+  uint8_t* sX = sG + 2 * szG;                                 // [2][Np k x 128 r]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sX + 2 * szX);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) mbar_init(bar, 1);
   // rows m >= M of the G operand stay zero for the whole kernel
-  for (int i = tid; i < 128 * 256 / 16; i += 128) {
-    reinterpret_cast<uint4*>(sGhi)[i] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4*>(sGlo)[i] = make_uint4(0, 0, 0, 0);
-  }
+  for (int i = tid; i < (int)(2 * szG / 16); i += 128) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -283,56 +327,60 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
   const uint32_t idesc = make_idesc(Np, 1, 1);
   const int64_t n_tiles = (n + 127) / 128;
   const int mchunks = (M + 7) / 8, xchunks = Np / 8;
+  const bool vecG = ((M & 1) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 7) == 0) && (!act || (reinterpret_cast<uintptr_t>(y) & 7) == 0);
+  const bool vecX = ((K & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   uint32_t phase = 0;
   bool any = false;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * 128;
-    for (int item = tid; item < 128 * mchunks; item += 128) {
-      const int r = item & 127, mc = item >> 7;
+    // element (row r, column m) -> (m/8)*SBO + (r/8)*128 + (r%8)*16 ... : here the *column* index is the MN index,
+    // so stage_block is called with (stride_g = 128 for the row group, stride_c = SBO for the 8-wide column chunk)
+    // and lanes split as (rr = row in group, q = column pair)  ->  offset rr*16 + q*4 is (k%8)*16 + (mn%8)*2.
+    stage_block<2>(sG, szG, 128u, SBO, mchunks, warp, lane, [&](int r, int m) {
       const int64_t row = row0 + r;
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = mc * 8 + i;
-        float g = 0.0f;
-        if (row < n && m < M) {
-          g = gy[row * M + m];
-          if (act) g *= tc_act_mask(y[row * M + m], act);
+      float2 v = make_float2(0.0f, 0.0f);
+      if (row < n && m < M) {
+        const float* p = gy + row * M + m;
+        if (vecG) {
+          v = *reinterpret_cast<const float2*>(p);
+          if (act) {
+            const float2 yy = *reinterpret_cast<const float2*>(y + row * M + m);
+            v.x *= tc_act_mask(yy.x, act);
+            v.y *= tc_act_mask(yy.y, act);
+          }
+        } else {
+          v.x = p[0];
+          if (act) v.x *= tc_act_mask(y[row * M + m], act);
+          if (m + 1 < M) {
+            v.y = p[1];
+            if (act) v.y *= tc_act_mask(y[row * M + m + 1], act);
+          }
         }
-        v[i] = g;
       }
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      const uint32_t off = (uint32_t)mc * SBO + (uint32_t)(r / 8) * 128u + (uint32_t)(r % 8) * 16u;
-      *reinterpret_cast<uint4*>(sGhi + off) = hi;
-      *reinterpret_cast<uint4*>(sGlo + off) = lo;
-    }
-    for (int item = tid; item < 128 * xchunks; item += 128) {
-      const int r = item & 127, kc = item >> 7;
+      return v;
+    });
+    stage_block<2>(sX, szX, 128u, SBO, xchunks, warp, lane, [&](int r, int k) {
       const int64_t row = row0 + r;
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = kc * 8 + i;
-        float xv = 0.0f;
-        if (row < n) xv = (k < K) ? x[row * K + k] : (k == K ? 1.0f : 0.0f);
-        v[i] = xv;
+      float2 v = make_float2(0.0f, 0.0f);
+      if (row < n) {
+        if (vecX && k + 1 < K) {
+          v = *reinterpret_cast<const float2*>(x + row * K + k);
+        } else {
+          v.x = k < K ? x[row * K + k] : (k == K ? 1.0f : 0.0f);
+          v.y = k + 1 < K ? x[row * K + k + 1] : (k + 1 == K ? 1.0f : 0.0f);
+        }
       }
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      const uint32_t off = (uint32_t)kc * SBO + (uint32_t)(r / 8) * 128u + (uint32_t)(r % 8) * 16u;
-      *reinterpret_cast<uint4*>(sXhi + off) = hi;
-      *reinterpret_cast<uint4*>(sXlo + off) = lo;
-    }
+      return v;
+    });
     proxy_fence();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t gH = smem_u32(sGhi), gL = smem_u32(sGlo), xH = smem_u32(sXhi), xL = smem_u32(sXlo);
+      const uint32_t gB = smem_u32(sG), xB = smem_u32(sX);
       for (int ks = 0; ks < 8; ++ks) {                        // 128 rows = 8 slices of K = 16
         const uint32_t o = (uint32_t)ks * 256u;
-        const uint64_t dGh = make_desc(gH + o, 128, SBO), dGl = make_desc(gL + o, 128, SBO);
-        const uint64_t dXh = make_desc(xH + o, 128, SBO), dXl = make_desc(xL + o, 128, SBO);
+        const uint64_t dGh = make_desc(gB + o, 128, SBO), dGl = make_desc(gB + szG + o, 128, SBO);
+        const uint64_t dXh = make_desc(xB + o, 128, SBO), dXl = make_desc(xB + szX + o, 128, SBO);
         umma_f16(tmem_d, dGh, dXh, idesc, (any || ks > 0) ? 1u : 0u);
         umma_f16(tmem_d, dGl, dXh, idesc, 1);
         umma_f16(tmem_d, dGh, dXl, idesc, 1);
@@ -396,14 +444,18 @@ int ffb_set_tensor_cores(int enabled) {
 }
 int ffb_tensor_cores_enabled(void) { return g_tc_enabled; }
 
-static bool tc_gemm_plan(int K, int N, int terms, int* Kp_, int* Np_, int* KC_, size_t* smem_) {
+static bool tc_gemm_plan(int K, int N, int terms, int* Kp_, int* Np_, int* KC_, int* CB_, uint32_t* szU_, size_t* smem_) {
   const int Kp = (K + 15) / 16 * 16, Np = (N + 15) / 16 * 16;
   if (Np > 256) return false;
+  const int CB = Np < 64 ? Np : (Np % 64 == 0 ? 64 : 16);    // output column block staged through shared memory
+  const size_t szE = (size_t)128 * (CB + 4) * 4;
   for (int KC = 64; KC >= 16; KC >>= 1) {
     const int kc = KC < Kp ? KC : Kp;
-    const size_t smem = (size_t)terms * ((size_t)Np * Kp * 2 + (size_t)128 * kc * 2) + 64;
+    size_t szU = (size_t)terms * 128 * kc * 2;
+    if (szU < szE) szU = szE;
+    const size_t smem = (size_t)terms * Np * Kp * 2 + szU + 64;
     if (smem <= (size_t)max_smem_optin()) {
-      *Kp_ = Kp; *Np_ = Np; *KC_ = kc; *smem_ = smem;
+      *Kp_ = Kp; *Np_ = Np; *KC_ = kc; *CB_ = CB; *szU_ = (uint32_t)szU; *smem_ = smem;
       return true;
     }
   }
@@ -413,16 +465,18 @@ static bool tc_gemm_plan(int K, int N, int terms, int* Kp_, int* Np_, int* KC_, 
 // returns 1 if the (K, N) layer shape fits the tcgen05 forward (3-term) and input-gradient (2-term) kernels
 int ffb_linear_tc_eligible(int32_t K, int32_t N) {
   if (!g_tc_enabled || K < 1 || N < 1) return 0;
-  int Kp, Np, KC;
+  int Kp, Np, KC, CB;
+  uint32_t szU;
   size_t smem;
-  return tc_gemm_plan(K, N, 3, &Kp, &Np, &KC, &smem) ? 1 : 0;
+  return tc_gemm_plan(K, N, 3, &Kp, &Np, &KC, &CB, &szU, &smem) ? 1 : 0;
 }
 
 static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in, const float* Bp, int64_t sbj, int64_t sbk,
                           const float* bias, int act_out, float* C, int64_t n, const int32_t* n_dev, int K, int N, cudaStream_t s) {
-  int Kp, Np, KC;
+  int Kp, Np, KC, CB;
+  uint32_t szU;
   size_t smem;
-  FFB_REQUIRE(tc_gemm_plan(K, N, terms, &Kp, &Np, &KC, &smem), "layer does not fit in shared memory");
+  FFB_REQUIRE(tc_gemm_plan(K, N, terms, &Kp, &Np, &KC, &CB, &szU, &smem), "layer does not fit in shared memory");
   const int cols = pow2_cols(Np);
   int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
   if (per_sm > 512 / cols) per_sm = 512 / cols;
@@ -433,10 +487,10 @@ static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in,
   if (grid > tiles) grid = tiles;
   if (terms == 3) {
     FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
-    tc_gemm_rows_kernel<3><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, cols);
+    tc_gemm_rows_kernel<3><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
   } else {
     FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
-    tc_gemm_rows_kernel<2><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, cols);
+    tc_gemm_rows_kernel<2><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
   }
   FFB_LAUNCHED();
   return FFB_OK;
