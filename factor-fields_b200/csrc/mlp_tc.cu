@@ -233,7 +233,9 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
       });
       proxy_fence();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {        // whole warp enters; lane 0 issues, the others wait at __syncwarp (not inside try_wait, which
+                              // would suspend the warp and delay the issuing lane)
+        if (lane == 0) {
         tc_fence_after();
         const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
         for (int ks = 0; ks < kc / 16; ++ks) {
@@ -250,6 +252,8 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
             }
         }
         umma_commit(bar);     // implies tcgen05.fence::before_thread_sync
+        }
+        __syncwarp();
       }
       mbar_wait(bar, phase);  // the chunk buffer may be overwritten only after the MMAs have read it
       phase ^= 1;
@@ -374,7 +378,8 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
     });
     proxy_fence();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+      if (lane == 0) {
       tc_fence_after();
       const uint32_t gB = smem_u32(sG), xB = smem_u32(sX);
       for (int ks = 0; ks < 8; ++ks) {                        // 128 rows = 8 slices of K = 16
@@ -386,6 +391,8 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
         umma_f16(tmem_d, dGh, dXl, idesc, 1);
       }
       umma_commit(bar);
+      }
+      __syncwarp();
     }
     any = true;
     mbar_wait(bar, phase);      // operands may be overwritten only after the MMAs have read them
@@ -485,11 +492,15 @@ static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in,
   const int64_t tiles = (n + 127) / 128;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > tiles) grid = tiles;
-  if (terms == 3) {
+  static bool attr_done = false;
+  if (!attr_done) {
     FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+    FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+    attr_done = true;
+  }
+  if (terms == 3) {
     tc_gemm_rows_kernel<3><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
   } else {
-    FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
     tc_gemm_rows_kernel<2><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
   }
   FFB_LAUNCHED();
@@ -529,7 +540,11 @@ int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const
   const int Np = (K + 1 + 15) / 16 * 16;
   const size_t smem = (size_t)2 * 128 * 256 + (size_t)2 * Np * 256 + 64;
   const int cols = pow2_cols(Np);
-  FFB_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+  static bool wattr_done = false;
+  if (!wattr_done) {
+    FFB_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+    wattr_done = true;
+  }
   int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
   if (per_sm > 512 / cols) per_sm = 512 / cols;
   if (per_sm > 4) per_sm = 4;
