@@ -132,21 +132,28 @@ __device__ __forceinline__ void splitN(const float x[8], uint4 out[TERMS]) {
 //     (r/8)*stride_g + (k/8)*stride_c + (r%8)*16 + (k%8)*2        (see the layout table at the top of the file)
 template <int TERMS, class Load>
 __device__ __forceinline__ void stage_block(uint8_t* dst, uint32_t part_bytes, uint32_t stride_g, uint32_t stride_c, int nchunks,
-                                            int warp, int lane, Load load) {
+                                            int warp, int nwarps, int lane, Load load) {
   const int rr = lane >> 2, q = lane & 3;
-  for (int g = warp; g < 16; g += 4) {
+  constexpr int BATCH = 8;     // independent loads in flight per lane
+  for (int g = warp; g < 16; g += nwarps) {
     const int r = g * 8 + rr;
     uint8_t* base = dst + (uint32_t)g * stride_g + (uint32_t)rr * 16u + (uint32_t)q * 4u;
-#pragma unroll 4
-    for (int c = 0; c < nchunks; ++c) {
-      float2 v = load(r, c * 8 + 2 * q);
+    for (int cb = 0; cb < nchunks; cb += BATCH) {
+      float2 v[BATCH];
 #pragma unroll
-      for (int t = 0; t < TERMS; ++t) {
-        const __nv_bfloat16 a = __float2bfloat16_rn(v.x), b = __float2bfloat16_rn(v.y);
-        v.x -= __bfloat162float(a);
-        v.y -= __bfloat162float(b);
-        __nv_bfloat162 ab = __halves2bfloat162(a, b);
-        *reinterpret_cast<uint32_t*>(base + (uint32_t)t * part_bytes + (uint32_t)c * stride_c) = *reinterpret_cast<uint32_t*>(&ab);
+      for (int i = 0; i < BATCH; ++i) v[i] = (cb + i < nchunks) ? load(r, (cb + i) * 8 + 2 * q) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        if (cb + i < nchunks) {
+#pragma unroll
+          for (int t = 0; t < TERMS; ++t) {
+            const __nv_bfloat16 a = __float2bfloat16_rn(v[i].x), b = __float2bfloat16_rn(v[i].y);
+            v[i].x -= __bfloat162float(a);
+            v[i].y -= __bfloat162float(b);
+            __nv_bfloat162 ab = __halves2bfloat162(a, b);
+            *reinterpret_cast<uint32_t*>(base + (uint32_t)t * part_bytes + (uint32_t)(cb + i) * stride_c) = *reinterpret_cast<uint32_t*>(&ab);
+          }
+        }
       }
     }
   }
@@ -160,14 +167,14 @@ __device__ __forceinline__ void stage_block(uint8_t* dst, uint32_t part_bytes, u
 // shared memory -> coalesced 16-byte global stores.
 // ---------------------------------------------------------------------------------------------------------
 template <int TERMS>
-__global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ Y, int act_in,
+__global__ void __launch_bounds__(512) tc_gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ Y, int act_in,
                                                            const float* __restrict__ Bp, int64_t sbj, int64_t sbk,
                                                            const float* __restrict__ bias, int act_out, float* __restrict__ C,
                                                            int64_t n, const int32_t* __restrict__ n_dev, int K, int N, int Kp, int Np,
                                                            int KC, int CB, uint32_t szU, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
   n = resolve_n(n, n_dev);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NT = blockDim.x, nwarps = NT >> 5;
   const uint32_t sboB = (uint32_t)(Kp / 8) * 128u;            // bytes between 8-row groups of the weight operand
   const uint32_t sboA = (uint32_t)(KC / 8) * 128u;            // ... of one A chunk
   const uint32_t szB = (uint32_t)Np * Kp * 2, szA = (uint32_t)128 * KC * 2;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) mbar_init(bar, 1);
   const int kchunks = Kp / 8;
-  for (int item = tid; item < Np * kchunks; item += 128) {
+  for (int item = tid; item < Np * kchunks; item += NT) {
     const int j = item % Np, c = item / Np;
     float x[8];
 #pragma unroll
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
     const int64_t row0 = tile * 128;
     for (int k0 = 0; k0 < Kp; k0 += KC) {
       const int kc = min(KC, Kp - k0);                        // multiple of 16
-      stage_block<TERMS>(sA, szA, sboA, 128u, kc / 8, warp, lane, [&](int r, int k) {
+      stage_block<TERMS>(sA, szA, sboA, 128u, kc / 8, warp, nwarps, lane, [&](int r, int k) {
         const int64_t row = row0 + r;
         const int kk = k0 + k;
         float2 v = make_float2(0.0f, 0.0f);
@@ -259,11 +266,13 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
       phase ^= 1;
     }
     tc_fence_after();
-    // ---- epilogue: thread <-> row (TMEM lane); CB columns at a time through shared memory
-    const int rloc = warp * 32 + lane;
-    const uint32_t tbase = tmem_d + ((uint32_t)(warp * 32) << 16);
+    // ---- epilogue: thread <-> row (TMEM lane quarter = warp % 4); warps sharing a quarter split the columns;
+    //      CB columns at a time through shared memory, then coalesced 16-byte stores
+    const int rloc = (warp & 3) * 32 + lane, wsplit = warp >> 2, nsplit = nwarps >> 2;
+    const uint32_t tbase = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    const int cbshift = CB == 64 ? 4 : (CB == 32 ? 3 : 2);    // log2(CB / 4)
     for (int cb0 = 0; cb0 < Np; cb0 += CB) {
-      for (int c0 = 0; c0 < CB; c0 += 16) {
+      for (int c0 = wsplit * 16; c0 < CB; c0 += nsplit * 16) {
         float v[16];
         tmem_ld16(tbase + (uint32_t)(cb0 + c0), v);
 #pragma unroll
@@ -281,16 +290,15 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
       const int cb = min(CB, N - cb0);                        // valid columns in this block (may be <= 0 for padding)
       if (cb > 0) {
         if ((N & 3) == 0) {
-          const int q4 = cb / 4;
-          for (int idx = tid; idx < 128 * q4; idx += 128) {
-            const int r = idx / q4, c4 = idx % q4;
-            if (row0 + r < n)
+          for (int idx = tid; idx < (128 << cbshift); idx += NT) {
+            const int r = idx >> cbshift, c4 = idx & ((1 << cbshift) - 1);
+            if (c4 * 4 < cb && row0 + r < n)
               *reinterpret_cast<float4*>(C + (row0 + r) * N + cb0 + c4 * 4) = *reinterpret_cast<const float4*>(sE + r * pitchE + c4 * 4);
           }
         } else {
-          for (int idx = tid; idx < 128 * cb; idx += 128) {
-            const int r = idx / cb, c = idx % cb;
-            if (row0 + r < n) C[(row0 + r) * N + cb0 + c] = sE[r * pitchE + c];
+          for (int idx = tid; idx < 128 * CB; idx += NT) {
+            const int r = idx >> (cbshift + 2), c = idx & (CB - 1);
+            if (c < cb && row0 + r < n) C[(row0 + r) * N + cb0 + c] = sE[r * pitchE + c];
           }
         }
       }
@@ -307,12 +315,12 @@ __global__ void __launch_bounds__(128) tc_gemm_rows_kernel(const float* __restri
 // D[128 (m, zero padded) x Np] accumulates in TMEM over all row tiles of this CTA; one atomic update at the end.
 // Both operands are MN-major (the reduction index = the sample row is the MMA K dimension).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ y, int act,
+__global__ void __launch_bounds__(512) tc_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ y, int act,
                                                        const float* __restrict__ x, float* __restrict__ gW, float* __restrict__ gb,
                                                        int64_t n, const int32_t* __restrict__ n_dev, int K, int M, int Np, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
   n = resolve_n(n, n_dev);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NT = blockDim.x, nwarps = NT >> 5;
   constexpr uint32_t SBO = 16 * 128;                          // bytes between 8-wide MN chunks: 128 rows = 16 k-groups of 128 B
   constexpr uint32_t szG = 128 * 256;
   const uint32_t szX = (uint32_t)Np * 256;
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) mbar_init(bar, 1);
   // rows m >= M of the G operand stay zero for the whole kernel
-  for (int i = tid; i < (int)(2 * szG / 16); i += 128) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)(2 * szG / 16); i += NT) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
     // element (row r, column m) -> (m/8)*SBO + (r/8)*128 + (r%8)*16 ... : here the *column* index is the MN index,
     // so stage_block is called with (stride_g = 128 for the row group, stride_c = SBO for the 8-wide column chunk)
     // and lanes split as (rr = row in group, q = column pair)  ->  offset rr*16 + q*4 is (k%8)*16 + (mn%8)*2.
-    stage_block<2>(sG, szG, 128u, SBO, mchunks, warp, lane, [&](int r, int m) {
+    stage_block<2>(sG, szG, 128u, SBO, mchunks, warp, nwarps, lane, [&](int r, int m) {
       const int64_t row = row0 + r;
       float2 v = make_float2(0.0f, 0.0f);
       if (row < n && m < M) {
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
       }
       return v;
     });
-    stage_block<2>(sX, szX, 128u, SBO, xchunks, warp, lane, [&](int r, int k) {
+    stage_block<2>(sX, szX, 128u, SBO, xchunks, warp, nwarps, lane, [&](int r, int k) {
       const int64_t row = row0 + r;
       float2 v = make_float2(0.0f, 0.0f);
       if (row < n) {
@@ -400,9 +408,9 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const float* __restrict__
   }
   tc_fence_after();
   if (any) {
-    const int m = warp * 32 + lane;
-    const uint32_t tbase = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < Np; c0 += 16) {
+    const int m = (warp & 3) * 32 + lane;
+    const uint32_t tbase = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = (warp >> 2) * 16; c0 < Np; c0 += (nwarps >> 2) * 16) {
       float v[16];
       tmem_ld16(tbase + (uint32_t)c0, v);
       if (m < M) {
@@ -454,7 +462,7 @@ int ffb_tensor_cores_enabled(void) { return g_tc_enabled; }
 static bool tc_gemm_plan(int K, int N, int terms, int* Kp_, int* Np_, int* KC_, int* CB_, uint32_t* szU_, size_t* smem_) {
   const int Kp = (K + 15) / 16 * 16, Np = (N + 15) / 16 * 16;
   if (Np > 256) return false;
-  const int CB = Np < 64 ? Np : (Np % 64 == 0 ? 64 : 16);    // output column block staged through shared memory
+  const int CB = (Np % 64 == 0) ? 64 : ((Np % 32 == 0) ? 32 : 16);    // output column block staged through shared memory
   const size_t szE = (size_t)128 * (CB + 4) * 4;
   for (int KC = 64; KC >= 16; KC >>= 1) {
     const int kc = KC < Kp ? KC : Kp;
@@ -489,6 +497,8 @@ static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in,
   if (per_sm > 512 / cols) per_sm = 512 / cols;
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
+  const int NT = per_sm >= 4 ? 256 : 512;
+  if (per_sm * NT > 2048) per_sm = 2048 / NT;
   const int64_t tiles = (n + 127) / 128;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > tiles) grid = tiles;
@@ -499,9 +509,9 @@ static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in,
     attr_done = true;
   }
   if (terms == 3) {
-    tc_gemm_rows_kernel<3><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
+    tc_gemm_rows_kernel<3><<<(unsigned)grid, NT, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
   } else {
-    tc_gemm_rows_kernel<2><<<(unsigned)grid, 128, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
+    tc_gemm_rows_kernel<2><<<(unsigned)grid, NT, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
   }
   FFB_LAUNCHED();
   return FFB_OK;
@@ -549,10 +559,11 @@ int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const
   if (per_sm > 512 / cols) per_sm = 512 / cols;
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
+  const int NT = per_sm >= 4 ? 256 : 512;
   const int64_t tiles = (n + 127) / 128;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > tiles) grid = tiles;
-  tc_wgrad_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(gy, y, act, x, gW, gb, n, n_dev, K, M, Np, cols);
+  tc_wgrad_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(gy, y, act, x, gW, gb, n, n_dev, K, M, Np, cols);
   FFB_LAUNCHED();
   return FFB_OK;
 }
