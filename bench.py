@@ -167,6 +167,7 @@ def run_ours(args):
     sys.stdout = real_stdout
     sd = {k: torch.from_numpy(v) for k, v in W.make_state(0).items()}
     model.load_state_dict(sd)
+    model.lazy_counts = not args.exact_counts   # no host round trips for the data-dependent sample counts
     assert model.nSamples == 440 and float(model.stepSize) == float(W.step_size())
     B, S = W.BATCH, W.N_SAMPLES
 
@@ -239,7 +240,7 @@ def run_ours(args):
         step_resident()
     clocks = ClockSampler(local) if rank == 0 else None
     ms_total, launches = timed(step_resident, args.steps)
-    n_valid, n_app = model.last_stats['n_valid'], model.last_stats['n_app']
+    n_valid, n_app = int(model.last_stats['n_valid']), int(model.last_stats['n_app'])
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
@@ -282,6 +283,7 @@ def run_ours(args):
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'rays_per_gpu_per_step': B, 'samples_per_ray': S, 'valid_fraction': round(n_valid / (B * S), 4),
                        'shaded_fraction_of_valid': round(n_app / max(n_valid, 1), 4), 'field_queries_per_step_per_gpu': n_valid,
+                       'host_syncs_per_step': 2 if args.exact_counts else 0,
                        'parallelism': f'ray-sharded dp{world}, one NCCL all-reduce of the flat fp32 gradient bucket per step' if world > 1 else 'single GPU',
                        'l2': 'per-step inputs+intermediates (~0.5 GB) exceed the 126 MB L2; no explicit flush; the 21 MB of parameters stay '
                              'L2-resident across steps as in training'},
@@ -303,6 +305,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exact-counts', action='store_true', help='read the sample counts back every step (the reference-like sync mode)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'ours' and args.gpus > 1 and world == 1:

@@ -137,7 +137,7 @@ class MLPMixer(torch.nn.Module):
                 params.append(lin.bias)
         return params, tuple(has_bias)
 
-    def forward(self, x, is_train=False):
+    def forward(self, x, is_train=False, n_dev=None):
         lead = x.shape[:-1]
         h = x.reshape(-1, x.shape[-1])
         params, has_bias = self._flat()
@@ -147,9 +147,9 @@ class MLPMixer(torch.nn.Module):
                 h = torch.cat([h, positional_encoding(h, self.pe)], dim=-1)
             keep = (torch.rand_like(h) >= 0.1).to(h.dtype)
             h = h * keep * (1.0 / 0.9)
-            out = ops.MLPFunction.apply(h, 0, has_bias, *params)
+            out = ops.MLPFunction.apply(h, 0, has_bias, n_dev, *params)
         else:
-            out = ops.MLPFunction.apply(h, self.pe, has_bias, *params)
+            out = ops.MLPFunction.apply(h, self.pe, has_bias, n_dev, *params)
         return out.reshape(*lead, out.shape[-1])
 
 
@@ -428,7 +428,7 @@ class FactorFields(torch.nn.Module):
         if self._coeff_is_mlp():
             return self.coeffs[self.scene_idx](self.normalize_coord(xyz_sampled))
         plan = self._plan('coeff')
-        return ops.FieldQuery.apply(plan, xyz_sampled, *plan.tensors)[1]
+        return ops.FieldQuery.apply(plan, xyz_sampled, None, *plan.tensors)[1]
 
     def get_basis(self, x):
         """FactorFields.py:467-516"""
@@ -439,7 +439,7 @@ class FactorFields(torch.nn.Module):
             xyz = grid_mapping(x, self.freq_bands, self.aabb[:, :self.in_dim], self.cfg.model.basis_mapping).reshape(-1, self.in_dim, F)
             return torch.cat([self.basises[i](xyz[..., i].reshape(-1, self.in_dim)) for i in range(F)], dim=-1)
         plan = self._plan('basis')
-        return ops.FieldQuery.apply(plan, x, *plan.tensors)[0]
+        return ops.FieldQuery.apply(plan, x, None, *plan.tensors)[0]
 
     @torch.no_grad()
     def normalize_basis(self):
@@ -447,8 +447,9 @@ class FactorFields(torch.nn.Module):
         for basis in self.basises:
             basis.data = _channels_last(basis.data / torch.norm(basis.data, dim=(2, 3), keepdim=True))
 
-    def get_coding(self, x):
-        """FactorFields.py:523-533 — one fused kernel when both factors are tensors."""
+    def get_coding(self, x, n_dev=None):
+        """FactorFields.py:523-533 — one fused kernel when both factors are tensors.  n_dev: optional device-side row
+        count (x is then a capacity-sized buffer; used by forward() in lazy mode)."""
         has_c, has_b = self.cfg.model.coeff_type != 'none', self.cfg.model.basis_type != 'none'
         if (has_c and self._coeff_is_mlp()) or (has_b and self._basis_is_mlp()):
             if has_c and has_b:
@@ -457,7 +458,7 @@ class FactorFields(torch.nn.Module):
             only = self.get_coeff(x) if has_c else self.get_basis(x)
             return only, only
         plan = self._plan('coding')
-        feats, coeff = ops.FieldQuery.apply(plan, x, *plan.tensors)
+        feats, coeff = ops.FieldQuery.apply(plan, x, n_dev, *plan.tensors)
         if has_c and has_b:
             return feats, coeff
         return feats, feats
@@ -716,7 +717,8 @@ class FactorFields(torch.nn.Module):
         N_samples = N_samples if N_samples > 0 else self.nSamples
         rays = rays_chunk[:, :6].contiguous().float()
         jitter = self._jitter(rays.shape[0], is_train)
-        samp = ops.sample_compact(self._sampler_desc(N_samples, self.alphaMask is not None), rays, jitter)
+        lazy = bool(getattr(self, 'lazy_counts', False)) and not (self._coeff_is_mlp() or self._basis_is_mlp())
+        samp = ops.sample_compact(self._sampler_desc(N_samples, self.alphaMask is not None), rays, jitter, lazy=lazy)
         self.last_stats = {'n_valid': samp['n_valid'], 'n_candidates': rays.shape[0] * N_samples}
 
         if not (white_bg or (is_train and torch.rand((1,)) < 0.5)):
@@ -724,15 +726,15 @@ class FactorFields(torch.nn.Module):
         else:
             white_bg = True
         width = sum(self.cfg.model.basis_dims)
-        if samp['n_valid'] > 0:
-            feats, coeffs = self.get_coding(samp['xyz'])
-            feat = self.linear_mat(feats, is_train=is_train)
+        if lazy or samp['n_valid'] > 0:
+            feats, coeffs = self.get_coding(samp['xyz'], samp['n_dev'])
+            feat = self.linear_mat(feats, is_train=is_train, n_dev=samp['n_dev'])
         else:
             coeffs = torch.zeros((1, width), device=rays.device)
             feat = torch.zeros((0, self.cfg.model.out_dim), device=rays.device)
         params, has_bias = self.renderModule._flat()
-        rgb_map, depth_map, acc, weight, app_idx = ops.RenderComposite.apply(
+        rgb_map, depth_map, acc, weight, app_idx, n_app = ops.RenderComposite.apply(
             feat, samp, self._cdesc(white_bg), self.renderModule.viewpe, self.renderModule.feape, has_bias, *params)
-        self.last_stats['n_app'] = int(app_idx.shape[0])
+        self.last_stats['n_app'] = n_app if lazy else int(n_app)
         self.last_aux = dict(samp=samp, weight=weight, app_idx=app_idx, acc=acc)
         return rgb_map, depth_map, coeffs

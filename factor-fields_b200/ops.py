@@ -114,7 +114,8 @@ class FieldQuery(torch.autograd.Function):
     factor tensors (the reference never needs d/dx)."""
 
     @staticmethod
-    def forward(ctx, plan, x, *tensors):
+    def forward(ctx, plan, x, n_dev, *tensors):
+        """n_dev: None, or a 1-element int32 CUDA tensor holding the live row count (x is then a capacity-sized buffer)."""
         _dev_check(x)
         x = x.contiguous().float()
         n = x.shape[0]
@@ -122,9 +123,9 @@ class FieldQuery(torch.autograd.Function):
         coeff = _empty((n, plan.width), x)
         if n > 0:
             with nv.section('field_fwd'):
-                nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(feats), nv.ptr(coeff),
+                nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(n_dev), nv.ptr(feats), nv.ptr(coeff),
                                                       nv.stream()))
-        ctx.plan = plan
+        ctx.plan, ctx.n_dev = plan, n_dev
         ctx.save_for_backward(x)
         return feats, coeff
 
@@ -137,7 +138,7 @@ class FieldQuery(torch.autograd.Function):
         grads = []
         arr = (C.c_void_p * nv.MAX_OPS)()
         for i, t in enumerate(plan.tensors):
-            if ctx.needs_input_grad[2 + i]:
+            if ctx.needs_input_grad[3 + i]:
                 g = torch.zeros_like(t)  # preserve_format keeps the channels-last strides
                 grads.append(g)
                 arr[i] = g.data_ptr()
@@ -148,9 +149,9 @@ class FieldQuery(torch.autograd.Function):
             gf = g_feats.contiguous() if g_feats is not None else None
             gc = g_coeff.contiguous() if g_coeff is not None else None
             with nv.section('field_bwd'):
-                nv.check(nv.lib().ffb_field_query_bwd(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(gf, allow_none=True),
-                                                      nv.ptr(gc, allow_none=True), arr, nv.stream()))
-        return (None, None, *grads)
+                nv.check(nv.lib().ffb_field_query_bwd(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(ctx.n_dev),
+                                                      nv.ptr(gf, allow_none=True), nv.ptr(gc, allow_none=True), arr, nv.stream()))
+        return (None, None, None, *grads)
 
 
 def grid_mapping(positions, freq_bands, aabb, basis_mapping='sawtooth'):
@@ -173,17 +174,17 @@ def grid_mapping(positions, freq_bands, aabb, basis_mapping='sawtooth'):
 # --------------------------------------------------------------------------------------------------
 # MLPs
 # --------------------------------------------------------------------------------------------------
-def _linear_fwd(x, W, b, act):
+def _linear_fwd(x, W, b, act, n_dev=None):
     n, K = x.shape
     M = W.shape[0]
     y = _empty((n, M), x)
     if n > 0:
-        nv.check(nv.lib().ffb_linear_fwd(nv.ptr(x), nv.ptr(W), nv.ptr(b, allow_none=True), nv.ptr(y), C.c_int64(n), None, K, M, act,
-                                         nv.stream()))
+        nv.check(nv.lib().ffb_linear_fwd(nv.ptr(x), nv.ptr(W), nv.ptr(b, allow_none=True), nv.ptr(y), C.c_int64(n), nv.i32p(n_dev), K, M,
+                                         act, nv.stream()))
     return y
 
 
-def _mlp_backward(acts, layers, acts_kind, g_out, need_input_grad, param_needs):
+def _mlp_backward(acts, layers, acts_kind, g_out, need_input_grad, param_needs, n_dev=None):
     """acts[l] = input of layer l, acts[l+1] = its (activated) output.  -> (g_input | None, [gW, gb, ...])"""
     lib = nv.lib()
     g = g_out.contiguous()
@@ -198,13 +199,13 @@ def _mlp_backward(acts, layers, acts_kind, g_out, need_input_grad, param_needs):
         gb = torch.zeros_like(b) if (b is not None and param_needs[l][1]) else None
         if n > 0 and gW is not None:
             nv.check(lib.ffb_linear_bwd_weight_act(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), act, nv.ptr(acts[l]), nv.ptr(gW),
-                                                   nv.ptr(gb, allow_none=True), C.c_int64(n), None, K, M, nv.stream()))
+                                                   nv.ptr(gb, allow_none=True), C.c_int64(n), nv.i32p(n_dev), K, M, nv.stream()))
         grads[l] = (gW, gb)
         if l > 0 or need_input_grad:
             gx = _empty((n, K), g)
             if n > 0:
-                nv.check(lib.ffb_linear_bwd_input(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), nv.ptr(W), nv.ptr(gx), C.c_int64(n), None,
-                                                  K, M, act, nv.stream()))
+                nv.check(lib.ffb_linear_bwd_input(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), nv.ptr(W), nv.ptr(gx), C.c_int64(n),
+                                                  nv.i32p(n_dev), K, M, act, nv.stream()))
             g = gx
         else:
             g = None
@@ -225,23 +226,24 @@ class MLPFunction(torch.autograd.Function):
     """MLPMixer.forward (FactorFields.py:144-159): optional PE concat, Linear+ReLU ..., bias-free last layer."""
 
     @staticmethod
-    def forward(ctx, x, pe, has_bias, *params):
+    def forward(ctx, x, pe, has_bias, n_dev, *params):
         _dev_check(x)
         x = x.contiguous().float()
         layers = _split_params(params, has_bias)
         n, D = x.shape
         h = x
+        ctx.n_dev = n_dev
         if pe > 0:
             h = _empty((n, D + 2 * D * pe), x)
             if n > 0:
-                nv.check(nv.lib().ffb_pe_concat_fwd(nv.ptr(x), nv.ptr(h), C.c_int64(n), None, D, pe, nv.stream()))
+                nv.check(nv.lib().ffb_pe_concat_fwd(nv.ptr(x), nv.ptr(h), C.c_int64(n), nv.i32p(n_dev), D, pe, nv.stream()))
         acts = [h]
         kinds = []
         with nv.section('mlp_fwd'):
             for l, (W, b) in enumerate(layers):
                 act = 1 if l != len(layers) - 1 else 0
                 kinds.append(act)
-                h = _linear_fwd(h, W, b, act)
+                h = _linear_fwd(h, W, b, act, n_dev)
                 acts.append(h)
         ctx.pe, ctx.has_bias, ctx.kinds = pe, has_bias, kinds
         ctx.save_for_backward(x, *acts, *params)
@@ -255,20 +257,21 @@ class MLPFunction(torch.autograd.Function):
         acts = list(saved[1:1 + ctx.n_acts])
         params = saved[1 + ctx.n_acts:]
         layers = _split_params(params, ctx.has_bias)
-        needs = ctx.needs_input_grad[3:]
+        needs = ctx.needs_input_grad[4:]
         pn, i = [], 0
         for hb in ctx.has_bias:
             pn.append((needs[i], needs[i + 1] if hb else False))
             i += 2 if hb else 1
         with nv.section('mlp_bwd'):
-            gin, grads = _mlp_backward(acts, layers, ctx.kinds, g, ctx.needs_input_grad[0], pn)
+            gin, grads = _mlp_backward(acts, layers, ctx.kinds, g, ctx.needs_input_grad[0], pn, ctx.n_dev)
         gx = None
         if ctx.needs_input_grad[0]:
             if ctx.pe > 0:
                 n, D = x.shape
                 gx = _empty((n, D), x)
                 if n > 0:
-                    nv.check(nv.lib().ffb_pe_concat_bwd(nv.ptr(x), nv.ptr(gin), nv.ptr(gx), C.c_int64(n), None, D, ctx.pe, nv.stream()))
+                    nv.check(nv.lib().ffb_pe_concat_bwd(nv.ptr(x), nv.ptr(gin), nv.ptr(gx), C.c_int64(n), nv.i32p(ctx.n_dev), D, ctx.pe,
+                                                        nv.stream()))
             else:
                 gx = gin
         flat = []
@@ -276,7 +279,7 @@ class MLPFunction(torch.autograd.Function):
             flat.append(gW)
             if hb:
                 flat.append(gb)
-        return (gx, None, None, *flat)
+        return (gx, None, None, None, *flat)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -310,8 +313,10 @@ def exclusive_scan(counts):
 
 
 @torch.no_grad()
-def sample_compact(desc, rays, jitter):
-    """-> dict(xyz [Nv,3], ray_id, sample_id, z, dist, offsets [R+1], n_valid int).  One host read of Nv."""
+def sample_compact(desc, rays, jitter, lazy=False):
+    """-> dict(xyz [Nv,3], ray_id, sample_id, z, dist, offsets [R+1], n_valid, n_dev).
+    lazy=False: one host read of Nv, exact-size buffers (n_dev None).  lazy=True: no host round trip; buffers have the
+    capacity R*S and every consumer reads the live count from n_dev (= offsets[R], a device int32)."""
     _dev_check(rays)
     lib = nv.lib()
     rays = rays.contiguous().float()
@@ -323,7 +328,11 @@ def sample_compact(desc, rays, jitter):
     sec.__enter__()
     nv.check(lib.ffb_sample_count(C.byref(desc), nv.ptr(rays), jp, C.c_int64(R), nv.i32p(counts), nv.ptr(tmin), nv.stream()))
     offsets = exclusive_scan(counts)
-    nvld = int(offsets[R].item())
+    n_dev = None
+    if lazy:
+        nvld, n_dev = R * desc.n_samples, offsets[R:R + 1]
+    else:
+        nvld = int(offsets[R].item())
     xyz = _empty((nvld, 3), rays)
     ray_id = _empty((nvld,), rays, torch.int32)
     sample_id = _empty((nvld,), rays, torch.int32)
@@ -333,7 +342,8 @@ def sample_compact(desc, rays, jitter):
         nv.check(lib.ffb_sample_fill(C.byref(desc), nv.ptr(rays), jp, nv.ptr(tmin), nv.i32p(offsets), C.c_int64(R), C.c_int64(nvld),
                                      nv.ptr(xyz), nv.i32p(ray_id), nv.i32p(sample_id), nv.ptr(z), nv.ptr(dist), nv.stream()))
     sec.__exit__()
-    return dict(xyz=xyz, ray_id=ray_id, sample_id=sample_id, z=z, dist=dist, offsets=offsets, counts=counts, n_valid=nvld, rays=rays)
+    return dict(xyz=xyz, ray_id=ray_id, sample_id=sample_id, z=z, dist=dist, offsets=offsets, counts=counts,
+                n_valid=(offsets[R] if lazy else nvld), n_dev=n_dev, rays=rays)
 
 
 @torch.no_grad()
@@ -377,7 +387,7 @@ class RenderComposite(torch.autograd.Function):
             ctx.Na, ctx.empty, ctx.has_bias = 0, True, has_bias
             ctx.save_for_backward(feat, *params)
             outs = (torch.full((R, 3), bg, device=feat.device), torch.zeros(R, device=feat.device), torch.zeros(R, device=feat.device),
-                    _empty((0,), feat), _empty((0,), feat, torch.int32))
+                    _empty((0,), feat), _empty((0,), feat, torch.int32), torch.tensor(0))
             ctx.mark_non_differentiable(*outs[1:])
             return outs
         ctx.empty = False
@@ -388,7 +398,9 @@ class RenderComposite(torch.autograd.Function):
         nv.check(lib.ffb_composite_weights(C.byref(cdesc), nv.ptr(feat), ld, nv.ptr(samp['dist']), nv.i32p(offsets), C.c_int64(R),
                                            nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight), nv.i32p(app_counts), nv.stream()))
         app_offsets = exclusive_scan(app_counts)
-        Na = int(app_offsets[R].item())
+        lazy = samp.get('n_dev') is not None
+        a_dev = app_offsets[R:R + 1] if lazy else None
+        Na = Nv if lazy else int(app_offsets[R].item())     # lazy: capacity; the live count stays on the device
         app_idx = _empty((Na,), feat, torch.int32)
         sec.__exit__()
         layers = _split_params(params, has_bias)
@@ -400,14 +412,14 @@ class RenderComposite(torch.autograd.Function):
                                                 C.c_int64(R), nv.i32p(app_idx), nv.stream()))
             inp = _empty((Na, Win), feat)
             nv.check(lib.ffb_render_input_fwd(nv.ptr(feat), ld, nv.ptr(rays), nv.i32p(samp['ray_id']), nv.i32p(app_idx), nv.ptr(inp),
-                                              C.c_int64(Na), None, Cf, view_pe, fea_pe, nv.stream()))
+                                              C.c_int64(Na), nv.i32p(a_dev), Cf, view_pe, fea_pe, nv.stream()))
             h = inp
             acts.append(h)
             with nv.section('rgbmlp_fwd'):
                 for l, (W, b) in enumerate(layers):
                     act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
                     kinds.append(act)
-                    h = _linear_fwd(h, W, b, act)
+                    h = _linear_fwd(h, W, b, act, a_dev)
                     acts.append(h)
             rgb = h
         else:
@@ -418,11 +430,11 @@ class RenderComposite(torch.autograd.Function):
                                          nv.i32p(app_offsets), C.c_int64(R), nv.ptr(rgb_map), nv.ptr(pre_clamp), nv.ptr(acc),
                                          nv.ptr(depth), nv.stream()))
         ctx.cdesc, ctx.samp, ctx.has_bias, ctx.kinds = cdesc, samp, has_bias, kinds
-        ctx.view_pe, ctx.fea_pe, ctx.n_acts, ctx.Na = view_pe, fea_pe, len(acts), Na
+        ctx.view_pe, ctx.fea_pe, ctx.n_acts, ctx.Na, ctx.a_dev = view_pe, fea_pe, len(acts), Na, a_dev
         ctx.save_for_backward(feat, sigma, trans, weight, rgb, app_offsets, app_idx, pre_clamp, *acts, *params)
-        ctx.mark_non_differentiable(depth, acc, weight, app_idx)
-        ctx.aux = dict(n_app=Na)
-        return rgb_map, depth, acc, weight, app_idx
+        n_app = app_offsets[R] if lazy else torch.tensor(Na)
+        ctx.mark_non_differentiable(depth, acc, weight, app_idx, n_app)
+        return rgb_map, depth, acc, weight, app_idx, n_app
 
     @staticmethod
     def backward(ctx, g_rgb_map, *_unused):
@@ -456,10 +468,10 @@ class RenderComposite(torch.autograd.Function):
         flat = []
         if Na > 0:
             with nv.section('rgbmlp_bwd'):
-                g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn)
+                g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn, ctx.a_dev)
             Cf = ld - 1
-            nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(Na), None, Cf,
-                                              ctx.view_pe, ctx.fea_pe, nv.stream()))
+            nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(Na),
+                                              nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
             for (gW, gb), hb in zip(grads, ctx.has_bias):
                 flat.append(gW)
                 if hb:

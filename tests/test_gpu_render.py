@@ -151,3 +151,27 @@ def test_render_full_size_properties():
     miss = torch.tensor([[5., 5., 5., 0., 0., 1.]] * 7, device='cuda')
     rgb3, d3, c3 = m(miss, white_bg=True, is_train=False, N_samples=64)
     assert torch.allclose(rgb3, torch.ones_like(rgb3)) and m.last_aux['samp']['n_valid'] == 0
+
+
+def test_lazy_counts_match_exact():
+    """lazy_counts (device-side counts, capacity-sized buffers, no host sync) gives the same pixels and gradients as the
+    exact-size path."""
+    from tests import gpu_helpers as G
+    g = H.golden('render_train_alpha')
+    from ffb200.models.FactorFields import AlphaGridMask
+    res = []
+    for lazy in (False, True):
+        cfg, m = G.build_model(g)
+        m.alphaMask = AlphaGridMask('cuda', G.t(g['alpha_aabb']), G.t(g['alpha_volume']))
+        m._jitter = lambda n, tr: G.t(g['jitter'])
+        m.lazy_counts = lazy
+        rgb, depth, coeffs = m(G.t(g['rays']), white_bg=True, is_train=True, N_samples=int(g['N_samples']))
+        loss = torch.mean((rgb - G.t(g['target'])) ** 2)
+        params = [p for _, p in m.named_parameters()]
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        assert int(m.last_stats['n_valid']) == int(g['n_valid'])
+        res.append((rgb, depth, grads, int(m.last_stats['n_app'])))
+    assert torch.allclose(res[0][0], res[1][0], atol=1e-7) and torch.allclose(res[0][1], res[1][1], atol=1e-6)
+    assert res[0][3] == res[1][3]
+    for a, b in zip(res[0][2], res[1][2]):
+        assert H.rel_err(G.npy(b), G.npy(a)) < 5e-5
