@@ -10,6 +10,7 @@ namespace ffb {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 int sm_count();
+void keep_pool_cached();
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return FFB_OK;

@@ -23,6 +23,20 @@ int sm_count() {
   cached = n;
   return n;
 }
+// Stream-ordered allocations (generic field backward, grid_mapping) come from the device's default memory pool; keep
+// freed blocks cached across synchronisation points instead of returning them to the driver (default threshold 0),
+// otherwise every host sync makes the next cudaMallocAsync a multi-millisecond driver call.
+void keep_pool_cached() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
 }  // namespace ffb
 
 extern "C" {

@@ -387,6 +387,7 @@ int ffb_field_generic_bwd(ffb_field_t f, const float* x, int64_t n, const int32_
   cudaStream_t s = (cudaStream_t)stream;
   const int W = f->h.basis_width > 0 ? f->h.basis_width : f->h.coeff_width;
   float *c = nullptr, *b = nullptr;
+  keep_pool_cached();
   FFB_CUDA(cudaMallocAsync(&c, sizeof(float) * n * W, s));
   cudaError_t e = cudaMallocAsync(&b, sizeof(float) * n * W, s);
   if (e != cudaSuccess) {
@@ -413,6 +414,7 @@ int ffb_grid_mapping(const float* x, int64_t n, int32_t in_dim, const float* h_a
   float msize = h_aabb_max[0] - h_aabb_min[0];
   for (int k = 1; k < in_dim; ++k) msize = fmaxf(msize, h_aabb_max[k] - h_aabb_min[k]);
   float* dfreq = nullptr;
+  keep_pool_cached();
   FFB_CUDA(cudaMallocAsync(&dfreq, sizeof(float) * n_freq, s));
   FFB_CUDA(cudaMemcpyAsync(dfreq, h_freq, sizeof(float) * n_freq, cudaMemcpyHostToDevice, s));
   float3 lo = make_float3(h_aabb_min[0], in_dim > 1 ? h_aabb_min[1] : 0.f, in_dim > 2 ? h_aabb_min[2] : 0.f);

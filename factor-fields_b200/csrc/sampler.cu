@@ -9,6 +9,9 @@
 // indices compare bit-exactly.  All decision arithmetic is the unfused fp32 sequence of ffb_math.h.
 #include "ffb_common.cuh"
 #include "ffb_math.h"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace ffb {
 
@@ -202,6 +205,82 @@ __global__ void __launch_bounds__(SCAN_T) scan_tiles_kernel(const int32_t* __res
   if (base <= n - 1 && n - 1 < base + SCAN_PER) out[n] = run;
 }
 
+// Single-CTA exclusive scan for small inputs (n <= SCAN_SINGLE_MAX): 1024 threads, 4 elements per thread per round,
+// running carry between rounds.  No workspace, so it is safe inside CUDA-graph capture and on any stream.
+constexpr int64_t SCAN_SINGLE_MAX = 1 << 16;
+
+__global__ void __launch_bounds__(1024) scan_single_block_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  __shared__ int warp_sums[32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t base0 = 0; base0 < n; base0 += 4096) {
+    const int64_t base = base0 + threadIdx.x * 4;
+    int v[4];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = (base + j < n) ? in[base + j] : 0;
+      sum += v[j];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int ws = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += y;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    int run = carry + (wid ? warp_sums[wid - 1] : 0) + inc - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (base + j < n) out[base + j] = run;
+      run += v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+// Look-back state for the multi-tile scan: one cached device buffer per stream (grown on demand, never freed), so the
+// hot path never calls the allocator.
+static unsigned long long* scan_workspace(cudaStream_t s, size_t words) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, std::pair<unsigned long long*, size_t>> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto& e = cache[{dev, s}];
+  if (e.second < words) {
+    if (e.first) {
+      cudaStreamSynchronize(s);
+      cudaFree(e.first);
+      e = {nullptr, 0};
+    }
+    size_t cap = words < 4096 ? 4096 : words * 2;
+    if (cudaMalloc(&e.first, cap * sizeof(unsigned long long)) != cudaSuccess) {
+      e = {nullptr, 0};
+      return nullptr;
+    }
+    e.second = cap;
+  }
+  return e.first;
+}
+
 }  // namespace ffb
 
 using namespace ffb;
@@ -233,13 +312,17 @@ int ffb_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t R, v
     FFB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int32_t), s));
     return FFB_OK;
   }
+  if (R <= SCAN_SINGLE_MAX) {   // one CTA, no workspace, no memset: the per-ray counts of a training batch
+    scan_single_block_kernel<<<1, 1024, 0, s>>>(counts, offsets, R);
+    FFB_LAUNCHED();
+    return FFB_OK;
+  }
   const int64_t tiles = (R + SCAN_TILE - 1) / SCAN_TILE;
-  unsigned long long* state = nullptr;
-  FFB_CUDA(cudaMallocAsync(&state, sizeof(unsigned long long) * (tiles + 1), s));
+  unsigned long long* state = scan_workspace(s, (size_t)(tiles + 1));
+  FFB_REQUIRE(state, "cannot allocate the scan workspace");
   FFB_CUDA(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (tiles + 1), s));
   scan_tiles_kernel<<<(unsigned)tiles, SCAN_T, 0, s>>>(counts, offsets, R, state, reinterpret_cast<unsigned int*>(state + tiles));
   FFB_LAUNCHED();
-  FFB_CUDA(cudaFreeAsync(state, s));
   return FFB_OK;
 }
 

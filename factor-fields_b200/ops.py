@@ -18,6 +18,26 @@ def _dev_check(t):
         raise RuntimeError('ffb200 ops need CUDA tensors: there is no CPU path (the oracle under oracle/ is test-only)')
 
 
+_host_cache = {}
+
+
+def host_list(t):
+    """t.tolist() for small, rarely-changing device tensors (aabb, stepSize, freq_bands) without a device->host sync on
+    every call: cached by (storage pointer, version counter, shape).  The cache keeps the tensor alive, so its address
+    cannot be recycled for another tensor while the entry exists; in-place writes bump the version counter."""
+    if not torch.is_tensor(t):
+        return t
+    if not t.is_cuda:
+        return t.tolist()
+    key = (t.data_ptr(), t._version, tuple(t.shape))
+    v = _host_cache.get(key)
+    if v is None:
+        if len(_host_cache) > 256:
+            _host_cache.clear()
+        v = _host_cache[key] = (t, t.tolist())
+    return v[1]
+
+
 def _empty(shape, like, dtype=torch.float32):
     return torch.empty(shape, device=like.device, dtype=dtype)
 
@@ -49,11 +69,11 @@ class PlanBuilder:
     def __init__(self, xdim, in_dim, aabb, mapping, freq):
         d = nv.FieldDesc()
         d.xdim, d.in_dim = xdim, in_dim
-        lo, hi = aabb[0].tolist(), aabb[1].tolist()
+        lo, hi = host_list(aabb)
         for k in range(len(lo)):
             d.aabb_min[k], d.aabb_max[k] = lo[k], hi[k]
         d.mapping = nv.MAP_IDS[mapping]
-        fl = freq.tolist() if freq is not None else []
+        fl = host_list(freq) if freq is not None else []
         if len(fl) > nv.MAX_FREQ:
             raise RuntimeError(f'ffb200: at most {nv.MAX_FREQ} frequency bands are supported')
         d.n_freq = len(fl)
@@ -163,9 +183,9 @@ def grid_mapping(positions, freq_bands, aabb, basis_mapping='sawtooth'):
     F = freq_bands.numel()
     Fo = 2 * F if basis_mapping == 'trigonometric' else F
     out = _empty((x.shape[0], d, Fo), x)
-    lo = (C.c_float * 3)(*aabb[0].tolist())
-    hi = (C.c_float * 3)(*aabb[1].tolist())
-    fr = (C.c_float * F)(*freq_bands.tolist())
+    lo = (C.c_float * 3)(*host_list(aabb)[0])
+    hi = (C.c_float * 3)(*host_list(aabb)[1])
+    fr = (C.c_float * F)(*host_list(freq_bands))
     nv.check(nv.lib().ffb_grid_mapping(nv.ptr(x), C.c_int64(x.shape[0]), d, lo, hi, fr, F, nv.MAP_IDS[basis_mapping], nv.ptr(out),
                                        nv.stream()))
     return out.reshape(*shp, Fo)
@@ -287,16 +307,16 @@ class MLPFunction(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------
 def make_sampler_desc(aabb, step_size, n_samples, alpha=None, alpha_thres=0.5):
     d = nv.SamplerDesc()
-    lo, hi = aabb[0].tolist(), aabb[1].tolist()
+    lo, hi = host_list(aabb)
     for k in range(3):
         d.aabb_min[k], d.aabb_max[k] = lo[k], hi[k]
-    d.step_size = float(step_size)
+    d.step_size = float(host_list(step_size))
     d.n_samples = int(n_samples)
     if alpha is not None:
         d.alpha_volume = alpha.volume_u8.data_ptr()
         D, H, W = alpha.volume_u8.shape
         d.alpha_size[0], d.alpha_size[1], d.alpha_size[2] = W, H, D
-        alo, ainv = alpha.aabb[0].tolist(), alpha.invgridSize.tolist()
+        alo, ainv = host_list(alpha.aabb)[0], host_list(alpha.invgridSize)
         for k in range(3):
             d.alpha_aabb_min[k], d.alpha_inv_size[k] = alo[k], ainv[k]
         d.alpha_thres = alpha_thres

@@ -5,6 +5,15 @@ import torch
 from . import ops
 
 
+def shard_slice(n, rank, world):
+    """Contiguous slice of a global batch of n rays (or sample points) owned by `rank`: disjoint, ordered, covering
+    [0, n); the first n % world ranks get one extra element (every rank draws the same global permutation
+    and takes its own slice)."""
+    base, rem = divmod(int(n), int(world))
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))
+
+
 class GradBucket:
     """Flat fp32 buffer holding every gradient back to back (parameter storage order), so that one all-reduce per
     step covers grids + MLPs.  Device-agnostic torch code (tested with gloo on CPU)."""
