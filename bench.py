@@ -146,7 +146,7 @@ def run_ours(args):
     from ffb200 import native as nv
     from ffb200.models.FactorFields import FactorFields
     from ffb200.renderer import render_ray
-    from ffb200.train import FusedAdam, GradBucket
+    from ffb200.train import FusedAdam, GradBucket, TrainStep
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -172,10 +172,8 @@ def run_ours(args):
     B, S = W.BATCH, W.N_SAMPLES
 
     groups = model.get_optparam_groups(cfg.training.lr_small, cfg.training.lr_large)
-    opt = FusedAdam(groups, betas=(0.9, 0.99))
-    params = opt.params
-    bucket = GradBucket(params) if world > 1 else None
     lr_factor = 0.1 ** (1.0 / cfg.training.n_iters)
+    eager = args.exact_counts or args.eager
 
     nb = 16                                                # distinct batches in the pool (weak scaling: 4096 rays per GPU)
     rays_np, target_np, jitter_np = W.make_rays(B * nb, seed=100 + rank)
@@ -185,37 +183,71 @@ def run_ours(args):
     rays_d, target_d, jitter_d = rays_h.to(dev), target_h.to(dev), jitter_h.to(dev)
     state = {'i': 0}
 
-    def optimise(loss):
-        grads = torch.autograd.grad(loss, params, allow_unused=True)
-        if bucket is not None:
-            bucket.pack(grads)
-            n = bucket.all_reduce()
-            opt.step([bucket.view(i) for i in range(len(params))], grad_scale=1.0 / n)
-        else:
-            opt.step(list(grads))
-        opt.decay_lr(lr_factor)
+    if eager:
+        # the pre-graph path: Python-driven launches, autograd + per-tensor fused Adam (kept for comparison)
+        opt = FusedAdam(groups, betas=(0.9, 0.99))
+        params = opt.params
+        bucket = GradBucket(params) if world > 1 else None
 
-    def step_resident():
-        """inputs already in HBM"""
-        b = state['i'] % nb
-        state['i'] += 1
-        sl = slice(b * B, (b + 1) * B)
-        model._jitter = lambda n, tr: jitter_d[sl]
-        rgb, depth, _ = model(rays_d[sl], white_bg=True, is_train=True, N_samples=S)
-        loss = torch.mean((rgb - target_d[sl]) ** 2)
-        optimise(loss)
-        return loss
+        def optimise(loss):
+            grads = torch.autograd.grad(loss, params, allow_unused=True)
+            if bucket is not None:
+                bucket.pack(grads)
+                n = bucket.all_reduce()
+                opt.step([bucket.view(i) for i in range(len(params))], grad_scale=1.0 / n)
+            else:
+                opt.step(list(grads))
+            opt.decay_lr(lr_factor)
 
-    def step_e2e():
-        """the reference-facing call: host (pinned) rays through render_ray, H2D inside, loss read back"""
-        b = state['i'] % nb
-        state['i'] += 1
-        sl = slice(b * B, (b + 1) * B)
-        model._jitter = lambda n, tr: jitter_h[sl].to(dev, non_blocking=True)
-        rgb, depth, _ = render_ray(rays_h[sl], model, chunk=B, N_samples=S, white_bg=True, is_train=True, device=dev)
-        loss = torch.mean((rgb - target_h[sl].to(dev, non_blocking=True)) ** 2)
-        optimise(loss)
-        return float(loss.item())
+        def step_resident():
+            b = state['i'] % nb
+            state['i'] += 1
+            sl = slice(b * B, (b + 1) * B)
+            model._jitter = lambda n, tr: jitter_d[sl]
+            rgb, depth, _ = model(rays_d[sl], white_bg=True, is_train=True, N_samples=S)
+            loss = torch.mean((rgb - target_d[sl]) ** 2)
+            optimise(loss)
+            return loss
+
+        def step_e2e():
+            b = state['i'] % nb
+            state['i'] += 1
+            sl = slice(b * B, (b + 1) * B)
+            model._jitter = lambda n, tr: jitter_h[sl].to(dev, non_blocking=True)
+            rgb, depth, _ = render_ray(rays_h[sl], model, chunk=B, N_samples=S, white_bg=True, is_train=True, device=dev)
+            loss = torch.mean((rgb - target_h[sl].to(dev, non_blocking=True)) ** 2)
+            optimise(loss)
+            return float(loss.item())
+
+        step_profile = step_resident
+        api = 'ffb200.renderer.render_ray(host rays) -> loss.item()'
+    else:
+        # the product path: the whole step (render, MSE, backward, all-reduce, Adam, lr decay) is one CUDA graph
+        ts = TrainStep(model, groups, batch=B, n_samples=S, white_bg=True, betas=(0.9, 0.99), lr_decay=lr_factor)
+
+        def step_resident():
+            """inputs already in HBM (device -> static-buffer copies only)"""
+            b = state['i'] % nb
+            state['i'] += 1
+            sl = slice(b * B, (b + 1) * B)
+            return ts.step(rays_d[sl], target_d[sl], jitter_d[sl])
+
+        def step_e2e():
+            """the user-facing call: host (pinned) rays / targets / jitter in, loss read back on the host"""
+            b = state['i'] % nb
+            state['i'] += 1
+            sl = slice(b * B, (b + 1) * B)
+            return float(ts.step(rays_h[sl], target_h[sl], jitter_h[sl]).item())
+
+        def step_profile():
+            """the same launch sequence outside the graph, so CUDA events can bracket each kernel group"""
+            b = state['i'] % nb
+            state['i'] += 1
+            sl = slice(b * B, (b + 1) * B)
+            ts.rays_s.copy_(rays_d[sl]); ts.target_s.copy_(target_d[sl]); ts.jitter_s.copy_(jitter_d[sl])
+            ts._body()
+
+        api = 'ffb200.train.TrainStep.step(host rays, host rgb, host jitter) -> loss.item()  [one CUDA-graph launch per step]'
 
     def barrier():
         if world > 1:
@@ -247,11 +279,17 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
 
     # per-kernel device time of the same step (CUDA events on the launching stream), for the roofline
+    step_profile()
+    torch.cuda.synchronize()
+    l0 = nv.launch_count()
     nv.profile_begin()
     P = 5
     for _ in range(P):
-        step_resident()
+        step_profile()
     sec = {k: v[0] / P for k, v in nv.profile_end().items()}      # ms per step
+    launches_per_step = (nv.launch_count() - l0) // P
+    if not eager:
+        launches = launches_per_step * args.steps                  # graph replays re-issue the captured launches
 
     if rank != 0:
         if world > 1:
@@ -283,13 +321,13 @@ def run_ours(args):
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'rays_per_gpu_per_step': B, 'samples_per_ray': S, 'valid_fraction': round(n_valid / (B * S), 4),
                        'shaded_fraction_of_valid': round(n_app / max(n_valid, 1), 4), 'field_queries_per_step_per_gpu': n_valid,
-                       'host_syncs_per_step': 2 if args.exact_counts else 0,
+                       'host_syncs_per_step': 2 if args.exact_counts else 0, 'cuda_graph': not eager, 'launches_per_step': launches_per_step,
                        'parallelism': f'ray-sharded dp{world}, one NCCL all-reduce of the flat fp32 gradient bucket per step' if world > 1 else 'single GPU',
                        'l2': 'per-step inputs+intermediates (~0.5 GB) exceed the 126 MB L2; no explicit flush; the 21 MB of parameters stay '
                              'L2-resident across steps as in training'},
             'field_queries_per_s': world * n_valid * args.steps / (ms_total * 1e-3),
             'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': B * (6 + 3 + 1) * 4,
-                    'd2h_bytes_per_step': 4 + 8, 'api': 'ffb200.renderer.render_ray(host rays) -> loss.item()'},
+                    'd2h_bytes_per_step': 4, 'api': api},
             'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clk}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_leg()
@@ -305,6 +343,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='Python-driven launches instead of the CUDA-graph TrainStep')
     ap.add_argument('--exact-counts', action='store_true', help='read the sample counts back every step (the reference-like sync mode)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -40,6 +40,52 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// Multi-tensor Adam: one launch for every parameter tensor.  Block b updates chunk b = CHUNK consecutive elements of
+// tensor chunk_tensor[b] starting at chunk_start[b]; the step-dependent scalars are read from DEVICE memory
+// (hyper[group] = {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)}) so the launch can sit inside a replayed CUDA graph.
+__global__ void __launch_bounds__(256) adam_multi_kernel(const int64_t* __restrict__ table /*[T][6]: p g m v n group*/,
+                                                         const int32_t* __restrict__ chunk_tensor,
+                                                         const int64_t* __restrict__ chunk_start, int chunk,
+                                                         const float* __restrict__ hyper, float beta1, float beta2, float eps,
+                                                         float grad_scale) {
+  const int t = chunk_tensor[blockIdx.x];
+  const int64_t* e = table + (int64_t)t * 6;
+  float* __restrict__ p = reinterpret_cast<float*>(e[0]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(e[1]);
+  float* __restrict__ m = reinterpret_cast<float*>(e[2]);
+  float* __restrict__ v = reinterpret_cast<float*>(e[3]);
+  const int64_t n = e[4];
+  const int grp = (int)e[5];
+  const float step_size = hyper[2 * grp], inv_sqrt_bc2 = hyper[2 * grp + 1];
+  const int64_t begin = chunk_start[blockIdx.x];
+  const int64_t end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] * beta1 + gi * (1.0f - beta1);
+    const float vi = v[i] * beta2 + gi * gi * (1.0f - beta2);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+
+// One thread: t += 1; hyper[g] = {lr_g / (1 - b1^t), 1 / sqrt(1 - b2^t)}; lr_g *= decay  (torch.optim.Adam's scalar
+// bookkeeping + train_per_scene.py:170-171, in double like the Python reference) -- device-side so that a replayed
+// CUDA graph advances the optimiser without host traffic.
+__global__ void adam_hyper_kernel(double* __restrict__ lr, long long* __restrict__ step, float* __restrict__ hyper, int n_groups,
+                                  double beta1, double beta2, double decay) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const long long t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow(beta1, (double)t), bc2 = 1.0 - pow(beta2, (double)t);
+  for (int g = 0; g < n_groups; ++g) {
+    hyper[2 * g] = (float)(lr[g] / bc1);
+    hyper[2 * g + 1] = (float)(1.0 / sqrt(bc2));
+    lr[g] *= decay;
+  }
+}
+
 }  // namespace ffb
 
 using namespace ffb;
@@ -61,6 +107,24 @@ int ffb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<blocks_for(n, 256, sm_count() * 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
                                                                                    (float)(1.0 / sqrt(bc2)), grad_scale);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_adam_hyper_advance(double* d_lr, int64_t* d_step, float* d_hyper, int32_t n_groups, double beta1, double beta2,
+                           double lr_decay, void* stream) {
+  FFB_REQUIRE(d_lr && d_step && d_hyper && n_groups > 0, "bad argument");
+  adam_hyper_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_lr, reinterpret_cast<long long*>(d_step), d_hyper, n_groups, beta1, beta2, lr_decay);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_adam_multi(const int64_t* d_table, const int32_t* d_chunk_tensor, const int64_t* d_chunk_start, int32_t n_chunks,
+                   int32_t chunk, const float* d_hyper, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  FFB_REQUIRE(d_table && d_chunk_tensor && d_chunk_start && d_hyper && chunk > 0, "bad argument");
+  if (n_chunks <= 0) return FFB_OK;
+  adam_multi_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(d_table, d_chunk_tensor, d_chunk_start, chunk, d_hyper, beta1,
+                                                                          beta2, eps, grad_scale);
   FFB_LAUNCHED();
   return FFB_OK;
 }

@@ -38,6 +38,25 @@ def host_list(t):
     return v[1]
 
 
+# Optional pre-allocated gradient storage (train.TrainStep): {parameter data_ptr: zeroed tensor with the parameter's
+# shape and strides}.  While set, the backward passes accumulate into these instead of allocating zeros_like tensors —
+# valid only when every parameter is used by exactly one forward call per backward (TrainStep guarantees that).
+_grad_arena = None
+
+
+def set_grad_arena(mapping):
+    global _grad_arena
+    _grad_arena = mapping
+
+
+def _grad_like(t):
+    if _grad_arena is not None:
+        g = _grad_arena.get(t.data_ptr())
+        if g is not None:
+            return g
+    return torch.zeros_like(t)   # preserve_format keeps the channels-last strides
+
+
 def _empty(shape, like, dtype=torch.float32):
     return torch.empty(shape, device=like.device, dtype=dtype)
 
@@ -159,7 +178,7 @@ class FieldQuery(torch.autograd.Function):
         arr = (C.c_void_p * nv.MAX_OPS)()
         for i, t in enumerate(plan.tensors):
             if ctx.needs_input_grad[3 + i]:
-                g = torch.zeros_like(t)  # preserve_format keeps the channels-last strides
+                g = _grad_like(t)
                 grads.append(g)
                 arr[i] = g.data_ptr()
             else:
@@ -215,8 +234,8 @@ def _mlp_backward(acts, layers, acts_kind, g_out, need_input_grad, param_needs, 
         M, K = W.shape
         act = acts_kind[l]
         y = acts[l + 1]
-        gW = torch.zeros_like(W) if param_needs[l][0] else None
-        gb = torch.zeros_like(b) if (b is not None and param_needs[l][1]) else None
+        gW = _grad_like(W) if param_needs[l][0] else None
+        gb = _grad_like(b) if (b is not None and param_needs[l][1]) else None
         if n > 0 and gW is not None:
             nv.check(lib.ffb_linear_bwd_weight_act(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), act, nv.ptr(acts[l]), nv.ptr(gW),
                                                    nv.ptr(gb, allow_none=True), C.c_int64(n), nv.i32p(n_dev), K, M, nv.stream()))
@@ -498,9 +517,9 @@ class RenderComposite(torch.autograd.Function):
                     flat.append(gb)
         else:
             for (W, b), hb, (nw, nb) in zip(layers, ctx.has_bias, pn):
-                flat.append(torch.zeros_like(W) if nw else None)
+                flat.append(_grad_like(W) if nw else None)
                 if hb:
-                    flat.append(torch.zeros_like(b) if nb else None)
+                    flat.append(_grad_like(b) if nb else None)
         return (g_feat, None, None, None, None, None, *flat)
 
 
@@ -577,10 +596,27 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
 
 
 @torch.no_grad()
-def mse_fwd_bwd(pred, target, g_scale=1.0):
+def adam_hyper_advance(lr_d, step_d, hyper_d, beta1, beta2, lr_decay):
+    """lr_d [G] float64, step_d [1] int64, hyper_d [G,2] float32 — all on the device."""
+    nv.check(nv.lib().ffb_adam_hyper_advance(nv.ptr(lr_d, torch.float64), nv.ptr(step_d, torch.int64), nv.ptr(hyper_d), lr_d.numel(),
+                                             C.c_double(beta1), C.c_double(beta2), C.c_double(lr_decay), nv.stream()))
+
+
+@torch.no_grad()
+def adam_multi(table, chunk_tensor, chunk_start, chunk, hyper_d, beta1, beta2, eps, grad_scale=1.0):
+    nv.check(nv.lib().ffb_adam_multi(nv.ptr(table, torch.int64), nv.ptr(chunk_tensor, torch.int32), nv.ptr(chunk_start, torch.int64),
+                                     chunk_tensor.numel(), int(chunk), nv.ptr(hyper_d), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                     C.c_float(grad_scale), nv.stream()))
+
+
+@torch.no_grad()
+def mse_fwd_bwd(pred, target, g_scale=1.0, loss=None):
     """-> (loss [1] device tensor, g_pred)"""
     pred, target = pred.contiguous(), target.contiguous()
-    loss = torch.zeros(1, device=pred.device)
+    if loss is None:
+        loss = torch.zeros(1, device=pred.device)
+    else:
+        loss.zero_()
     g = torch.empty_like(pred)
     nv.check(nv.lib().ffb_mse_fwd_bwd(nv.ptr(pred), nv.ptr(target), C.c_int64(pred.numel()), C.c_float(g_scale), nv.ptr(loss), nv.ptr(g),
                                       nv.stream()))

@@ -84,3 +84,152 @@ class FusedAdam:
     def decay_lr(self, factor):
         for g in self.groups:
             g['lr'] = g['lr'] * factor
+
+
+class TrainStep:
+    """One NeRF optimisation step of the reference's training loop (train_per_scene.py:149-171: render the ray batch,
+    MSE, backward, Adam with two lr groups, multiplicative lr decay) as ONE replayable CUDA graph.
+
+    B200-first design: every data-dependent size (valid samples, shaded samples) stays on the device
+    (`model.lazy_counts`), so the whole step has a static launch sequence; it is captured once and replayed with a
+    single `cudaGraphLaunch` per step — no Python, no allocator and no host synchronisation inside the step.  The
+    optimiser scalars (step count, lr, bias corrections) live in device memory and are advanced by a kernel inside the
+    graph.  Gradients accumulate directly into one flat fp32 arena (zeroed by one memset, all-reduced in place when
+    world_size > 1, consumed by one multi-tensor Adam launch).
+
+        ts = TrainStep(model, model.get_optparam_groups(lr_small, lr_large), batch=4096, n_samples=443, lr_decay=f)
+        loss = ts.step(rays_host, rgb_host)          # host (pinned) or device tensors; returns a device scalar
+
+    Schedule events that re-allocate factors or change the sample count (upsample / shrink / alpha-mask update) need a
+    new TrainStep (`ts.rebuild()` keeps the optimiser scalars), exactly where the reference rebuilds its optimiser.
+    """
+
+    CHUNK = 16384
+
+    def __init__(self, model, param_groups, batch, n_samples, white_bg=True, betas=(0.9, 0.99), eps=1e-8, lr_decay=1.0,
+                 group=None, use_graph=True, warmup=2):
+        self.model, self.B, self.S, self.white_bg = model, int(batch), int(n_samples), bool(white_bg)
+        self.betas, self.eps, self.lr_decay, self.group, self.use_graph = betas, eps, float(lr_decay), group, use_graph
+        self.groups = [{'params': [p for p in g['params']], 'lr': float(g['lr'])} for g in param_groups]
+        self.params = [p for g in self.groups for p in g['params']]
+        dev = self.params[0].device
+        self.dev = dev
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(group)
+        model.lazy_counts = True
+        # gradient arena + optimiser state
+        self.bucket = GradBucket(self.params)
+        self.m = torch.zeros_like(self.bucket.flat)
+        self.v = torch.zeros_like(self.bucket.flat)
+        self.lr_d = torch.tensor([g['lr'] for g in self.groups], dtype=torch.float64, device=dev)
+        self.step_d = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.hyper_d = torch.zeros(len(self.groups), 2, dtype=torch.float32, device=dev)
+        self._build_tables()
+        # static inputs / outputs
+        self.rays_s = torch.zeros(self.B, 6, device=dev)
+        self.target_s = torch.zeros(self.B, 3, device=dev)
+        self.jitter_s = torch.zeros(self.B, device=dev)
+        self.loss_s = torch.zeros(1, device=dev)
+        self.graph = None
+        self._warmup = warmup
+
+    def _build_tables(self):
+        rows, ct, cs = [], [], []
+        i = 0
+        for gi, g in enumerate(self.groups):
+            for p in g['params']:
+                off, n = self.bucket.offsets[i], p.numel()
+                base = off * 4
+                rows.append([p.data_ptr(), self.bucket.flat.data_ptr() + base, self.m.data_ptr() + base, self.v.data_ptr() + base, n, gi])
+                for s in range(0, n, self.CHUNK):
+                    ct.append(i)
+                    cs.append(s)
+                i += 1
+        self.table = torch.tensor(rows, dtype=torch.int64, device=self.dev)
+        self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=self.dev)
+        self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=self.dev)
+        self.arena = {p.data_ptr(): self.bucket.view(k) for k, p in enumerate(self.params)}
+        self._param_ptrs = [p.data_ptr() for p in self.params]
+
+    # -- the step body: only stream-ordered device work (capturable) ------------------------------------------
+    def _body(self):
+        from . import ops as _ops
+        m = self.model
+        self.bucket.flat.zero_()
+        _ops.set_grad_arena(self.arena)
+        prev_jitter = m.__dict__.get('_jitter')
+        m._jitter = lambda n, tr: self.jitter_s
+        try:
+            rgb, depth, _ = m(self.rays_s, white_bg=self.white_bg, is_train=True, N_samples=self.S)
+            _, g_rgb = _ops.mse_fwd_bwd(rgb, self.target_s, loss=self.loss_s)
+            grads = torch.autograd.grad([rgb], self.params, grad_outputs=[g_rgb], allow_unused=True)
+        finally:
+            _ops.set_grad_arena(None)
+            if prev_jitter is None:
+                m.__dict__.pop('_jitter', None)
+            else:
+                m._jitter = prev_jitter
+        for k, g in enumerate(grads):       # gradients produced outside the arena (factor types without arena support)
+            if g is not None:
+                v = self.bucket.view(k)
+                if g.data_ptr() != v.data_ptr():
+                    v.copy_(g)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.bucket.flat, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        _ops.adam_hyper_advance(self.lr_d, self.step_d, self.hyper_d, self.betas[0], self.betas[1], self.lr_decay)
+        _ops.adam_multi(self.table, self.chunk_tensor, self.chunk_start, self.CHUNK, self.hyper_d, self.betas[0], self.betas[1],
+                        self.eps, 1.0 / self.world)
+
+    def _check_params(self):
+        if [p.data_ptr() for p in self.params] != self._param_ptrs:
+            raise RuntimeError('TrainStep: a parameter tensor was re-allocated (shrink / upsample); build a new TrainStep')
+
+    def _capture(self):
+        # warm-up on a side stream (allocator, lazy kernel attributes), then restore the state it touched
+        snap = [p.detach().clone() for p in self.params]
+        st = (self.m.clone(), self.v.clone(), self.lr_d.clone(), self.step_d.clone())
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(self._warmup, 1)):
+                self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        with torch.no_grad():
+            for p, q in zip(self.params, snap):
+                p.copy_(q)
+            self.m.copy_(st[0]); self.v.copy_(st[1]); self.lr_d.copy_(st[2]); self.step_d.copy_(st[3])
+        if self.use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+        else:
+            self.graph = False
+
+    def step(self, rays, target, jitter=None):
+        """rays [B,6], target [B,3]: host (ideally pinned) or device fp32 tensors; jitter [B] (default: torch.rand on the
+        CPU generator, one draw per ray, as FactorFields.py:593-595).  Returns the loss as a 1-element DEVICE tensor
+        (valid until the next step); call .item() to read it back."""
+        if rays.shape[0] != self.B:
+            raise RuntimeError(f'TrainStep was built for batches of {self.B} rays, got {rays.shape[0]}')
+        self._check_params()
+        if jitter is None:
+            jitter = torch.rand(self.B, 1)[:, 0]
+        if self.graph is None:
+            self._capture()
+        self.rays_s.copy_(rays[:, :6], non_blocking=True)
+        self.target_s.copy_(target, non_blocking=True)
+        self.jitter_s.copy_(jitter, non_blocking=True)
+        if self.graph:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss_s
+
+    @property
+    def lrs(self):
+        return self.lr_d.tolist()
+
+    def set_lrs(self, lrs):
+        self.lr_d.copy_(torch.tensor(lrs, dtype=torch.float64))

@@ -253,6 +253,17 @@ int ffb_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float g_s
 int ffb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);
 
+/* Multi-tensor Adam, one launch for all parameter tensors, CUDA-graph friendly: every step-dependent scalar lives in
+ * DEVICE memory.  d_table [T][6] int64 = {p, g, m, v (device addresses), n, group}; block b updates `chunk` elements of
+ * tensor d_chunk_tensor[b] from d_chunk_start[b]; d_hyper [n_groups][2] = {lr/(1-beta1^t), 1/sqrt(1-beta2^t)}. */
+/* Device-side scalar bookkeeping for ffb_adam_multi: *d_step += 1; d_hyper[g] = {lr_g/(1-beta1^t), 1/sqrt(1-beta2^t)};
+ * d_lr[g] *= lr_decay (train_per_scene.py:170-171), all in double as the Python reference. */
+int ffb_adam_hyper_advance(double* d_lr, int64_t* d_step, float* d_hyper, int32_t n_groups, double beta1,
+                           double beta2, double lr_decay, void* stream);
+int ffb_adam_multi(const int64_t* d_table, const int32_t* d_chunk_tensor, const int64_t* d_chunk_start,
+                   int32_t n_chunks, int32_t chunk, const float* d_hyper, float beta1, float beta2, float eps,
+                   float grad_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry point (the end-to-end boundary: host rays in, host pixels out; includes the
  * H2D/D2H copies and a stream synchronise).  Mirrors renderer.py:8-27 + FactorFields.py:586-602 for

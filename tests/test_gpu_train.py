@@ -1,0 +1,86 @@
+"""GPU: the CUDA-graph train step (ffb200.train.TrainStep) against the eager path driven the way the reference's
+training loop drives it (train_per_scene.py:149-171): render_ray -> MSE -> loss.backward() -> torch.optim.Adam with two
+lr groups -> multiplicative lr decay.  Same rays / jitter / targets on both sides; tolerance covers only the
+non-deterministic order of the fp32 atomics."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_rays import blender_like_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_model(seed=0):
+    import ffb200
+    from ffb200.models.FactorFields import FactorFields
+    torch.manual_seed(seed)
+    cfg = ffb200.load_cfg('nerf.yaml', ['model.total_params=60000', 'model.coeff_reso=8'])
+    cfg.dataset.aabb = [[-1., -1., -1.], [1., 1., 1.]]
+    m = FactorFields(cfg, 'cuda:0')
+    with torch.no_grad():   # make a visible density blob so the appearance MLP is exercised
+        m.linear_mat.backbone[0].weight.mul_(10.0)
+        m.linear_mat.backbone[1].weight[0].normal_(0, 2.0)
+        m.linear_mat.backbone[0].weight[63].zero_()
+        m.linear_mat.backbone[0].bias[63] = 1.0
+        m.linear_mat.backbone[1].weight[0, 63] = 6.0
+    return cfg, m
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_train_step_matches_eager_torch_adam(use_graph):
+    from ffb200.renderer import render_ray
+    from ffb200.train import TrainStep
+    cfg, ma = _small_model()
+    mb = copy.deepcopy(ma)
+    mb._plans = {}
+    R, S, steps, decay = 256, 96, 4, 0.97
+    rays = torch.from_numpy(blender_like_rays(R * steps, 5))
+    rng = np.random.RandomState(7)
+    target = torch.from_numpy(rng.rand(R * steps, 3).astype(np.float32))
+    jitter = torch.from_numpy(rng.rand(R * steps).astype(np.float32))
+
+    # --- eager side: unmodified caller code (autograd + torch.optim.Adam)
+    opt = torch.optim.Adam(ma.get_optparam_groups(0.001, 0.02), betas=(0.9, 0.99))
+    losses_a = []
+    for i in range(steps):
+        sl = slice(i * R, (i + 1) * R)
+        ma._jitter = lambda n, tr: jitter[sl].cuda()
+        rgb, depth, _ = render_ray(rays[sl], ma, chunk=R, N_samples=S, white_bg=True, is_train=True, device='cuda:0')
+        loss = torch.mean((rgb - target[sl].cuda()) ** 2)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        for g in opt.param_groups:
+            g['lr'] = g['lr'] * decay
+        losses_a.append(float(loss.detach()))
+
+    # --- graph side
+    ts = TrainStep(mb, mb.get_optparam_groups(0.001, 0.02), batch=R, n_samples=S, lr_decay=decay, use_graph=use_graph)
+    losses_b = []
+    for i in range(steps):
+        sl = slice(i * R, (i + 1) * R)
+        losses_b.append(float(ts.step(rays[sl].pin_memory(), target[sl].pin_memory(), jitter[sl].pin_memory()).item()))
+
+    assert int(mb.last_stats['n_app']) > 0, 'test scene shades nothing: the appearance MLP is not exercised'
+    np.testing.assert_allclose(losses_b, losses_a, rtol=2e-5, atol=1e-7)
+    for (n, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+        d = float((pa - pb).abs().max())
+        assert d < 2e-4 * max(1.0, float(pa.abs().max())), (n, d)
+    # lr bookkeeping on the device equals the Python-side decay
+    np.testing.assert_allclose(ts.lrs, [g['lr'] for g in opt.param_groups], rtol=1e-12)
+
+
+def test_train_step_does_not_disturb_state_on_capture():
+    """Capturing (warm-up + graph build) must leave parameters and optimiser state exactly as they were."""
+    from ffb200.train import TrainStep
+    cfg, m = _small_model(1)
+    before = [p.detach().clone() for p in m.parameters()]
+    ts = TrainStep(m, m.get_optparam_groups(0.001, 0.02), batch=128, n_samples=64)
+    ts._capture()
+    torch.cuda.synchronize()
+    for a, p in zip(before, m.parameters()):
+        assert torch.equal(a, p)
+    assert int(ts.step_d.item()) == 0 and float(ts.m.abs().sum()) == 0.0 and float(ts.v.abs().sum()) == 0.0
