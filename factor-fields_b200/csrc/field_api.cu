@@ -11,6 +11,26 @@ int ffb_field_fast_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* 
 int ffb_field_fast_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
                        float* const* h_grads, void* stream);
 
+int ffb_field_fast_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
+                             void* stream);
+int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                             const float* coeff, const float* basis, float* const* h_grads, void* stream);
+
+// Training forward: also writes the concatenated basis row (needed by ffb_field_query_bwd_saved).
+int ffb_field_query_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
+                              void* stream) {
+  if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_fwd_train(f, x, n, n_dev, feats, coeff, basis, stream);
+  return ffb_field_generic_fwd(f, x, n, n_dev, feats, coeff, basis, stream);
+}
+
+// Backward from the saved coefficient / basis rows (no re-gather) where the specialised kernels apply; otherwise
+// identical to ffb_field_query_bwd.
+int ffb_field_query_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                              const float* coeff, const float* basis, float* const* h_grads, void* stream) {
+  if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_bwd_saved(f, x, n, n_dev, g_feats, g_coeff, coeff, basis, h_grads, stream);
+  return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
+}
+
 int ffb_field_query_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, void* stream) {
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_fwd(f, x, n, n_dev, feats, coeff, stream);
   return ffb_field_generic_fwd(f, x, n, n_dev, feats, coeff, nullptr, stream);

@@ -9,6 +9,7 @@
 // tap indices are identical to the generic path and to the reference.
 #include "ffb_common.cuh"
 #include "ffb_math.h"
+#include <string.h>
 
 struct ffb_field {
   ffb_field_desc h;
@@ -186,49 +187,90 @@ __device__ __forceinline__ float fast_msize(const FastParams& P) {
   return m;
 }
 
-template <int DB, int DC, bool NEAR_B, bool NEAR_C>
-__global__ void __launch_bounds__(128) fast_fwd_kernel(const FastParams P, const float* __restrict__ x, int64_t n,
-                                                       const int32_t* __restrict__ n_dev, float* __restrict__ feats,
-                                                       float* __restrict__ coeff) {
+// NT threads per CTA, at least MINB CTAs resident per SM (caps the register count: the kernel is bound by the latency
+// of L2-resident gathers, so more resident warps = more loads in flight).  basis (optional): the concatenated basis
+// row, saved for the gather-free backward pass.
+// STAGE (experiment knob "field_fwd_stage", off by default — measured 6 % SLOWER on nerf.yaml: 315 vs 299 us): a warp
+// parks its 32 coefficient / basis rows in shared memory and streams the contiguous 32*W-float chunk out with
+// coalesced 8-byte stores, forming feats = coeff * basis on the way.  The warp-wide barrier costs more overlap than
+// the partially-written sectors of the direct per-lane row stores.
+template <int DB, int DC, bool NEAR_B, bool NEAR_C, int NT, int MINB, bool STAGE>
+__global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, const float* __restrict__ x, int64_t n,
+                                                            const int32_t* __restrict__ n_dev, float* __restrict__ feats,
+                                                            float* __restrict__ coeff, float* __restrict__ basis) {
+  extern __shared__ float2 fwd_stage[];
   n = resolve_n(n, n_dev);
   const float msize = fast_msize(P);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float xr[3];
-    for (int k = 0; k < P.xdim; ++k) xr[k] = x[i * P.xdim + k];
-    TapSet<DC, NEAR_C> tc;
-    coeff_taps<DC, NEAR_C>(P, xr, tc);
-    float* frow = feats ? feats + i * P.W : nullptr;
-    float* crow = coeff ? coeff + i * P.W : nullptr;
-    for (int l = 0; l < P.n_levels; ++l) {
-      const FastLevel L = P.lv[l];
-      TapSet<DB, NEAR_B> tb;
-      basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
-      if ((L.C & 3) == 0) {
-        for (int c0 = 0; c0 < L.C; c0 += 4) {
-          float b[4], ca[2], cb[2];
-          gather_vec<DB, NEAR_B, 4>(L.data, L.C, c0, tb, b);
-          gather_vec<DC, NEAR_C, 2>(P.cdata, P.W, L.col + c0, tc, ca);
-          gather_vec<DC, NEAR_C, 2>(P.cdata, P.W, L.col + c0 + 2, tc, cb);
-          const int o = L.col + c0;
-          if (frow) {
-            *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
-            *reinterpret_cast<float2*>(frow + o + 2) = make_float2(b[2] * cb[0], b[3] * cb[1]);
+  const int lane = threadIdx.x & 31, W = P.W;
+  float* sC = nullptr;
+  float* sB = nullptr;
+  if (STAGE) {
+    sC = reinterpret_cast<float*>(fwd_stage) + (size_t)(threadIdx.x >> 5) * 64 * W;
+    sB = sC + 32 * W;
+  }
+  const int64_t n_chunks = (n + 31) / 32;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp0; k < n_chunks; k += nwarps) {
+    const int64_t i = k * 32 + lane;
+    if (i < n) {
+      float xr[3];
+      for (int d = 0; d < P.xdim; ++d) xr[d] = x[i * P.xdim + d];
+      TapSet<DC, NEAR_C> tc;
+      coeff_taps<DC, NEAR_C>(P, xr, tc);
+      float* frow = feats ? feats + i * W : nullptr;
+      float* crow = STAGE ? sC + lane * W : (coeff ? coeff + i * W : nullptr);
+      float* brow = STAGE ? sB + lane * W : (basis ? basis + i * W : nullptr);
+      for (int l = 0; l < P.n_levels; ++l) {
+        const FastLevel L = P.lv[l];
+        TapSet<DB, NEAR_B> tb;
+        basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
+        if ((L.C & 3) == 0) {
+          for (int c0 = 0; c0 < L.C; c0 += 4) {
+            float b[4], ca[2], cb[2];
+            gather_vec<DB, NEAR_B, 4>(L.data, L.C, c0, tb, b);
+            gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
+            gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0 + 2, tc, cb);
+            const int o = L.col + c0;
+            if (!STAGE && frow) {
+              *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
+              *reinterpret_cast<float2*>(frow + o + 2) = make_float2(b[2] * cb[0], b[3] * cb[1]);
+            }
+            if (crow) {
+              *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
+              *reinterpret_cast<float2*>(crow + o + 2) = make_float2(cb[0], cb[1]);
+            }
+            if (brow) {
+              *reinterpret_cast<float2*>(brow + o) = make_float2(b[0], b[1]);
+              *reinterpret_cast<float2*>(brow + o + 2) = make_float2(b[2], b[3]);
+            }
           }
-          if (crow) {
-            *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
-            *reinterpret_cast<float2*>(crow + o + 2) = make_float2(cb[0], cb[1]);
+        } else {
+          for (int c0 = 0; c0 < L.C; c0 += 2) {
+            float b[2], ca[2];
+            gather_vec<DB, NEAR_B, 2>(L.data, L.C, c0, tb, b);
+            gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
+            const int o = L.col + c0;
+            if (!STAGE && frow) *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
+            if (crow) *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
+            if (brow) *reinterpret_cast<float2*>(brow + o) = make_float2(b[0], b[1]);
           }
-        }
-      } else {
-        for (int c0 = 0; c0 < L.C; c0 += 2) {
-          float b[2], ca[2];
-          gather_vec<DB, NEAR_B, 2>(L.data, L.C, c0, tb, b);
-          gather_vec<DC, NEAR_C, 2>(P.cdata, P.W, L.col + c0, tc, ca);
-          const int o = L.col + c0;
-          if (frow) *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
-          if (crow) *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
         }
       }
+    }
+    if (STAGE) {
+      __syncwarp();
+      const int64_t rows = (n - k * 32) < 32 ? (n - k * 32) : 32;
+      const int total = (int)rows * (W >> 1);                 // float2 elements of the chunk
+      const int64_t base = k * 32 * (W >> 1);
+      const float2* c2 = reinterpret_cast<const float2*>(sC);
+      const float2* b2 = reinterpret_cast<const float2*>(sB);
+      for (int t = lane; t < total; t += 32) {
+        const float2 cv = c2[t], bv = b2[t];
+        if (coeff) reinterpret_cast<float2*>(coeff)[base + t] = cv;
+        if (basis) reinterpret_cast<float2*>(basis)[base + t] = bv;
+        if (feats) reinterpret_cast<float2*>(feats)[base + t] = make_float2(bv.x * cv.x, bv.y * cv.y);
+      }
+      __syncwarp();
     }
   }
 }
@@ -265,6 +307,123 @@ __global__ void __launch_bounds__(128) fast_bwd_kernel(const FastParams P, const
         const float gb[2] = {g.x * ca[0], g.y * ca[1]};
         if (G.c) scatter_vec<DC, NEAR_C, 2>(G.c, P.W, o, tc, gc);
         if (G.b[l]) scatter_vec<DB, NEAR_B, 2>(G.b[l], L.C, c0, tb, gb);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gather-free backward: the forward pass saved the coefficient row and the basis row of every query, so the
+// backward pass only recomputes the tap indices / weights (ALU) and scatters.  Per query this removes the 120
+// scattered loads of the re-gathering kernel; what remains is the reduction traffic, issued as 16-byte
+// red.global.add.v4.f32 wherever the target is 16-byte aligned (basis texels with 4 channels; the coefficient
+// texel is W floats = 8-byte aligned, so even/odd texels use {v4.., v2} / {v2, v4..} splits).
+// AGGW > 0: the coefficient gradient row (W <= AGGW) is accumulated in registers over the levels and scattered
+// once per corner with that split; AGGW == 0: wide rows (image presets) scatter level by level.
+// ---------------------------------------------------------------------------------------------------------
+template <int D, bool NEAREST, int wmax>
+__device__ __forceinline__ void scatter_row(float* __restrict__ grad, int W, const TapSet<D, NEAREST>& t, const float* g /*[wmax]*/) {
+  constexpr int ROWS = NEAREST ? 1 : (1 << (D - 1));
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (!t.row_ok[r]) continue;
+#pragma unroll
+    for (int xs = 0; xs < (NEAREST ? 1 : 2); ++xs) {
+      const float wx = xs ? t.wx1 : t.wx0;
+      if (xs ? !t.x1_ok : (!NEAREST && wx == 0.0f)) continue;
+      const float w = t.wrow[r] * wx;
+      const size_t e0 = (size_t)(t.base[r] + xs) * W;      // first float of the texel
+      float* p = grad + e0;
+      if ((e0 & 3) == 0) {                                 // 16-byte aligned texel: v4 v4 ... [v2]
+#pragma unroll
+        for (int c = 0; c < wmax; c += 4) {
+          if (c + 4 <= wmax && c + 4 <= W) red_add_v4(p + c, g[c] * w, g[c + 1] * w, g[c + 2] * w, g[c + 3] * w);
+          else if (c + 2 <= wmax && c + 2 <= W) red_add_v2(p + c, g[c] * w, g[c + 1] * w);
+        }
+      } else {                                             // 8-byte aligned only: v2 v4 v4 ... [v2]
+        red_add_v2(p, g[0] * w, g[1] * w);
+#pragma unroll
+        for (int c = 2; c < wmax; c += 4) {
+          if (c + 4 <= wmax && c + 4 <= W) red_add_v4(p + c, g[c] * w, g[c + 1] * w, g[c + 2] * w, g[c + 3] * w);
+          else if (c + 2 <= wmax && c + 2 <= W) red_add_v2(p + c, g[c] * w, g[c + 1] * w);
+        }
+      }
+    }
+  }
+}
+
+template <int DB, int DC, bool NEAR_B, bool NEAR_C, int AGGW, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_kernel(const FastParams P, const FastGrads G, const float* __restrict__ x,
+                                                                  int64_t n, const int32_t* __restrict__ n_dev,
+                                                                  const float* __restrict__ g_feats, const float* __restrict__ g_coeff,
+                                                                  const float* __restrict__ coeff, const float* __restrict__ basis) {
+  n = resolve_n(n, n_dev);
+  const float msize = fast_msize(P);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float xr[3];
+    for (int k = 0; k < P.xdim; ++k) xr[k] = x[i * P.xdim + k];
+    const float* gf = g_feats ? g_feats + i * P.W : nullptr;
+    const float* gcf = g_coeff ? g_coeff + i * P.W : nullptr;
+    const float* crow = coeff + i * P.W;
+    const float* brow = basis + i * P.W;
+    TapSet<DC, NEAR_C> tc;
+    if (G.c) coeff_taps<DC, NEAR_C>(P, xr, tc);
+    if (AGGW > 0 && G.c) {
+      // d/d coeff row = g_feats * basis (+ g_coeff): a flat pass over the W columns, no level structure needed
+      float gacc[AGGW > 0 ? AGGW : 2];
+#pragma unroll
+      for (int c = 0; c < AGGW; c += 2) {
+        gacc[c] = gacc[c + 1] = 0.0f;
+        if (c < P.W) {
+          const float2 g = gf ? *reinterpret_cast<const float2*>(gf + c) : make_float2(0.f, 0.f);
+          const float2 b = *reinterpret_cast<const float2*>(brow + c);
+          gacc[c] = g.x * b.x;
+          gacc[c + 1] = g.y * b.y;
+          if (gcf) {
+            const float2 g2 = *reinterpret_cast<const float2*>(gcf + c);
+            gacc[c] += g2.x;
+            gacc[c + 1] += g2.y;
+          }
+        }
+      }
+      scatter_row<DC, NEAR_C, (AGGW > 0 ? AGGW : 2)>(G.c, P.W, tc, gacc);
+    }
+#pragma unroll 1
+    for (int l = 0; l < P.n_levels; ++l) {
+      const FastLevel L = P.lv[l];
+      if (!G.b[l] && (AGGW > 0 || !G.c)) continue;
+      TapSet<DB, NEAR_B> tb;
+      if (G.b[l]) basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
+      for (int c0 = 0; c0 < L.C; c0 += 2) {
+        const int o = L.col + c0;
+        const float2 g = gf ? *reinterpret_cast<const float2*>(gf + o) : make_float2(0.f, 0.f);
+        const float2 ca = *reinterpret_cast<const float2*>(crow + o);
+        if (AGGW == 0 && G.c) {
+          const float2 b = *reinterpret_cast<const float2*>(brow + o);
+          float gc[2] = {g.x * b.x, g.y * b.y};
+          if (gcf) {
+            const float2 g2 = *reinterpret_cast<const float2*>(gcf + o);
+            gc[0] += g2.x;
+            gc[1] += g2.y;
+          }
+          scatter_vec<DC, NEAR_C, 2>(G.c, P.W, o, tc, gc);
+        }
+        if (G.b[l]) {
+          float gb[4];
+          gb[0] = g.x * ca.x;
+          gb[1] = g.y * ca.y;
+          if ((L.C & 3) == 0) {          // 16-byte texels: two channel pairs -> one v4 reduction per corner
+            if ((c0 & 2) == 0) {
+              const float2 g_n = gf ? *reinterpret_cast<const float2*>(gf + o + 2) : make_float2(0.f, 0.f);
+              const float2 ca_n = *reinterpret_cast<const float2*>(crow + o + 2);
+              gb[2] = g_n.x * ca_n.x;
+              gb[3] = g_n.y * ca_n.y;
+              scatter_vec<DB, NEAR_B, 4>(G.b[l], L.C, c0, tb, gb);
+            }
+          } else {
+            scatter_vec<DB, NEAR_B, 2>(G.b[l], L.C, c0, tb, gb);
+          }
+        }
       }
     }
   }
@@ -317,15 +476,57 @@ static bool build_params(const ffb_field_desc& d, FastParams& P, int op_index[FA
 
 using namespace ffb;
 
-#define FAST_DISPATCH(KERNEL, ...)                                                                              \
+// ---- launch configuration (tunable at run time for experiments; defaults are the measured best) -------------
+static int g_fwd_cfg = 1;   // 0: 128 threads, compiler-chosen registers   1: 128 x >=8 CTAs/SM   2: 128 x >=6   3: 256 x >=4
+static int g_fwd_stage = 0; // 1: narrow rows leave through shared memory as coalesced chunks
+static int g_bwd_cfg = 1;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)
+
+template <int DB, int DC, bool NB, bool NC, int NT, int MINB>
+static void launch_fwd_cfg(const FastParams& P, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
+                           cudaStream_t s) {
+  const unsigned grid = blocks_for(n, NT, (int64_t)sm_count() * 64);
+  if (P.W <= 32 && g_fwd_stage) {
+    const size_t smem = (size_t)(NT / 32) * 64 * P.W * sizeof(float);
+    fast_fwd_kernel<DB, DC, NB, NC, NT, MINB, true><<<grid, NT, smem, s>>>(P, x, n, n_dev, feats, coeff, basis);
+  } else {
+    fast_fwd_kernel<DB, DC, NB, NC, NT, MINB, false><<<grid, NT, 0, s>>>(P, x, n, n_dev, feats, coeff, basis);
+  }
+}
+
+template <int DB, int DC, bool NB, bool NC>
+static void launch_fwd(const FastParams& P, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
+                       cudaStream_t s) {
+  switch (g_fwd_cfg) {
+    case 0: launch_fwd_cfg<DB, DC, NB, NC, 128, 1>(P, x, n, n_dev, feats, coeff, basis, s); break;
+    case 2: launch_fwd_cfg<DB, DC, NB, NC, 128, 6>(P, x, n, n_dev, feats, coeff, basis, s); break;
+    case 3: launch_fwd_cfg<DB, DC, NB, NC, 256, 4>(P, x, n, n_dev, feats, coeff, basis, s); break;
+    default: launch_fwd_cfg<DB, DC, NB, NC, 128, 8>(P, x, n, n_dev, feats, coeff, basis, s); break;
+  }
+}
+
+template <int DB, int DC, bool NB, bool NC>
+static void launch_bwd(const FastParams& P, const FastGrads& G, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
+                       const float* g_coeff, const float* coeff, const float* basis, cudaStream_t s) {
+  const int64_t cap = (int64_t)sm_count() * 64;
+  if (coeff && basis && g_bwd_cfg != 0) {
+    if (P.W <= 24)
+      fast_bwd_saved_kernel<DB, DC, NB, NC, 24, 128, 6><<<blocks_for(n, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis);
+    else
+      fast_bwd_saved_kernel<DB, DC, NB, NC, 0, 128, 6><<<blocks_for(n, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis);
+  } else {
+    fast_bwd_kernel<DB, DC, NB, NC><<<blocks_for(n, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff);
+  }
+}
+
+#define FAST_DISPATCH(FN, ...)                                                                                  \
   do {                                                                                                          \
     const bool nb = f->h.ops[f->h.bterms[0].op[0]].nearest, nc = f->h.ops[f->h.cterms[0].op[0]].nearest;        \
     const int db = P.in_dim, dc = P.xdim;                                                                       \
-    if (db == 3 && dc == 3 && !nb && !nc) KERNEL<3, 3, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__);         \
-    else if (db == 3 && dc == 3 && nb && nc) KERNEL<3, 3, true, true><<<grid, 128, 0, s>>>(__VA_ARGS__);        \
-    else if (db == 2 && dc == 2 && !nb && !nc) KERNEL<2, 2, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__);    \
-    else if (db == 2 && dc == 2 && nb && nc) KERNEL<2, 2, true, true><<<grid, 128, 0, s>>>(__VA_ARGS__);        \
-    else if (db == 2 && dc == 3 && !nb && !nc) KERNEL<2, 3, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__);    \
+    if (db == 3 && dc == 3 && !nb && !nc) FN<3, 3, false, false>(__VA_ARGS__);                                  \
+    else if (db == 3 && dc == 3 && nb && nc) FN<3, 3, true, true>(__VA_ARGS__);                                 \
+    else if (db == 2 && dc == 2 && !nb && !nc) FN<2, 2, false, false>(__VA_ARGS__);                             \
+    else if (db == 2 && dc == 2 && nb && nc) FN<2, 2, true, true>(__VA_ARGS__);                                 \
+    else if (db == 2 && dc == 3 && !nb && !nc) FN<2, 3, false, false>(__VA_ARGS__);                             \
     else { set_error("fast path: unsupported dim/mode combination"); return FFB_EINVAL; }                       \
   } while (0)
 
@@ -340,6 +541,15 @@ static bool mode_supported(ffb_field_t f, const FastParams& P) {
 
 extern "C" {
 
+int ffb_set_tuning(const char* key, int value) {
+  FFB_REQUIRE(key, "null key");
+  if (!strcmp(key, "field_fwd_cfg")) g_fwd_cfg = value;
+  else if (!strcmp(key, "field_bwd_cfg")) g_bwd_cfg = value;
+  else if (!strcmp(key, "field_fwd_stage")) g_fwd_stage = value;
+  else { set_error("ffb_set_tuning: unknown key %s", key); return FFB_EINVAL; }
+  return FFB_OK;
+}
+
 int ffb_field_fast_eligible(ffb_field_t f) {
   if (!f) return 0;
   FastParams P;
@@ -347,21 +557,25 @@ int ffb_field_fast_eligible(ffb_field_t f) {
   return (build_params(f->h, P, idx) && mode_supported(f, P)) ? 1 : 0;
 }
 
-int ffb_field_fast_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, void* stream) {
+int ffb_field_fast_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
+                             void* stream) {
   FFB_REQUIRE(f && x, "null argument");
   FastParams P;
   int idx[FAST_MAX_LEVELS + 1];
   FFB_REQUIRE(build_params(f->h, P, idx) && mode_supported(f, P), "descriptor is not eligible for the fast path");
   if (n <= 0) return FFB_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned grid = blocks_for(n, 128, sm_count() * 64);
-  FAST_DISPATCH(fast_fwd_kernel, P, x, n, n_dev, feats, coeff);
+  FAST_DISPATCH(launch_fwd, P, x, n, n_dev, feats, coeff, basis, s);
   FFB_LAUNCHED();
   return FFB_OK;
 }
 
-int ffb_field_fast_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
-                       float* const* h_grads, void* stream) {
+int ffb_field_fast_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, void* stream) {
+  return ffb_field_fast_fwd_train(f, x, n, n_dev, feats, coeff, nullptr, stream);
+}
+
+int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                             const float* coeff, const float* basis, float* const* h_grads, void* stream) {
   FFB_REQUIRE(f && x, "null argument");
   FastParams P;
   int idx[FAST_MAX_LEVELS + 1];
@@ -369,12 +583,21 @@ int ffb_field_fast_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* 
   if (n <= 0) return FFB_OK;
   FastGrads G;
   G.c = h_grads ? h_grads[idx[0]] : f->h.ops[idx[0]].grad;
-  for (int l = 0; l < FAST_MAX_LEVELS; ++l) G.b[l] = l < P.n_levels ? (h_grads ? h_grads[idx[l + 1]] : f->h.ops[idx[l + 1]].grad) : nullptr;
+  bool aligned = ((uintptr_t)G.c & 15) == 0;
+  for (int l = 0; l < FAST_MAX_LEVELS; ++l) {
+    G.b[l] = l < P.n_levels ? (h_grads ? h_grads[idx[l + 1]] : f->h.ops[idx[l + 1]].grad) : nullptr;
+    aligned = aligned && ((uintptr_t)G.b[l] & 15) == 0;
+  }
+  FFB_REQUIRE(aligned, "gradient tensors must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned grid = blocks_for(n, 128, sm_count() * 64);
-  FAST_DISPATCH(fast_bwd_kernel, P, G, x, n, n_dev, g_feats, g_coeff);
+  FAST_DISPATCH(launch_bwd, P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis, s);
   FFB_LAUNCHED();
   return FFB_OK;
+}
+
+int ffb_field_fast_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                       float* const* h_grads, void* stream) {
+  return ffb_field_fast_bwd_saved(f, x, n, n_dev, g_feats, g_coeff, nullptr, nullptr, h_grads, stream);
 }
 
 }  // extern "C"

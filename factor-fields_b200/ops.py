@@ -72,6 +72,7 @@ class FieldPlan:
         self.handle = C.c_void_p()
         nv.check(nv.lib().ffb_field_create(C.byref(desc), C.byref(self.handle)))
         self.ptrs = [t.data_ptr() if t is not None else 0 for t in tensors]
+        self.fast = nv.lib().ffb_field_fast_eligible(self.handle) == 1   # specialised grid x grid kernels apply
 
     def stale(self):
         return any((t.data_ptr() if t is not None else 0) != p for t, p in zip(self.tensors, self.ptrs))
@@ -160,18 +161,29 @@ class FieldQuery(torch.autograd.Function):
         n = x.shape[0]
         feats = _empty((n, plan.width), x)
         coeff = _empty((n, plan.width), x)
+        # training: also keep the basis row, so the backward pass scatters without re-gathering
+        train = plan.fast and any(ctx.needs_input_grad[3:])
+        basis = _empty((n, plan.width), x) if train else None
         if n > 0:
             with nv.section('field_fwd'):
-                nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(n_dev), nv.ptr(feats), nv.ptr(coeff),
-                                                      nv.stream()))
-        ctx.plan, ctx.n_dev = plan, n_dev
-        ctx.save_for_backward(x)
+                if train:
+                    nv.check(nv.lib().ffb_field_query_fwd_train(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(n_dev), nv.ptr(feats),
+                                                                nv.ptr(coeff), nv.ptr(basis), nv.stream()))
+                else:
+                    nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(n_dev), nv.ptr(feats), nv.ptr(coeff),
+                                                          nv.stream()))
+        ctx.plan, ctx.n_dev, ctx.train = plan, n_dev, train
+        if train:
+            ctx.save_for_backward(x, coeff, basis)
+        else:
+            ctx.save_for_backward(x)
         return feats, coeff
 
     @staticmethod
     def backward(ctx, g_feats, g_coeff):
         plan = ctx.plan
-        (x,) = ctx.saved_tensors
+        x = ctx.saved_tensors[0]
+        coeff, basis = (ctx.saved_tensors[1], ctx.saved_tensors[2]) if ctx.train else (None, None)
         n = x.shape[0]
         # one gradient tensor per distinct factor tensor (an op list may reference a tensor once only)
         grads = []
@@ -188,8 +200,9 @@ class FieldQuery(torch.autograd.Function):
             gf = g_feats.contiguous() if g_feats is not None else None
             gc = g_coeff.contiguous() if g_coeff is not None else None
             with nv.section('field_bwd'):
-                nv.check(nv.lib().ffb_field_query_bwd(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(ctx.n_dev),
-                                                      nv.ptr(gf, allow_none=True), nv.ptr(gc, allow_none=True), arr, nv.stream()))
+                nv.check(nv.lib().ffb_field_query_bwd_saved(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(ctx.n_dev),
+                                                            nv.ptr(gf, allow_none=True), nv.ptr(gc, allow_none=True),
+                                                            nv.ptr(coeff, allow_none=True), nv.ptr(basis, allow_none=True), arr, nv.stream()))
         return (None, None, None, *grads)
 
 

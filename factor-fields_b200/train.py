@@ -22,8 +22,8 @@ class GradBucket:
         self.params = [p for p in params]
         self.sizes = [p.numel() for p in self.params]
         self.offsets = [0]
-        for n in self.sizes:
-            self.offsets.append(self.offsets[-1] + n)
+        for n in self.sizes:      # every slice starts on a 256-byte boundary (the scatter kernels use 16-byte vector reductions)
+            self.offsets.append((self.offsets[-1] + n + 63) // 64 * 64)
         dev = self.params[0].device
         self.flat = torch.zeros(self.offsets[-1], device=dev, dtype=torch.float32)
 

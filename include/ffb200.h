@@ -106,6 +106,15 @@ int ffb_field_query_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t*
  * tensor), or NULL to use ops[i].grad of the descriptor.  g_coeff may be NULL. */
 int ffb_field_query_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
                         const float* g_feats, const float* g_coeff, float* const* h_grads, void* stream);
+/* Training pair: the forward also stores the concatenated basis row `basis` [n, W]; the backward then needs no
+ * re-gather — it reads the saved `coeff` / `basis` rows, recomputes only the tap indices and weights, and issues the
+ * scatter as 16-byte vector reductions.  Fields outside the specialised grid x grid kernels fall back to
+ * ffb_field_query_bwd's behaviour (coeff / basis are then ignored). */
+int ffb_field_query_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
+                              float* feats, float* coeff, float* basis, void* stream);
+int ffb_field_query_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
+                              const float* g_feats, const float* g_coeff, const float* coeff,
+                              const float* basis, float* const* h_grads, void* stream);
 /* grid_mapping (:11-33) on its own: x [n, in_dim] -> out [n, in_dim, F] (trig: [n, in_dim, 2F]). */
 int ffb_grid_mapping(const float* x, int64_t n, int32_t in_dim, const float* h_aabb_min,
                      const float* h_aabb_max, const float* h_freq, int32_t n_freq, int32_t mapping,
@@ -118,6 +127,13 @@ int ffb_field_fast_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* 
                        float* coeff, void* stream);
 int ffb_field_fast_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
                        const float* g_feats, const float* g_coeff, float* const* h_grads, void* stream);
+int ffb_field_fast_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,
+                             float* coeff, float* basis, void* stream);
+int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
+                             const float* g_feats, const float* g_coeff, const float* coeff,
+                             const float* basis, float* const* h_grads, void* stream);
+/* Experiment knobs (launch configurations of the field kernels): "field_fwd_cfg", "field_bwd_cfg". */
+int ffb_set_tuning(const char* key, int value);
 /* The descriptor-driven generic kernels, callable directly (parity tests compare both paths).
  * basis_out: optional [n, W] copy of the (re-ordered) basis row. */
 int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,
