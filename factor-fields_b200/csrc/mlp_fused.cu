@@ -1,0 +1,561 @@
+// mlp_fused.cu — whole decoder MLPs per launch on the 5th-generation tensor cores.
+//
+// ffb_mlp2_fwd / ffb_mlp2_bwd: the 2-layer MLPMixer (FactorFields.py:113-159 with pe = 0:  Linear(K0->H) + bias,
+// ReLU, Linear(H->N) without bias) — `linear_mat`, which runs on EVERY field query, so its activation traffic is what
+// matters: the per-layer kernels (mlp_tc.cu) move the [n, H] hidden activation through HBM seven times per training
+// step; here it never leaves the SM.
+//   forward : x tile -> smem (bf16 x3 split) -> MMA -> TMEM -> ReLU -> smem -> MMA -> TMEM -> y
+//   backward: recomputes the hidden tile (one extra small MMA) instead of reading a saved copy, then forms
+//             g_h = (g_y W2) .* [h > 0],  g_x = g_h W1,  gW2 += h^T g_y,  gW1 += g_h^T x,  gb1 += colsum(g_h)
+//             with the weight gradients accumulating in TMEM across all tiles of the CTA (one atomic flush at the end).
+// The ReLU decision is taken once: the forward kernel stores one bit per hidden unit (uint16 per 16 columns) and the
+// backward kernel masks with those bits, so forward and backward agree exactly (a recomputed hidden value a few ulps
+// from zero could otherwise flip).  The layer-1 bias rides in the GEMM: x gets an all-ones column at index K0 and W1 a matching column holding b1 — the
+// same column yields gb1 in the weight-gradient GEMM.
+//
+// Precision: operands are split into bf16 parts (tc_common.cuh): 3 parts / 6 MMAs per product in the forward pass
+// (~3e-7 relative: its density output feeds exp() in the compositor), 2 parts / 3 MMAs for gradients (~5e-6).
+// Operand tiles are staged once and used in both K-major and MN-major roles (see tc_common.cuh).
+#include "tc_common.cuh"
+#include "ffb_math.h"
+
+namespace ffb {
+
+constexpr uint32_t TILE_SR = 128;   // bytes between 8-row groups inside one 8-column chunk
+
+__device__ __forceinline__ uint64_t desc_k(uint32_t base, uint32_t sc, int kslice) {   // M/N = tile rows, K = tile cols
+  return make_desc(base + (uint32_t)kslice * 2u * sc, sc, TILE_SR);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t base, uint32_t sc, int kslice) {  // M/N = tile cols, K = tile rows
+  return make_desc(base + (uint32_t)kslice * 2u * TILE_SR, TILE_SR, sc);
+}
+
+// Stage a [rows x 8*nchunks] fp32 block as TERMS bf16 operand tiles (tile column chunk stride sc = tile_rows*16).
+// Warp-cooperative: a warp owns an 8-row group at a time; lane = (rr = lane>>2: row in the group, q = lane&3: column
+// pair 2q, 2q+1 of an 8-wide chunk), so one store instruction writes 128 contiguous bytes.
+template <int TERMS, class Load>
+__device__ __forceinline__ void stage_tile(uint8_t* dst, uint32_t part_bytes, uint32_t sc, int rows, int nchunks, int warp, int nwarps,
+                                           int lane, Load load) {
+  const int rr = lane >> 2, q = lane & 3;
+  const int items = (rows >> 3) * nchunks;                 // (row group, column chunk) pairs
+  constexpr int BATCH = 8;
+  for (int it0 = warp * BATCH; it0 < items; it0 += nwarps * BATCH) {
+    float2 v[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const int it = it0 + b;
+      v[b] = make_float2(0.f, 0.f);
+      if (it < items) v[b] = load((it / nchunks) * 8 + rr, (it % nchunks) * 8 + 2 * q);
+    }
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const int it = it0 + b;
+      if (it < items) {
+        uint8_t* p = dst + (uint32_t)(it % nchunks) * sc + (uint32_t)(it / nchunks) * TILE_SR + (uint32_t)rr * 16u + (uint32_t)q * 4u;
+#pragma unroll
+        for (int t = 0; t < TERMS; ++t) {
+          const __nv_bfloat16 a = __float2bfloat16_rn(v[b].x), c = __float2bfloat16_rn(v[b].y);
+          v[b].x -= __bfloat162float(a);
+          v[b].y -= __bfloat162float(c);
+          __nv_bfloat162 ac = __halves2bfloat162(a, c);
+          *reinterpret_cast<uint32_t*>(p + (uint32_t)t * part_bytes) = *reinterpret_cast<uint32_t*>(&ac);
+        }
+      }
+    }
+  }
+}
+
+// The same staging split in two halves, so the global loads of the NEXT tile can be in flight while the current tile
+// is computed: tile_load fills NB float2 registers per lane, tile_store converts and writes them.
+template <int NB, class Load>
+__device__ __forceinline__ void tile_load(float2 v[NB], int rows, int nchunks, int warp, int nwarps, int lane, Load load) {
+  const int rr = lane >> 2, q = lane & 3, items = (rows >> 3) * nchunks;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int it = warp + nwarps * b;
+    v[b] = make_float2(0.f, 0.f);
+    if (it < items) v[b] = load((it / nchunks) * 8 + rr, (it % nchunks) * 8 + 2 * q);
+  }
+}
+template <int TERMS, int NB>
+__device__ __forceinline__ void tile_store(float2 v[NB], uint8_t* dst, uint32_t part_bytes, uint32_t sc, int rows, int nchunks, int warp,
+                                           int nwarps, int lane) {
+  const int rr = lane >> 2, q = lane & 3, items = (rows >> 3) * nchunks;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int it = warp + nwarps * b;
+    if (it < items) {
+      uint8_t* p = dst + (uint32_t)(it % nchunks) * sc + (uint32_t)(it / nchunks) * TILE_SR + (uint32_t)rr * 16u + (uint32_t)q * 4u;
+#pragma unroll
+      for (int t = 0; t < TERMS; ++t) {
+        const __nv_bfloat16 a = __float2bfloat16_rn(v[b].x), c = __float2bfloat16_rn(v[b].y);
+        v[b].x -= __bfloat162float(a);
+        v[b].y -= __bfloat162float(c);
+        __nv_bfloat162 ac = __halves2bfloat162(a, c);
+        *reinterpret_cast<uint32_t*>(p + (uint32_t)t * part_bytes) = *reinterpret_cast<uint32_t*>(&ac);
+      }
+    }
+  }
+}
+
+// thread-per-row store of 8 consecutive columns (c0 % 8 == 0) of an activation tile
+template <int TERMS>
+__device__ __forceinline__ void store_row8(uint8_t* dst, uint32_t part_bytes, uint32_t sc, int r, int c0, const float v[8]) {
+  uint4 parts[TERMS];
+  split8_parts<TERMS>(v, parts);
+  uint8_t* p = dst + (uint32_t)(c0 >> 3) * sc + (uint32_t)(r >> 3) * TILE_SR + (uint32_t)(r & 7) * 16u;
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint4*>(p + (uint32_t)t * part_bytes) = parts[t];
+}
+
+// D (+)= A * B^T with every kept cross term of the bf16 split: parts (ta, tb) with ta + tb < TERMS
+template <int TERMS, class DA, class DB>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t idesc, int kslices, bool accumulate, DA da, DB db) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  for (int s = 0; s < kslices; ++s) {
+#pragma unroll
+    for (int ta = 0; ta < TERMS; ++ta)
+#pragma unroll
+      for (int tb = 0; tb < TERMS; ++tb) {
+        if (ta + tb >= TERMS) continue;
+        umma_f16(tmem_d, da(ta, s), db(tb, s), idesc, acc);
+        acc = 1u;
+      }
+  }
+}
+
+struct Mlp2Shape {
+  int K0, H, N;       // logical sizes
+  int K0p, Np;        // padded to multiples of 16 (K0p includes the bias column)
+};
+
+// weights -> operand tiles (once per CTA).  W1 tile: rows j < H, cols k < K0p (col K0 = b1[j]);  W2 tile: rows n < Np, cols j < H
+template <int TERMS>
+__device__ __forceinline__ void stage_weights(const Mlp2Shape S, const float* __restrict__ W1, const float* __restrict__ b1,
+                                              const float* __restrict__ W2, uint8_t* sW1, uint8_t* sW2, int tid, int nthreads) {
+  const uint32_t szW1 = (uint32_t)S.H * S.K0p * 2, szW2 = (uint32_t)S.Np * S.H * 2;
+  const uint32_t scW1 = (uint32_t)S.H * 16, scW2 = (uint32_t)S.Np * 16;
+  for (int item = tid; item < S.H * (S.K0p / 8); item += nthreads) {
+    const int j = item % S.H, c = item / S.H;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = c * 8 + i;
+      v[i] = k < S.K0 ? __ldg(W1 + (int64_t)j * S.K0 + k) : ((k == S.K0 && b1) ? __ldg(b1 + j) : 0.0f);
+    }
+    store_row8<TERMS>(sW1, szW1, scW1, j, c * 8, v);
+  }
+  for (int item = tid; item < S.Np * (S.H / 8); item += nthreads) {
+    const int nn = item % S.Np, c = item / S.Np;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = nn < S.N ? __ldg(W2 + (int64_t)nn * S.H + c * 8 + i) : 0.0f;
+    store_row8<TERMS>(sW2, szW2, scW2, nn, c * 8, v);
+  }
+}
+
+// x rows with the all-ones bias column at index K0 (rows beyond n are zero, including that column)
+struct XLoader {
+  const float* x;
+  int64_t row0, n;
+  int K0;
+  bool vec2;
+  __device__ __forceinline__ float2 operator()(int r, int c) const {
+    const int64_t row = row0 + r;
+    float2 v = make_float2(0.f, 0.f);
+    if (row < n) {
+      if (c + 1 < K0) {
+        if (vec2) v = *reinterpret_cast<const float2*>(x + row * K0 + c);
+        else { v.x = x[row * K0 + c]; v.y = x[row * K0 + c + 1]; }
+      } else {
+        v.x = c < K0 ? x[row * K0 + c] : (c == K0 ? 1.0f : 0.0f);
+        v.y = c + 1 < K0 ? x[row * K0 + c + 1] : (c + 1 == K0 ? 1.0f : 0.0f);
+      }
+    }
+    return v;
+  }
+};
+__device__ __forceinline__ XLoader x_loader(const Mlp2Shape& S, const float* x, int64_t row0, int64_t n) {
+  return XLoader{x, row0, n, S.K0, ((S.K0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)};
+}
+// generic row-major [n, N] block (columns beyond N and rows beyond n read as zero)
+struct RowLoader {
+  const float* g;
+  int64_t row0, n;
+  int N;
+  bool vec2;
+  __device__ __forceinline__ float2 operator()(int r, int c) const {
+    const int64_t row = row0 + r;
+    float2 v = make_float2(0.f, 0.f);
+    if (row < n && c < N) {
+      if (vec2 && c + 1 < N) v = *reinterpret_cast<const float2*>(g + row * N + c);
+      else { v.x = g[row * N + c]; if (c + 1 < N) v.y = g[row * N + c + 1]; }
+    }
+    return v;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+template <int TERMS, bool PREFETCH>
+__global__ void __launch_bounds__(256, 2) mlp2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ b1,
+                                                          const float* __restrict__ W2, float* __restrict__ y, uint16_t* __restrict__ mask,
+                                                          int64_t n, const int32_t* __restrict__ n_dev, const Mlp2Shape S, int tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  n = resolve_n(n, n_dev);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const uint32_t szW1 = (uint32_t)S.H * S.K0p * 2, szW2 = (uint32_t)S.Np * S.H * 2, szX = 128u * S.K0p * 2, szH = 128u * S.H * 2;
+  const uint32_t scW1 = (uint32_t)S.H * 16, scW2 = (uint32_t)S.Np * 16;
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = sW1 + TERMS * szW1;
+  uint8_t* sX = sW2 + TERMS * szW2;
+  uint8_t* sH = sX + TERMS * szX;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sH + TERMS * szH);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) mbar_init(bar, 1);
+  stage_weights<TERMS>(S, W1, b1, W2, sW1, sW2, tid, blockDim.x);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t d1 = tmem, d2 = tmem + (uint32_t)S.H;
+  const uint32_t idesc1 = make_idesc(S.H, 0, 0), idesc2 = make_idesc(S.Np, 0, 0);
+  const uint32_t aX = smem_u32(sX), aH = smem_u32(sH), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2);
+  const int rloc = (warp & 3) * 32 + lane, half = warp >> 2;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int64_t n_tiles = (n + 127) / 128;
+  const int xchunks = S.K0p / 8;
+  constexpr int NB = 8;     // PREFETCH: 16 row groups x (K0p/8 <= 4) chunks over 8 warps
+  float2 pre[NB];
+  if (PREFETCH && (int64_t)blockIdx.x < n_tiles) tile_load<NB>(pre, 128, xchunks, warp, nwarps, lane, x_loader(S, x, (int64_t)blockIdx.x * 128, n));
+  uint32_t phase = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * 128;
+    if (PREFETCH) tile_store<TERMS, NB>(pre, sX, szX, 2048u, 128, xchunks, warp, nwarps, lane);
+    else stage_tile<TERMS>(sX, szX, 2048u, 128, xchunks, warp, nwarps, lane, x_loader(S, x, row0, n));
+    proxy_fence();
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        tc_fence_after();
+        issue_gemm<TERMS>(d1, idesc1, S.K0p / 16, false, [&](int t, int s) { return desc_k(aX + t * szX, 2048u, s); },
+                          [&](int t, int s) { return desc_k(aW1 + t * szW1, scW1, s); });
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    // the next tile's rows travel while this tile is computed
+    if (PREFETCH && tile + gridDim.x < n_tiles) tile_load<NB>(pre, 128, xchunks, warp, nwarps, lane, x_loader(S, x, (tile + gridDim.x) * 128, n));
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    const int64_t row = row0 + rloc;
+    // hidden activation: TMEM -> ReLU (+ the decision bits for the backward pass) -> bf16 parts -> operand tile of GEMM 2
+    for (int c0 = half * 16; c0 < S.H; c0 += 32) {
+      float v[16];
+      tmem_ld16(d1 + lane_base + (uint32_t)c0, v);
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        bits |= (v[i] > 0.0f ? 1u : 0u) << i;
+        v[i] = fmaxf(v[i], 0.0f);
+      }
+      if (mask && row < n) mask[row * (S.H >> 4) + (c0 >> 4)] = (uint16_t)bits;
+      store_row8<TERMS>(sH, szH, 2048u, rloc, c0, v);
+      store_row8<TERMS>(sH, szH, 2048u, rloc, c0 + 8, v + 8);
+    }
+    tc_fence_before();
+    proxy_fence();
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        tc_fence_after();
+        issue_gemm<TERMS>(d2, idesc2, S.H / 16, false, [&](int t, int s) { return desc_k(aH + t * szH, 2048u, s); },
+                          [&](int t, int s) { return desc_k(aW2 + t * szW2, scW2, s); });
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    for (int c0 = half * 16; c0 < S.Np; c0 += 32) {
+      float v[16];
+      tmem_ld16(d2 + lane_base + (uint32_t)c0, v);
+      if (row < n) {
+        float* yr = y + row * S.N + c0;
+        if ((S.N & 3) == 0 && c0 + 16 <= S.N) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yr + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < S.N) yr[i] = v[i];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // all TMEM reads done before the next tile's MMAs overwrite the accumulators
+  }
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward (H == 64).  Shared-memory tiles (2 bf16 parts each, 128 rows, column chunk stride 2048 B):
+//   tile A2 = [ h | g_h ]   (2H = 128 columns)      tile B2 = [ g_y | x ]   (Np + K0p columns)
+// so that ONE accumulator  DW[128, Np+K0p] += A2^T B2  (both read MN-major, reduction over the 128 rows) carries
+// gW2^T in rows 0..63 x columns 0..Np-1 and [gW1 | gb1] in rows 64..127 x columns Np.. (the two off-diagonal blocks
+// are by-products nobody reads) — half the MMA instructions of two separate M = 64 products.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) mlp2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ W1,
+                                                          const float* __restrict__ b1, const float* __restrict__ W2,
+                                                          const uint16_t* __restrict__ mask, float* __restrict__ gx, float* __restrict__ gW1,
+                                                          float* __restrict__ gb1, float* __restrict__ gW2, int64_t n,
+                                                          const int32_t* __restrict__ n_dev, const Mlp2Shape S, int tmem_cols) {
+  constexpr int TERMS = 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  n = resolve_n(n, n_dev);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int H = S.H, NB2 = S.Np + S.K0p;                                // NB2: columns of tile B2
+  const uint32_t szW1 = (uint32_t)H * S.K0p * 2, szW2 = (uint32_t)S.Np * H * 2, szA2 = 128u * 2u * H * 2, szB2 = 128u * NB2 * 2;
+  const uint32_t scW1 = (uint32_t)H * 16, scW2 = (uint32_t)S.Np * 16;
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = sW1 + TERMS * szW1;
+  uint8_t* sB2 = sW2 + TERMS * szW2;
+  uint8_t* sA2 = sB2 + TERMS * szB2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sA2 + TERMS * szA2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const uint32_t offX = (uint32_t)(S.Np / 8) * 2048u, offGH = (uint32_t)(H / 8) * 2048u;   // x inside B2, g_h inside A2
+
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) mbar_init(bar, 1);
+  stage_weights<TERMS>(S, W1, b1, W2, sW1, sW2, tid, blockDim.x);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t d1 = tmem, d2 = d1 + (uint32_t)H, d3 = d2 + (uint32_t)H, dW = d3 + (uint32_t)S.K0p;
+  const uint32_t id_h = make_idesc(H, 0, 0);                   // D1 = X    W1^T  (K-major x K-major)
+  const uint32_t id_gh = make_idesc(H, 0, 1);                  // D2 = GY   W2    (B = W2 tile read MN-major)
+  const uint32_t id_gx = make_idesc(S.K0p, 0, 1);              // D3 = GH   W1    (B = W1 tile read MN-major)
+  const uint32_t id_w = make_idesc(NB2, 1, 1, 128);            // DW = A2^T B2    (both read MN-major)
+  const uint32_t aA2 = smem_u32(sA2), aB2 = smem_u32(sB2), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2);
+  const int rloc = (warp & 3) * 32 + lane, half = warp >> 2;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const bool vecG = ((S.N & 1) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 7) == 0);
+  const int64_t n_tiles = (n + 127) / 128;
+  uint32_t phase = 0;
+  bool any = false;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * 128;
+    stage_tile<TERMS>(sB2, szB2, 2048u, 128, S.Np / 8, warp, nwarps, lane, RowLoader{gy, row0, n, S.N, vecG});
+    stage_tile<TERMS>(sB2 + offX, szB2, 2048u, 128, S.K0p / 8, warp, nwarps, lane, x_loader(S, x, row0, n));
+    proxy_fence();
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        tc_fence_after();
+        issue_gemm<TERMS>(d1, id_h, S.K0p / 16, false, [&](int t, int s) { return desc_k(aB2 + offX + t * szB2, 2048u, s); },
+                          [&](int t, int s) { return desc_k(aW1 + t * szW1, scW1, s); });
+        issue_gemm<TERMS>(d2, id_gh, S.Np / 16, false, [&](int t, int s) { return desc_k(aB2 + t * szB2, 2048u, s); },
+                          [&](int t, int s) { return desc_mn(aW2 + t * szW2, scW2, s); });
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    const int64_t row = row0 + rloc;
+    for (int c0 = half * 16; c0 < H; c0 += 32) {
+      float h[16], g[16];
+      tmem_ld16(d1 + lane_base + (uint32_t)c0, h);
+      tmem_ld16(d2 + lane_base + (uint32_t)c0, g);
+      uint32_t bits;
+      if (mask) {
+        bits = row < n ? (uint32_t)mask[row * (H >> 4) + (c0 >> 4)] : 0u;    // the forward pass's ReLU decisions
+      } else {
+        bits = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bits |= (h[i] > 0.0f ? 1u : 0u) << i;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const bool on = (bits >> i) & 1u;
+        g[i] = on ? g[i] : 0.0f;
+        h[i] = on ? fmaxf(h[i], 0.0f) : 0.0f;
+      }
+      store_row8<TERMS>(sA2, szA2, 2048u, rloc, c0, h);
+      store_row8<TERMS>(sA2, szA2, 2048u, rloc, c0 + 8, h + 8);
+      store_row8<TERMS>(sA2 + offGH, szA2, 2048u, rloc, c0, g);
+      store_row8<TERMS>(sA2 + offGH, szA2, 2048u, rloc, c0 + 8, g + 8);
+    }
+    tc_fence_before();
+    proxy_fence();
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        tc_fence_after();
+        issue_gemm<TERMS>(d3, id_gx, H / 16, false, [&](int t, int s) { return desc_k(aA2 + offGH + t * szA2, 2048u, s); },
+                          [&](int t, int s) { return desc_mn(aW1 + t * szW1, scW1, s); });
+        issue_gemm<TERMS>(dW, id_w, 8, any, [&](int t, int s) { return desc_mn(aA2 + t * szA2, 2048u, s); },
+                          [&](int t, int s) { return desc_mn(aB2 + t * szB2, 2048u, s); });
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    any = true;
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (gx) {
+      for (int c0 = half * 16; c0 < S.K0p; c0 += 32) {
+        float v[16];
+        tmem_ld16(d3 + lane_base + (uint32_t)c0, v);
+        if (row < n) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            if (c0 + i + 1 < S.K0 && (S.K0 & 1) == 0) *reinterpret_cast<float2*>(gx + row * S.K0 + c0 + i) = make_float2(v[i], v[i + 1]);
+            else {
+              if (c0 + i < S.K0) gx[row * S.K0 + c0 + i] = v[i];
+              if (c0 + i + 1 < S.K0) gx[row * S.K0 + c0 + i + 1] = v[i + 1];
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  // ---- flush the weight gradients: accumulator row m = lane (M = 128): m < 64 -> gW2^T row j = m; m >= 64 -> [gW1 | gb1] row j = m - 64
+  if (any) {
+    tc_fence_after();
+    const int m = rloc;
+    for (int c0 = half * 16; c0 < NB2; c0 += 32) {
+      float v[16];
+      tmem_ld16(dW + lane_base + (uint32_t)c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        if (v[i] == 0.0f) continue;
+        if (m < H) {
+          if (c < S.N && gW2) atomicAdd(gW2 + (int64_t)c * H + m, v[i]);
+        } else if (c >= S.Np) {
+          const int k = c - S.Np, j = m - H;
+          if (k < S.K0) { if (gW1) atomicAdd(gW1 + (int64_t)j * S.K0 + k, v[i]); }
+          else if (k == S.K0 && gb1) atomicAdd(gb1 + j, v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+static int fused_enabled = 1;
+
+static int smem_optin() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  return v;
+}
+static int pow2_cols32(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+static bool mlp2_plan(int K0, int H, int N, Mlp2Shape* S, size_t* smem_fwd, size_t* smem_bwd, int* cols_fwd, int* cols_bwd) {
+  if (K0 < 1 || N < 1 || H != 64) return false;     // the backward kernel stacks [h | g_h] into one M = 128 operand
+  S->K0 = K0; S->H = H; S->N = N;
+  S->K0p = (K0 + 1 + 15) / 16 * 16;
+  S->Np = (N + 15) / 16 * 16;
+  if (S->K0p > 256 || S->Np > 256) return false;
+  const size_t w = (size_t)H * S->K0p * 2 + (size_t)S->Np * H * 2;
+  *smem_fwd = 3 * (w + (size_t)128 * S->K0p * 2 + (size_t)128 * H * 2) + 64;
+  *smem_bwd = 2 * (w + (size_t)128 * S->K0p * 2 + (size_t)128 * S->Np * 2 + (size_t)2 * 128 * H * 2) + 64;
+  if (S->Np + S->K0p > 256) return false;
+  const int cf = H + S->Np, cb = 2 * H + 2 * S->K0p + S->Np;
+  if (cf > 512 || cb > 512) return false;
+  *cols_fwd = pow2_cols32(cf);
+  *cols_bwd = pow2_cols32(cb);
+  return *smem_fwd <= (size_t)smem_optin() && *smem_bwd <= (size_t)smem_optin();
+}
+static unsigned persistent_grid(int64_t n, size_t smem, int cols) {
+  int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+  if (per_sm > 512 / cols) per_sm = 512 / cols;
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = (n + 127) / 128;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > tiles) grid = tiles;
+  return (unsigned)(grid < 1 ? 1 : grid);
+}
+
+}  // namespace ffb
+
+using namespace ffb;
+
+extern "C" {
+
+int ffb_set_fused_mlp(int enabled) {
+  fused_enabled = enabled ? 1 : 0;
+  return FFB_OK;
+}
+
+int ffb_mlp2_eligible(int32_t K0, int32_t H, int32_t N) {
+  if (!fused_enabled || !ffb_tensor_cores_enabled()) return 0;
+  Mlp2Shape S;
+  size_t sf, sb;
+  int cf, cb;
+  return mlp2_plan(K0, H, N, &S, &sf, &sb, &cf, &cb) ? 1 : 0;
+}
+
+int ffb_mlp2_fwd(const float* x, const float* W1, const float* b1, const float* W2, float* y, uint16_t* relu_mask, int64_t n,
+                 const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream) {
+  FFB_REQUIRE(x && W1 && W2 && y, "null argument");
+  Mlp2Shape S;
+  size_t sf, sb;
+  int cf, cb;
+  FFB_REQUIRE(mlp2_plan(K0, H, N, &S, &sf, &sb, &cf, &cb), "MLP shape not eligible for the fused tensor-core path");
+  if (n <= 0) return FFB_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FFB_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin()));
+    FFB_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin()));
+    attr_done = true;
+  }
+  if (S.K0p <= 32)
+    mlp2_fwd_kernel<3, true><<<persistent_grid(n, sf, cf), 256, sf, (cudaStream_t)stream>>>(x, W1, b1, W2, y, relu_mask, n, n_dev, S, cf);
+  else
+    mlp2_fwd_kernel<3, false><<<persistent_grid(n, sf, cf), 256, sf, (cudaStream_t)stream>>>(x, W1, b1, W2, y, relu_mask, n, n_dev, S, cf);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_mlp2_bwd(const float* x, const float* gy, const float* W1, const float* b1, const float* W2, const uint16_t* relu_mask, float* gx,
+                 float* gW1, float* gb1, float* gW2, int64_t n, const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream) {
+  FFB_REQUIRE(x && gy && W1 && W2, "null argument");
+  Mlp2Shape S;
+  size_t sf, sb;
+  int cf, cb;
+  FFB_REQUIRE(mlp2_plan(K0, H, N, &S, &sf, &sb, &cf, &cb), "MLP shape not eligible for the fused tensor-core path");
+  if (n <= 0) return FFB_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FFB_CUDA(cudaFuncSetAttribute(mlp2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin()));
+    attr_done = true;
+  }
+  mlp2_bwd_kernel<<<persistent_grid(n, sb, cb), 256, sb, (cudaStream_t)stream>>>(x, gy, W1, b1, W2, relu_mask, gx, gW1, gb1, gW2, n, n_dev, S, cb);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// tc_common.cuh — tcgen05 / TMEM / mbarrier primitives (inline PTX) and the bf16-split helpers shared by the
+// tensor-core MLP kernels (mlp_tc.cu: one layer per launch; mlp_fused.cu: whole decoder MLPs per launch).
+//
+// Shared-memory operand tiles use the canonical NO-SWIZZLE UMMA layout built from 8x8 bf16 core matrices (128
+// contiguous bytes, 16 bytes per row).  For a tile of R rows x C columns, element (r, c) lives at
+//     (r/8)*SR + (c/8)*SC + (r%8)*16 + (c%8)*2
+// and the SAME bytes serve two roles:
+//   * K-major operand  (M/N index = r, K index = c): descriptor LBO = SC, SBO = SR, one K=16 slice = 2*SC bytes;
+//   * MN-major operand (M/N index = c, K index = r): descriptor LBO = SR, SBO = SC, one K=16 slice = 2*SR bytes
+// (LBO is always the stride between core matrices along K, SBO along M/N), which is what lets the backward kernels
+// use one staged activation tile both as the A operand of the input-gradient GEMM and, transposed, as an operand of
+// the weight-gradient GEMM.
+#pragma once
+#include <cuda_bf16.h>
+#include "ffb_common.cuh"
+
+namespace ffb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive columns (fp32) of this warp's TMEM lane quarter
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | 1<<46
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// Instruction descriptor for kind::f16: D=f32, A=B=bf16, M=128, N=n; major bits: 0 = K-major, 1 = MN-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn, int m = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+
+// x = p0 + p1 (+ p2) + O(2^-9*TERMS x): round-to-nearest bf16 parts of an fp32 value
+template <int TERMS>
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 out[TERMS]) {
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+    out[t] = __float2bfloat16_rn(v);
+    v -= __bfloat162float(out[t]);
+  }
+}
+
+// 8 consecutive fp32 values -> one 16-byte chunk (8 bf16) per part
+template <int TERMS>
+__device__ __forceinline__ void split8_parts(const float x[8], uint4 out[TERMS]) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = x[i];
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16 a = __float2bfloat16_rn(r[2 * i]), b = __float2bfloat16_rn(r[2 * i + 1]);
+      r[2 * i] -= __bfloat162float(a);
+      r[2 * i + 1] -= __bfloat162float(b);
+      __nv_bfloat162 ab = __halves2bfloat162(a, b);
+      w[i] = *reinterpret_cast<uint32_t*>(&ab);
+    }
+    out[t] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+}  // namespace ffb

@@ -285,6 +285,21 @@ class MLPFunction(torch.autograd.Function):
         n, D = x.shape
         h = x
         ctx.n_dev = n_dev
+        ctx.fused = False
+        if (pe == 0 and len(layers) == 2 and layers[0][1] is not None and layers[1][1] is None and (n >= 1024 or n_dev is not None)
+                and nv.lib().ffb_mlp2_eligible(D, layers[0][0].shape[0], layers[1][0].shape[0]) == 1):
+            # whole MLP in one tcgen05 kernel; the hidden activation is recomputed by the backward kernel
+            (W1, b1), (W2, _) = layers
+            y = _empty((n, W2.shape[0]), x)
+            need_bwd = any(ctx.needs_input_grad)
+            relu_bits = torch.empty((n, W1.shape[0] // 16), device=x.device, dtype=torch.int16) if need_bwd else None
+            with nv.section('mlp_fwd'):
+                nv.check(nv.lib().ffb_mlp2_fwd(nv.ptr(x), nv.ptr(W1), nv.ptr(b1), nv.ptr(W2), nv.ptr(y), nv.ptr(relu_bits, torch.int16, True),
+                                               C.c_int64(n), nv.i32p(n_dev), D, W1.shape[0], W2.shape[0], nv.stream()))
+            ctx.fused, ctx.has_bias = True, has_bias
+            if need_bwd:
+                ctx.save_for_backward(x, *params, relu_bits)
+            return y
         if pe > 0:
             h = _empty((n, D + 2 * D * pe), x)
             if n > 0:
@@ -306,6 +321,20 @@ class MLPFunction(torch.autograd.Function):
     def backward(ctx, g):
         saved = ctx.saved_tensors
         x = saved[0]
+        if ctx.fused:
+            W1, b1, W2, relu_bits = saved[1:5]
+            needs = ctx.needs_input_grad
+            n, D = x.shape
+            gx = _empty((n, D), x) if needs[0] else None
+            gW1 = _grad_like(W1) if needs[4] else None
+            gb1 = _grad_like(b1) if needs[5] else None
+            gW2 = _grad_like(W2) if needs[6] else None
+            with nv.section('mlp_bwd'):
+                nv.check(nv.lib().ffb_mlp2_bwd(nv.ptr(x), nv.ptr(g.contiguous()), nv.ptr(W1), nv.ptr(b1), nv.ptr(W2), nv.ptr(relu_bits, torch.int16),
+                                               nv.ptr(gx, allow_none=True),
+                                               nv.ptr(gW1, allow_none=True), nv.ptr(gb1, allow_none=True), nv.ptr(gW2, allow_none=True),
+                                               C.c_int64(n), nv.i32p(ctx.n_dev), D, W1.shape[0], W2.shape[0], nv.stream()))
+            return (gx, None, None, None, gW1, gb1, gW2)
         acts = list(saved[1:1 + ctx.n_acts])
         params = saved[1 + ctx.n_acts:]
         layers = _split_params(params, ctx.has_bias)

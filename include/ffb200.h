@@ -174,6 +174,22 @@ int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const
                              float* gb, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
                              void* stream);
 
+/* Whole 2-layer MLPMixer (:144-159 with pe = 0, no dropout) in one launch: y = relu(x W1^T + b1) W2^T.
+ * x [n,K0], W1 [H,K0], b1 [H] (may be NULL), W2 [N,H], y [n,N].  The hidden activation stays on the SM (TMEM / shared
+ * memory); the backward pass recomputes its values and takes the ReLU decisions from relu_mask [n, H/16] uint16 (bit i
+ * of word c = hidden unit 16c+i was positive), written by the forward pass (NULL: not written / re-decided).
+ * Eligible shapes: H == 64 and the operand tiles fit in shared memory (ffb_mlp2_eligible); everything else goes
+ * through the per-layer entry points above.
+ * ffb_mlp2_bwd: gx [n,K0] (may be NULL), gW1 [H,K0], gb1 [H], gW2 [N,H] are ACCUMULATED (+=), not zeroed. */
+int ffb_set_fused_mlp(int enabled);
+int ffb_mlp2_eligible(int32_t K0, int32_t H, int32_t N);
+int ffb_mlp2_fwd(const float* x, const float* W1, const float* b1, const float* W2, float* y,
+                 uint16_t* relu_mask, int64_t n, const int32_t* n_dev, int32_t K0, int32_t H, int32_t N,
+                 void* stream);
+int ffb_mlp2_bwd(const float* x, const float* gy, const float* W1, const float* b1, const float* W2,
+                 const uint16_t* relu_mask, float* gx, float* gW1, float* gb1, float* gW2, int64_t n,
+                 const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream);
+
 /* positional_encoding (:74-79) appended to the input: out [n, D + 2*D*pe] = [x, sin, cos]. */
 int ffb_pe_concat_fwd(const float* x, float* out, int64_t n, const int32_t* n_dev, int32_t D,
                       int32_t pe, void* stream);

@@ -66,9 +66,17 @@ def test_train_step_matches_eager_torch_adam(use_graph):
 
     assert int(mb.last_stats['n_app']) > 0, 'test scene shades nothing: the appearance MLP is not exercised'
     np.testing.assert_allclose(losses_b, losses_a, rtol=2e-5, atol=1e-7)
+    # Adam normalises each element's step by its own gradient scale, so where a gradient is within rounding noise of
+    # zero (|g| ~ eps) the step is +-lr whatever the implementation: run-to-run atomics order alone moves those
+    # elements.  Hence: all but a sliver of the elements must agree tightly, and none may differ by more than the
+    # largest possible drift (sum of the lrs used).
+    max_drift = sum(0.02 * decay ** i for i in range(steps)) * 2
     for (n, pa), pb in zip(ma.named_parameters(), mb.parameters()):
-        d = float((pa - pb).abs().max())
-        assert d < 2e-4 * max(1.0, float(pa.abs().max())), (n, d)
+        d = (pa - pb).abs().flatten()
+        tol = 2e-4 * max(1.0, float(pa.abs().max()))
+        frac_bad = float((d > tol).float().mean())
+        assert frac_bad < 2e-3, (n, frac_bad, float(d.max()))
+        assert float(d.max()) <= max_drift, (n, float(d.max()))
     # lr bookkeeping on the device equals the Python-side decay
     np.testing.assert_allclose(ts.lrs, [g['lr'] for g in opt.param_groups], rtol=1e-12)
 
