@@ -269,38 +269,53 @@ __global__ void pe_concat_bwd_kernel(const float* __restrict__ x, const float* _
   }
 }
 
-// MLPRender_Fea input: [features(C), viewdirs(3), PE(features, feape), PE(viewdirs, viewpe)]
-__global__ void render_input_fwd_kernel(const float* __restrict__ feat, int ld_feat, const float* __restrict__ rays,
-                                        const int32_t* __restrict__ ray_id, const int32_t* __restrict__ app_idx,
-                                        float* __restrict__ out, int64_t n, const int32_t* __restrict__ n_dev, int C, int viewpe, int feape) {
+// MLPRender_Fea input: [features(C), viewdirs(3), PE(features, feape), PE(viewdirs, viewpe)]   (FactorFields.py:190-196)
+// One work item = (row, input channel): ONE sincosf of the channel value, the higher octaves sin/cos(2^k v) by exact
+// angle doubling (sin 2a = 2 sa ca, cos 2a = (ca - sa)(ca + sa); each step at most doubles the rounding error: <= 2^5
+// ulp ~ 4e-6 absolute for viewpe = 6, far inside the 1e-4 bar) instead of 2*pe separate sinf / cosf range reductions.
+// A CTA assembles RIN_ROWS rows in shared memory and writes them out as one contiguous, fully coalesced block.
+constexpr int RIN_ROWS = 16;
+__global__ void __launch_bounds__(256) render_input_fwd_kernel(const float* __restrict__ feat, int ld_feat, const float* __restrict__ rays,
+                                                               const int32_t* __restrict__ ray_id, const int32_t* __restrict__ app_idx,
+                                                               float* __restrict__ out, int64_t n, const int32_t* __restrict__ n_dev, int C,
+                                                               int viewpe, int feape) {
+  extern __shared__ float rin[];
   n = resolve_n(n, n_dev);
   const int W = 3 + C + 6 * viewpe + 2 * feape * C;
-  const int oV = C, oPF = C + 3, oPV = C + 3 + 2 * feape * C;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * W; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = t / W;
-    const int c = (int)(t % W);
-    const int64_t i = app_idx ? app_idx[j] : j;
-    float v;
-    if (c < oV) {
-      v = feat[i * ld_feat + 1 + c];
-    } else if (c < oPF) {
-      const int64_t r = ray_id ? ray_id[i] : i;
-      v = rays[r * 6 + 3 + (c - oV)];
-    } else if (c < oPV) {
-      int e = c - oPF;
-      const bool is_cos = e >= C * feape;
-      if (is_cos) e -= C * feape;
-      const float a = FFB_MUL(feat[i * ld_feat + 1 + e / feape], (float)(1 << (e % feape)));
-      v = is_cos ? cosf(a) : sinf(a);
-    } else {
-      int e = c - oPV;
-      const bool is_cos = e >= 3 * viewpe;
-      if (is_cos) e -= 3 * viewpe;
-      const int64_t r = ray_id ? ray_id[i] : i;
-      const float a = FFB_MUL(rays[r * 6 + 3 + e / viewpe], (float)(1 << (e % viewpe)));
-      v = is_cos ? cosf(a) : sinf(a);
+  const int oV = C, oPF = C + 3, oPV = C + 3 + 2 * feape * C, nch = C + 3;
+  for (int64_t j0 = (int64_t)blockIdx.x * RIN_ROWS; j0 < n; j0 += (int64_t)gridDim.x * RIN_ROWS) {
+    const int rows = (int)((n - j0) < RIN_ROWS ? (n - j0) : RIN_ROWS);
+    for (int it = threadIdx.x; it < rows * nch; it += blockDim.x) {
+      const int r = it / nch, ch = it % nch;
+      const int64_t i = app_idx ? app_idx[j0 + r] : (j0 + r);
+      float* o = rin + r * W;
+      float v;
+      int pe, o_sin, o_cos;
+      if (ch < C) {
+        v = feat[i * ld_feat + 1 + ch];
+        o[ch] = v;
+        pe = feape; o_sin = oPF + ch * feape; o_cos = oPF + C * feape + ch * feape;
+      } else {
+        const int d = ch - C;
+        const int64_t rr = ray_id ? ray_id[i] : i;
+        v = rays[rr * 6 + 3 + d];
+        o[oV + d] = v;
+        pe = viewpe; o_sin = oPV + d * viewpe; o_cos = oPV + 3 * viewpe + d * viewpe;
+      }
+      float sa, ca;
+      sincosf(v, &sa, &ca);
+      for (int k = 0; k < pe; ++k) {
+        o[o_sin + k] = sa;
+        o[o_cos + k] = ca;
+        const float s2 = 2.0f * sa * ca, c2 = (ca - sa) * (ca + sa);
+        sa = s2;
+        ca = c2;
+      }
     }
-    out[t] = v;
+    __syncthreads();
+    float* dst = out + j0 * W;
+    for (int t = threadIdx.x; t < rows * W; t += blockDim.x) dst[t] = rin[t];
+    __syncthreads();
   }
 }
 
@@ -317,10 +332,14 @@ __global__ void render_input_bwd_kernel(const float* __restrict__ feat, int ld_f
     const float* gr = g_in + j * W;
     const float xv = feat[i * ld_feat + 1 + c];
     float s = gr[c];
+    float sa, ca;
+    sincosf(xv, &sa, &ca);                 // octaves by angle doubling, as in the forward kernel
     for (int k = 0; k < feape; ++k) {
       const float f = (float)(1 << k);
-      const float a = FFB_MUL(xv, f);
-      s += (gr[oPF + c * feape + k] * cosf(a) - gr[oPF + C * feape + c * feape + k] * sinf(a)) * f;
+      s += (gr[oPF + c * feape + k] * ca - gr[oPF + C * feape + c * feape + k] * sa) * f;
+      const float s2 = 2.0f * sa * ca, c2 = (ca - sa) * (ca + sa);
+      sa = s2;
+      ca = c2;
     }
     g_feat[i * ld_feat + 1 + c] += s;
   }
@@ -340,11 +359,19 @@ int ffb_linear_tc_bwd_input(const float* gy, const float* y, const float* W, flo
 int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const float* x, float* gW, float* gb, int64_t n,
                              const int32_t* n_dev, int32_t K, int32_t M, void* stream);
 
+int ffb_linear_tc_fwd_ex(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
+                         int32_t act, int32_t split_terms, void* stream);
+
 int ffb_linear_fwd(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K,
                    int32_t M, int32_t act, void* stream) {
+  return ffb_linear_fwd_ex(x, W, b, y, n, n_dev, K, M, act, 3, stream);
+}
+
+int ffb_linear_fwd_ex(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K,
+                      int32_t M, int32_t act, int32_t split_terms, void* stream) {
   FFB_REQUIRE(x && W && y && K > 0 && M > 0, "bad argument");
   if (n <= 0) return FFB_OK;
-  if (n >= 1024 && ffb_linear_tc_eligible(K, M)) return ffb_linear_tc_fwd(x, W, b, y, n, n_dev, K, M, act, stream);
+  if (n >= 1024 && ffb_linear_tc_eligible(K, M)) return ffb_linear_tc_fwd_ex(x, W, b, y, n, n_dev, K, M, act, split_terms, stream);
   cudaStream_t s = (cudaStream_t)stream;
   if (M <= 8 && (size_t)(8 * K + 256 * 33) * sizeof(float) <= 96 * 1024) {
     const size_t smem = (size_t)(8 * K + 256 * 33) * sizeof(float);
@@ -424,8 +451,9 @@ int ffb_render_input_fwd(const float* feat, int32_t ld_feat, const float* rays, 
   FFB_REQUIRE(feat && rays && out && C > 0 && ld_feat >= C + 1, "bad argument");
   if (n <= 0) return FFB_OK;
   const int W = 3 + C + 6 * viewpe + 2 * feape * C;
-  render_input_fwd_kernel<<<blocks_for(n * W, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(feat, ld_feat, rays, ray_id, app_idx, out,
-                                                                                              n, n_dev, C, viewpe, feape);
+  FFB_REQUIRE((size_t)RIN_ROWS * W * sizeof(float) <= 48 * 1024, "input row too wide");
+  render_input_fwd_kernel<<<blocks_for(n, RIN_ROWS, sm_count() * 8), 256, (size_t)RIN_ROWS * W * sizeof(float), (cudaStream_t)stream>>>(
+      feat, ld_feat, rays, ray_id, app_idx, out, n, n_dev, C, viewpe, feape);
   FFB_LAUNCHED();
   return FFB_OK;
 }

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(512) tc_gemm_rows_kernel(const float* __restri
     const uint32_t tbase = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     const int cbshift = CB == 64 ? 4 : (CB == 32 ? 3 : 2);    // log2(CB / 4)
     for (int cb0 = 0; cb0 < Np; cb0 += CB) {
-      for (int c0 = wsplit * 16; c0 < CB; c0 += nsplit * 16) {
+      for (int c0 = wsplit * 16; c0 < CB && cb0 + c0 < Np; c0 += nsplit * 16) {
         float v[16];
         tmem_ld16(tbase + (uint32_t)(cb0 + c0), v);
 #pragma unroll
@@ -400,7 +400,7 @@ int ffb_tensor_cores_enabled(void) { return g_tc_enabled; }
 static bool tc_gemm_plan(int K, int N, int terms, int* Kp_, int* Np_, int* KC_, int* CB_, uint32_t* szU_, size_t* smem_) {
   const int Kp = (K + 15) / 16 * 16, Np = (N + 15) / 16 * 16;
   if (Np > 256) return false;
-  const int CB = (Np % 64 == 0) ? 64 : ((Np % 32 == 0) ? 32 : 16);    // output column block staged through shared memory
+  const int CB = Np >= 64 ? 64 : (Np >= 32 ? 32 : 16);   // output column block staged through shared memory (last block may be partial)
   const size_t szE = (size_t)128 * (CB + 4) * 4;
   for (int KC = 64; KC >= 16; KC >>= 1) {
     const int kc = KC < Kp ? KC : Kp;
@@ -455,12 +455,20 @@ static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in,
   return FFB_OK;
 }
 
-int ffb_linear_tc_fwd(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
-                      int32_t act, void* stream) {
+// split_terms: 3 = fp32-class (6 MMAs per product), 2 = ~5e-6 relative (3 MMAs): enough wherever the output does not
+// feed exp() — the appearance MLP.
+int ffb_linear_tc_fwd_ex(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
+                         int32_t act, int32_t split_terms, void* stream) {
   FFB_REQUIRE(x && W && y, "null argument");
+  FFB_REQUIRE(split_terms == 2 || split_terms == 3, "split_terms must be 2 or 3");
   FFB_REQUIRE(ffb_linear_tc_eligible(K, M), "layer shape not eligible for the tensor-core path");
   if (n <= 0) return FFB_OK;
-  return tc_gemm_launch(3, x, nullptr, 0, W, K, 1, b, act, y, n, n_dev, K, M, (cudaStream_t)stream);
+  return tc_gemm_launch(split_terms, x, nullptr, 0, W, K, 1, b, act, y, n, n_dev, K, M, (cudaStream_t)stream);
+}
+
+int ffb_linear_tc_fwd(const float* x, const float* W, const float* b, float* y, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
+                      int32_t act, void* stream) {
+  return ffb_linear_tc_fwd_ex(x, W, b, y, n, n_dev, K, M, act, 3, stream);
 }
 
 int ffb_linear_tc_bwd_input(const float* gy, const float* y, const float* W, float* gx, int64_t n, const int32_t* n_dev, int32_t K,

@@ -226,13 +226,14 @@ def grid_mapping(positions, freq_bands, aabb, basis_mapping='sawtooth'):
 # --------------------------------------------------------------------------------------------------
 # MLPs
 # --------------------------------------------------------------------------------------------------
-def _linear_fwd(x, W, b, act, n_dev=None):
+def _linear_fwd(x, W, b, act, n_dev=None, terms=3):
+    """terms: bf16 parts per operand on the tensor-core path (3: fp32-class, 2: ~5e-6 relative)."""
     n, K = x.shape
     M = W.shape[0]
     y = _empty((n, M), x)
     if n > 0:
-        nv.check(nv.lib().ffb_linear_fwd(nv.ptr(x), nv.ptr(W), nv.ptr(b, allow_none=True), nv.ptr(y), C.c_int64(n), nv.i32p(n_dev), K, M,
-                                         act, nv.stream()))
+        nv.check(nv.lib().ffb_linear_fwd_ex(nv.ptr(x), nv.ptr(W), nv.ptr(b, allow_none=True), nv.ptr(y), C.c_int64(n), nv.i32p(n_dev), K, M,
+                                            act, terms, nv.stream()))
     return y
 
 
@@ -500,7 +501,7 @@ class RenderComposite(torch.autograd.Function):
                 for l, (W, b) in enumerate(layers):
                     act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
                     kinds.append(act)
-                    h = _linear_fwd(h, W, b, act, a_dev)
+                    h = _linear_fwd(h, W, b, act, a_dev, terms=2)   # colours: 5e-6 is ample (bar 1e-4), half the MMAs
                     acts.append(h)
             rgb = h
         else:
@@ -586,7 +587,7 @@ class RenderMLP(torch.autograd.Function):
         for l, (W, b) in enumerate(layers):
             act = 1 if l != len(layers) - 1 else 2
             kinds.append(act)
-            h = _linear_fwd(h, W, b, act)
+            h = _linear_fwd(h, W, b, act, terms=2)
             acts.append(h)
         ctx.has_bias, ctx.kinds, ctx.n_acts, ctx.view_pe, ctx.fea_pe = has_bias, kinds, len(acts), view_pe, fea_pe
         ctx.save_for_backward(feat, *acts, *params)

@@ -148,6 +148,11 @@ int ffb_field_generic_bwd(ffb_field_t f, const float* x, int64_t n, const int32_
 /* y = act(x W^T + b); act: 0 none, 1 relu, 2 sigmoid.  b may be NULL. */
 int ffb_linear_fwd(const float* x, const float* W, const float* b, float* y, int64_t n,
                    const int32_t* n_dev, int32_t K, int32_t M, int32_t act, void* stream);
+/* Same, choosing the tensor-core operand split: split_terms 3 = fp32-class accuracy (default), 2 = ~5e-6 relative and
+ * half the MMAs (used for the appearance MLP, whose output does not feed exp()).  Ignored by the exact SIMT path. */
+int ffb_linear_fwd_ex(const float* x, const float* W, const float* b, float* y, int64_t n,
+                      const int32_t* n_dev, int32_t K, int32_t M, int32_t act, int32_t split_terms,
+                      void* stream);
 /* gx = (gy .* act'(y)) W, where y is the saved forward OUTPUT of the layer and act the activation that
  * produced it (mask applied on the fly; gy is not modified).  act == 0: y may be NULL. */
 int ffb_linear_bwd_input(float* gy, const float* y, const float* W, float* gx, int64_t n,
@@ -168,6 +173,9 @@ int ffb_linear_tc_eligible(int32_t K, int32_t N);
 int ffb_linear_tc_wgrad_eligible(int32_t K, int32_t M);
 int ffb_linear_tc_fwd(const float* x, const float* W, const float* b, float* y, int64_t n,
                       const int32_t* n_dev, int32_t K, int32_t M, int32_t act, void* stream);
+int ffb_linear_tc_fwd_ex(const float* x, const float* W, const float* b, float* y, int64_t n,
+                         const int32_t* n_dev, int32_t K, int32_t M, int32_t act, int32_t split_terms,
+                         void* stream);
 int ffb_linear_tc_bwd_input(const float* gy, const float* y, const float* W, float* gx, int64_t n,
                             const int32_t* n_dev, int32_t K, int32_t M, int32_t act, void* stream);
 int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const float* x, float* gW,
