@@ -140,6 +140,8 @@ def cpu_baseline_leg(n=256, steps=2):
 
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('FFB_BENCH_WATCHDOG_S', '240')), exit=True)   # never hang a GPU box
     import torch
     import torch.distributed as dist
     import ffb200
@@ -156,6 +158,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')    # keep stdout for the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(20211202)
     np.random.seed(20211202)
@@ -223,7 +226,8 @@ def run_ours(args):
         api = 'ffb200.renderer.render_ray(host rays) -> loss.item()'
     else:
         # the product path: the whole step (render, MSE, backward, all-reduce, Adam, lr decay) is one CUDA graph
-        ts = TrainStep(model, groups, batch=B, n_samples=S, white_bg=True, betas=(0.9, 0.99), lr_decay=lr_factor)
+        ts = TrainStep(model, groups, batch=B, n_samples=S, white_bg=True, betas=(0.9, 0.99), lr_decay=lr_factor,
+                       nccl_in_graph=bool(int(os.environ.get('FFB_NCCL_IN_GRAPH', '0'))))
 
         def step_resident():
             """inputs already in HBM (device -> static-buffer copies only)"""
@@ -332,6 +336,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
 

@@ -107,9 +107,10 @@ class TrainStep:
     CHUNK = 16384
 
     def __init__(self, model, param_groups, batch, n_samples, white_bg=True, betas=(0.9, 0.99), eps=1e-8, lr_decay=1.0,
-                 group=None, use_graph=True, warmup=2):
+                 group=None, use_graph=True, warmup=2, nccl_in_graph=False):
         self.model, self.B, self.S, self.white_bg = model, int(batch), int(n_samples), bool(white_bg)
         self.betas, self.eps, self.lr_decay, self.group, self.use_graph = betas, eps, float(lr_decay), group, use_graph
+        self.nccl_in_graph = nccl_in_graph
         self.groups = [{'params': [p for p in g['params']], 'lr': float(g['lr'])} for g in param_groups]
         self.params = [p for g in self.groups for p in g['params']]
         dev = self.params[0].device
@@ -153,7 +154,8 @@ class TrainStep:
         self._param_ptrs = [p.data_ptr() for p in self.params]
 
     # -- the step body: only stream-ordered device work (capturable) ------------------------------------------
-    def _body(self):
+    def _render_backward(self):
+        """zero the arena, render, loss, backward: leaves this rank's gradients in self.bucket.flat"""
         from . import ops as _ops
         m = self.model
         self.bucket.flat.zero_()
@@ -175,11 +177,21 @@ class TrainStep:
                 v = self.bucket.view(k)
                 if g.data_ptr() != v.data_ptr():
                     v.copy_(g)
+
+    def _all_reduce(self):
         if self.world > 1:
             torch.distributed.all_reduce(self.bucket.flat, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def _optimise(self):
+        from . import ops as _ops
         _ops.adam_hyper_advance(self.lr_d, self.step_d, self.hyper_d, self.betas[0], self.betas[1], self.lr_decay)
         _ops.adam_multi(self.table, self.chunk_tensor, self.chunk_start, self.CHUNK, self.hyper_d, self.betas[0], self.betas[1],
                         self.eps, 1.0 / self.world)
+
+    def _body(self):
+        self._render_backward()
+        self._all_reduce()
+        self._optimise()
 
     def _check_params(self):
         if [p.data_ptr() for p in self.params] != self._param_ptrs:
@@ -199,13 +211,22 @@ class TrainStep:
             for p, q in zip(self.params, snap):
                 p.copy_(q)
             self.m.copy_(st[0]); self.v.copy_(st[1]); self.lr_d.copy_(st[2]); self.step_d.copy_(st[3])
-        if self.use_graph:
+        if not self.use_graph:
+            self.graph = False
+        elif self.world == 1 or self.nccl_in_graph:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._body()
-            self.graph = g
+            self.graph = (g,)
         else:
-            self.graph = False
+            # data parallel: [render + backward] graph -> NCCL all-reduce of the arena (a normal stream-ordered call
+            # between the two replays) -> [Adam] graph
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._render_backward()
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._optimise()
+            self.graph = (ga, gb)
 
     def step(self, rays, target, jitter=None):
         """rays [B,6], target [B,3]: host (ideally pinned) or device fp32 tensors; jitter [B] (default: torch.rand on the
@@ -221,10 +242,14 @@ class TrainStep:
         self.rays_s.copy_(rays[:, :6], non_blocking=True)
         self.target_s.copy_(target, non_blocking=True)
         self.jitter_s.copy_(jitter, non_blocking=True)
-        if self.graph:
-            self.graph.replay()
-        else:
+        if not self.graph:
             self._body()
+        elif len(self.graph) == 1:
+            self.graph[0].replay()
+        else:
+            self.graph[0].replay()
+            self._all_reduce()
+            self.graph[1].replay()
         return self.loss_s
 
     @property
