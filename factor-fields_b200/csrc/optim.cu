@@ -59,14 +59,38 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const int64_t* __restri
   const float step_size = hyper[2 * grp], inv_sqrt_bc2 = hyper[2 * grp + 1];
   const int64_t begin = chunk_start[blockIdx.x];
   const int64_t end = begin + chunk < n ? begin + chunk : n;
-  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    const float mi = m[i] * beta1 + gi * (1.0f - beta1);
-    const float vi = v[i] * beta2 + gi * gi * (1.0f - beta2);
+  const float ob1 = 1.0f - beta1, ob2 = 1.0f - beta2;
+  auto upd = [&](float pi, float gi, float& mi, float& vi) {
+    gi *= grad_scale;
+    mi = mi * beta1 + gi * ob1;
+    vi = vi * beta2 + gi * gi * ob2;
+    return pi - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+  };
+  int64_t i0 = begin;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(p + begin) | reinterpret_cast<uintptr_t>(g + begin) |
+                         reinterpret_cast<uintptr_t>(m + begin) | reinterpret_cast<uintptr_t>(v + begin);
+  if ((bits & 15) == 0) {      // 16-byte vector path (arena slices and torch allocations are 256-byte aligned)
+    const int64_t n4 = (end - begin) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p + begin);
+    const float4* g4 = reinterpret_cast<const float4*>(g + begin);
+    float4* m4 = reinterpret_cast<float4*>(m + begin);
+    float4* v4 = reinterpret_cast<float4*>(v + begin);
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 pp = p4[i], mm = m4[i], vv = v4[i];
+      const float4 gg = g4[i];
+      pp.x = upd(pp.x, gg.x, mm.x, vv.x);
+      pp.y = upd(pp.y, gg.y, mm.y, vv.y);
+      pp.z = upd(pp.z, gg.z, mm.z, vv.z);
+      pp.w = upd(pp.w, gg.w, mm.w, vv.w);
+      p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    }
+    i0 = begin + n4 * 4;
+  }
+  for (int64_t i = i0 + threadIdx.x; i < end; i += blockDim.x) {
+    float mi = m[i], vi = v[i];
+    p[i] = upd(p[i], g[i], mi, vi);
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] -= step_size * (mi / denom);
   }
 }
 

@@ -104,7 +104,7 @@ class TrainStep:
     new TrainStep (`ts.rebuild()` keeps the optimiser scalars), exactly where the reference rebuilds its optimiser.
     """
 
-    CHUNK = 16384
+    CHUNK = 4096
 
     def __init__(self, model, param_groups, batch, n_samples, white_bg=True, betas=(0.9, 0.99), eps=1e-8, lr_decay=1.0,
                  group=None, use_graph=True, warmup=2, nccl_in_graph=False):
@@ -251,6 +251,16 @@ class TrainStep:
             self._all_reduce()
             self.graph[1].replay()
         return self.loss_s
+
+    def snapshot(self):
+        """Copy of everything a step mutates (parameters, Adam moments, lr, step count)."""
+        return ([p.detach().clone() for p in self.params], self.m.clone(), self.v.clone(), self.lr_d.clone(), self.step_d.clone())
+
+    @torch.no_grad()
+    def restore(self, snap):
+        for p, q in zip(self.params, snap[0]):
+            p.copy_(q)
+        self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.lr_d.copy_(snap[3]); self.step_d.copy_(snap[4])
 
     @property
     def lrs(self):
