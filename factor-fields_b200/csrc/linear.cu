@@ -228,6 +228,70 @@ __global__ void __launch_bounds__(256) bgrad_kernel(const float* __restrict__ gy
   }
 }
 
+// Skinny layer (M <= 8 outputs, e.g. the 128 -> 3 colour head) backward in ONE pass, exact fp32: thread <-> input
+// column k, rows streamed in chunks of 32 whose masked output gradients gm = gy .* act'(y) sit in shared memory;
+// gx[r,k] = sum_m gm[r,m] W[m,k] is written coalesced and gW[m,k] / gb[m] accumulate in registers (one atomic per
+// block at the end).  Replaces a padded K=16 tensor-core GEMM plus a 128-row-padded weight-gradient GEMM.
+template <int MMAX>
+__global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, int act,
+                                                         const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ gx,
+                                                         float* __restrict__ gW, float* __restrict__ gb, int64_t n,
+                                                         const int32_t* __restrict__ n_dev, int K, int M, int64_t rows_per_block) {
+  n = resolve_n(n, n_dev);
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(n, r_begin + rows_per_block);
+  if (r_begin >= r_end) return;
+  __shared__ float gm[32][MMAX];
+  const int t = threadIdx.x;
+  for (int k0 = 0; k0 < K; k0 += blockDim.x) {
+    const int k = k0 + t;
+    float w[MMAX], acc[MMAX], accb = 0.0f;
+#pragma unroll
+    for (int m = 0; m < MMAX; ++m) {
+      w[m] = (m < M && k < K) ? __ldg(W + (int64_t)m * K + k) : 0.0f;
+      acc[m] = 0.0f;
+    }
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += 32) {
+      __syncthreads();
+      if (t < 32 * MMAX) {
+        const int rr = t / MMAX, m = t % MMAX;
+        const int64_t row = r0 + rr;
+        float g = 0.0f;
+        if (row < r_end && m < M) {
+          g = gy[row * M + m];
+          if (act) g *= act_mask(y[row * M + m], act);
+        }
+        gm[rr][m] = g;
+      }
+      __syncthreads();
+      const int rows = (int)min((int64_t)32, r_end - r0);
+      if (k < K) {
+#pragma unroll 4
+        for (int rr = 0; rr < rows; ++rr) {
+          const float xv = x ? x[(r0 + rr) * K + k] : 0.0f;
+          float s = 0.0f;
+#pragma unroll
+          for (int m = 0; m < MMAX; ++m) {
+            const float g = gm[rr][m];
+            s = fmaf(g, w[m], s);
+            acc[m] = fmaf(g, xv, acc[m]);
+          }
+          if (gx) gx[(r0 + rr) * K + k] = s;
+        }
+      }
+      if (k0 == 0 && t < M && gb) {
+        for (int rr = 0; rr < rows; ++rr) accb += gm[rr][t];
+      }
+    }
+    if (k < K && gW) {
+#pragma unroll
+      for (int m = 0; m < MMAX; ++m)
+        if (m < M && acc[m] != 0.0f) atomicAdd(gW + (int64_t)m * K + k, acc[m]);
+    }
+    if (k0 == 0 && t < M && gb && accb != 0.0f) atomicAdd(gb + t, accb);
+  }
+}
+
 // ---- positional encoding ---------------------------------------------------------------------
 __global__ void pe_concat_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, const int32_t* __restrict__ n_dev,
                                      int D, int pe) {
@@ -371,9 +435,10 @@ int ffb_linear_fwd_ex(const float* x, const float* W, const float* b, float* y, 
                       int32_t M, int32_t act, int32_t split_terms, void* stream) {
   FFB_REQUIRE(x && W && y && K > 0 && M > 0, "bad argument");
   if (n <= 0) return FFB_OK;
-  if (n >= 1024 && ffb_linear_tc_eligible(K, M)) return ffb_linear_tc_fwd_ex(x, W, b, y, n, n_dev, K, M, act, split_terms, stream);
+  const bool skinny = M <= 8 && (size_t)(8 * K + 256 * 33) * sizeof(float) <= 96 * 1024;   // exact fp32 and cheaper than a padded MMA
+  if (!skinny && n >= 1024 && ffb_linear_tc_eligible(K, M)) return ffb_linear_tc_fwd_ex(x, W, b, y, n, n_dev, K, M, act, split_terms, stream);
   cudaStream_t s = (cudaStream_t)stream;
-  if (M <= 8 && (size_t)(8 * K + 256 * 33) * sizeof(float) <= 96 * 1024) {
+  if (skinny) {
     const size_t smem = (size_t)(8 * K + 256 * 33) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
@@ -422,6 +487,17 @@ int ffb_linear_bwd_weight_act(const float* gy, const float* y, int32_t act, cons
     bgrad_kernel<<<blocks_for(n, (int)rpb), 256, 0, s>>>(gy, y, act, gb, n, n_dev, M, rpb);
     FFB_LAUNCHED();
   }
+  return FFB_OK;
+}
+
+int ffb_linear_bwd_skinny(const float* gy, const float* y, int32_t act, const float* x, const float* W, float* gx, float* gW, float* gb,
+                          int64_t n, const int32_t* n_dev, int32_t K, int32_t M, void* stream) {
+  FFB_REQUIRE(gy && W && K > 0 && M > 0 && M <= 8 && (act == 0 || y) && (x || !gW), "bad argument");
+  if (n <= 0) return FFB_OK;
+  const int threads = 256;   // also the size of the gm staging pass (32 rows x 8 outputs)
+  const int64_t rows = 64;   // ~n/64 CTAs: enough resident warps to cover the streaming loads
+  skinny_bwd_kernel<8><<<blocks_for(n, (int)rows), threads, 0, (cudaStream_t)stream>>>(gy, y, act, x, W, gx, gW, gb, n, n_dev, K, M, rows);
+  FFB_LAUNCHED();
   return FFB_OK;
 }
 

@@ -250,11 +250,21 @@ def _mlp_backward(acts, layers, acts_kind, g_out, need_input_grad, param_needs, 
         y = acts[l + 1]
         gW = _grad_like(W) if param_needs[l][0] else None
         gb = _grad_like(b) if (b is not None and param_needs[l][1]) else None
+        want_gx = l > 0 or need_input_grad
+        if M <= 8 and n > 0:
+            # colour / density heads: one exact-fp32 pass for gx, gW and gb
+            gx = _empty((n, K), g) if want_gx else None
+            nv.check(lib.ffb_linear_bwd_skinny(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), act, nv.ptr(acts[l]), nv.ptr(W),
+                                               nv.ptr(gx, allow_none=True), nv.ptr(gW, allow_none=True), nv.ptr(gb, allow_none=True),
+                                               C.c_int64(n), nv.i32p(n_dev), K, M, nv.stream()))
+            grads[l] = (gW, gb)
+            g = gx
+            continue
         if n > 0 and gW is not None:
             nv.check(lib.ffb_linear_bwd_weight_act(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), act, nv.ptr(acts[l]), nv.ptr(gW),
                                                    nv.ptr(gb, allow_none=True), C.c_int64(n), nv.i32p(n_dev), K, M, nv.stream()))
         grads[l] = (gW, gb)
-        if l > 0 or need_input_grad:
+        if want_gx:
             gx = _empty((n, K), g)
             if n > 0:
                 nv.check(lib.ffb_linear_bwd_input(nv.ptr(g), nv.ptr(y, allow_none=(act == 0)), nv.ptr(W), nv.ptr(gx), C.c_int64(n),

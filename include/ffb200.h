@@ -161,6 +161,11 @@ int ffb_linear_bwd_input(float* gy, const float* y, const float* W, float* gx, i
 int ffb_linear_bwd_weight_act(const float* gy, const float* y, int32_t act, const float* x, float* gW,
                               float* gb, int64_t n, const int32_t* n_dev, int32_t K, int32_t M,
                               void* stream);
+/* Skinny layers (M <= 8 outputs): input gradient, weight gradient and bias gradient in one exact-fp32 pass.
+ * gx [n,K] = (gy .* act'(y)) W (may be NULL); gW / gb accumulate (+=). */
+int ffb_linear_bwd_skinny(const float* gy, const float* y, int32_t act, const float* x, const float* W,
+                          float* gx, float* gW, float* gb, int64_t n, const int32_t* n_dev, int32_t K,
+                          int32_t M, void* stream);
 int ffb_linear_bwd_weight(const float* gy, const float* x, float* gW, float* gb, int64_t n,
                           const int32_t* n_dev, int32_t K, int32_t M, void* stream);
 
