@@ -268,3 +268,81 @@ class TrainStep:
 
     def set_lrs(self, lrs):
         self.lr_d.copy_(torch.tensor(lrs, dtype=torch.float64))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Training-loop host (train_per_scene.py:89-234 `reconstruction`): same schedule, same optimiser bookkeeping, same RNG
+# consumption (numpy permutation sampler + one torch CPU uniform per ray), with the per-step work in TrainStep.
+# Datasets, image writers and tensorboard are out of scope: rays / colours come in as tensors.
+# ----------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def evaluate_psnr(model, rays, rgbs, white_bg=True, chunk=8192, N_samples=-1):
+    """Mean-squared error -> PSNR of a forward-only render of `rays` (renderer.py:29-98 without the image writers)."""
+    from .renderer import render_ray
+    from .utils import mse2psnr
+    lazy, model.lazy_counts = getattr(model, 'lazy_counts', False), False
+    try:
+        rgb_map, _ = render_ray(rays, model, chunk=chunk, N_samples=N_samples, white_bg=white_bg, is_train=False, device=model.device)
+    finally:
+        model.lazy_counts = lazy
+    mse = float(torch.mean((rgb_map - rgbs.to(rgb_map.device)) ** 2))
+    return mse2psnr(max(mse, 1e-12))
+
+
+def reconstruction(cfg, model, allrays, allrgbs, white_bg=True, n_iters=None, test=None, log=None, use_graph=True):
+    """Per-scene optimisation with the reference's schedule (train_per_scene.py:125-234).
+
+    allrays [N,6] / allrgbs [N,3]: host tensors (the reference keeps them on the host, :146,151-152).  test: optional
+    (rays, rgbs) evaluated at the end.  Returns dict(psnr_train=[...per step], psnr_test=float|None, steps=int)."""
+    from .utils import N_to_reso, SimpleSampler, cal_n_samples, mse2psnr
+    t = cfg.training
+    n_iters = int(n_iters if n_iters is not None else t.n_iters)
+    decay_iters = t.lr_decay_iters if t.lr_decay_iters > 0 else t.n_iters
+    lr_factor = t.lr_decay_target_ratio ** (1.0 / decay_iters)
+    upsamp_list, mask_list, shrink_list = list(t.upsamp_list), list(t.update_AlphaMask_list), list(t.shrinking_list)
+    reso_list = torch.linspace(t.volume_resoInit, t.volume_resoFinal, len(upsamp_list)).ceil().long().tolist()
+    reso_cur = N_to_reso(t.volume_resoInit ** model.in_dim, model.aabb)
+    n_samples = min(cfg.renderer.max_samples, cal_n_samples(reso_cur, cfg.renderer.step_ratio))
+    sampler = SimpleSampler(allrays.shape[0], t.batch_size)
+    pinned = allrays.is_pinned()
+
+    def new_step(keep=None):
+        ts = TrainStep(model, model.get_optparam_groups(t.lr_small, t.lr_large), batch=t.batch_size, n_samples=n_samples,
+                       white_bg=white_bg, betas=(0.9, 0.99), lr_decay=lr_factor, use_graph=use_graph)
+        if keep is not None:       # same parameters, new launch sequence (alpha mask changed): carry the optimiser over
+            ts.m.copy_(keep.m); ts.v.copy_(keep.v); ts.lr_d.copy_(keep.lr_d); ts.step_d.copy_(keep.step_d)
+        return ts
+
+    ts = new_step()
+    psnrs, reso_mask = [], None
+    for it in range(n_iters):
+        idx = sampler.nextids()
+        rays_b, rgb_b = allrays[idx], allrgbs[idx]
+        if pinned:
+            rays_b, rgb_b = rays_b.pin_memory(), rgb_b.pin_memory()
+        loss = float(ts.step(rays_b, rgb_b).item())           # the reference reads the loss every step too (:164)
+        psnrs.append(mse2psnr(max(loss, 1e-12)))
+        if log is not None and it % cfg.defaults.progress_refresh_rate == 0:
+            log(f'Iteration {it:05d}: train_psnr = {psnrs[-1]:.2f} mse = {loss:.6f}')
+        if it in mask_list or it in shrink_list:
+            if reso_list and reso_list[0] < 256:
+                reso_mask = N_to_reso(reso_list[0] ** model.in_dim, model.aabb)
+            new_aabb = model.updateAlphaMask(tuple(reso_mask), is_update_alphaMask=it >= 1500)
+            if it in shrink_list:
+                model.shrink(new_aabb)
+                ts = new_step()
+            else:
+                ts = new_step(keep=ts)
+            if not cfg.dataset.ndc_ray and mask_list and it == mask_list[0] and not cfg.dataset.is_unbound:
+                allrays, allrgbs = model.filtering_rays(allrays, allrgbs)
+                sampler = SimpleSampler(allrgbs.shape[0], t.batch_size)
+        if it in upsamp_list:
+            n_voxels = reso_list.pop(0)
+            reso_cur = N_to_reso(n_voxels ** model.in_dim, model.aabb)
+            n_samples = min(cfg.renderer.max_samples, cal_n_samples(reso_cur, cfg.renderer.step_ratio))
+            model.upsample_volume_grid(reso_cur)
+            ts = new_step()
+    out = dict(psnr_train=psnrs, psnr_test=None, steps=n_iters)
+    if test is not None:
+        out['psnr_test'] = evaluate_psnr(model, test[0], test[1], white_bg=white_bg)
+    return out

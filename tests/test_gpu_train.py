@@ -92,3 +92,62 @@ def test_train_step_does_not_disturb_state_on_capture():
     for a, p in zip(before, m.parameters()):
         assert torch.equal(a, p)
     assert int(ts.step_d.item()) == 0 and float(ts.m.abs().sum()) == 0.0 and float(ts.v.abs().sum()) == 0.0
+
+
+def test_training_psnr_parity_with_reference_port():
+    """End-of-run PSNR within 0.1 dB of the reference's CPU path (north_star), on an analytic scene at reduced size:
+    same initial weights, same ray batches (numpy permutation sampler), same per-ray jitter draws (torch CPU generator),
+    200 optimisation steps.  Reference side: oracle/torch_port.py (the reference's train step restated with the torch
+    CPU operators it calls, pinned against the golden vectors)."""
+    import ffb200
+    from ffb200.models.FactorFields import FactorFields
+    from ffb200.train import evaluate_psnr, reconstruction
+    from ffb200.utils import SimpleSampler, mse2psnr
+    from oracle.torch_port import TorchPort
+    from tests.synth_scene import sphere_scene
+    steps, B = 200, 1024
+    cfg = ffb200.load_cfg('nerf.yaml', ['model.total_params=400000', 'model.coeff_reso=16', 'training.volume_resoInit=48',
+                                        f'training.batch_size={B}', f'training.n_iters={steps}', 'renderer.density_shift=-4.0'])
+    cfg.dataset.aabb = [[-1., -1., -1.], [1., 1., 1.]]
+    cfg.training.upsamp_list, cfg.training.update_AlphaMask_list, cfg.training.shrinking_list = [10 ** 9], [10 ** 9], [10 ** 9]
+    torch.manual_seed(11)
+    m = FactorFields(cfg, 'cuda:0')
+    state = {k: v.detach().cpu().contiguous().numpy() for k, v in m.state_dict().items()}
+    rays, rgbs = sphere_scene(20000, 1)
+    test_rays, test_rgbs = sphere_scene(4096, 2)
+    allrays, allrgbs = torch.from_numpy(rays), torch.from_numpy(rgbs)
+    from ffb200.utils import N_to_reso, cal_n_samples
+    n_samples = min(cfg.renderer.max_samples, cal_n_samples(N_to_reso(cfg.training.volume_resoInit ** 3, m.aabb), cfg.renderer.step_ratio))
+    lr_factor = cfg.training.lr_decay_target_ratio ** (1.0 / steps)
+
+    # ---- ours (CUDA graph train step inside the reference's schedule loop)
+    np.random.seed(5)
+    torch.manual_seed(6)
+    res = reconstruction(cfg, m, allrays, allrgbs, white_bg=True, n_iters=steps, test=(torch.from_numpy(test_rays), torch.from_numpy(test_rgbs)))
+
+    # ---- reference port on the host cores, identical random streams
+    np.random.seed(5)
+    torch.manual_seed(6)
+    rcfg = dict(density_shift=-4.0, distance_scale=25.0, rayMarch_weight_thres=1e-3, view_pe=6, fea_pe=2)
+    tp = TorchPort(state, m.aabb.cpu().numpy(), m.freq_bands.cpu().numpy(), float(m.stepSize), rcfg)
+    sampler = SimpleSampler(allrays.shape[0], B)
+    ref_psnr = []
+    for it in range(steps):
+        idx = sampler.nextids()
+        jitter = torch.rand(B, 1)[:, 0]
+        loss = tp.train_step(allrays[idx], allrgbs[idx], n_samples, jitter)
+        ref_psnr.append(mse2psnr(loss))
+        for g in tp.opt.param_groups:
+            g['lr'] = g['lr'] * lr_factor
+    with torch.no_grad():
+        rgb_map, _, _, _ = tp.forward(torch.from_numpy(test_rays), m.nSamples, None)
+        ref_test = mse2psnr(float(torch.mean((rgb_map - torch.from_numpy(test_rgbs)) ** 2)))
+
+    ours_train, ref_train = float(np.mean(res['psnr_train'][-20:])), float(np.mean(ref_psnr[-20:]))
+    print(f'train PSNR (last 20 steps): ours {ours_train:.3f} dB, reference port {ref_train:.3f} dB; '
+          f'test PSNR: ours {res["psnr_test"]:.3f} dB, reference port {ref_test:.3f} dB; first-step loss ours '
+          f'{res["psnr_train"][0]:.4f} ref {ref_psnr[0]:.4f}')
+    assert abs(res['psnr_train'][0] - ref_psnr[0]) < 1e-3          # identical first step (same weights, rays, jitter)
+    assert ref_test > 18.0, 'the scene was not learnt: the comparison would be vacuous'
+    assert abs(ours_train - ref_train) < 0.1
+    assert abs(res['psnr_test'] - ref_test) < 0.1
