@@ -326,8 +326,17 @@ def run_ours(args):
             kern[k]['achieved_TFLOPs'] = round(f / (sec[k] * 1e-3) / 1e12, 3)
     dom = max(('field_fwd', 'field_bwd'), key=lambda k: sec.get(k, 0.0))
     ach = alg[dom] / (sec[dom] * 1e-3) / 1e9
+    # DRAM traffic of the same kernel per launch: from the committed `ncu --set full` capture (profiles/), never measured here
+    traffic, traffic_src = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_field_v2.json')))
+        for name, rec in cap.items():
+            if ('bwd' in name) == (dom == 'field_bwd') and rec.get('traffic_bytes'):
+                traffic, traffic_src = int(rec['traffic_bytes']), 'profiles/r01_ncu_field_v2.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)'
+    except Exception:
+        pass
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 4),
-                'traffic': None, 'peak_source': pk['src'],
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['src'],
                 'algorithmic_bytes_per_launch': alg[dom], 'queries_per_launch': n_valid, 'launch_ms': round(sec[dom], 4),
                 'share_of_step': round(sec[dom] / (ms_total / args.steps), 4)}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
