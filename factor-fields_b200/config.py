@@ -65,10 +65,13 @@ def apply_dotlist(cfg, dotlist):
     """`model.basis_type=vm training.n_iters=100` style overrides."""
     for item in dotlist:
         key, _, val = item.partition('=')
-        try:
-            val = ast.literal_eval(val)
+        try:       # OmegaConf.from_cli gives dot-list values YAML semantics: true / false / null / 1e-3 / [1, 2] / bare strings
+            val = yaml.load(val, Loader=_Loader)
         except Exception:
-            pass
+            try:
+                val = ast.literal_eval(val)
+            except Exception:
+                pass
         node = cfg
         parts = key.split('.')
         for p in parts[:-1]:

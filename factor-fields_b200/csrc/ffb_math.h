@@ -144,6 +144,21 @@ FFB_HD bool sample_pos(const float o[3], const float d[3], float t, const float 
   return inside;
 }
 
+// sample_point_unbound (FactorFields.py:625-633): p = o + d t; outside the unit cube (inf-norm > 1) the point is
+// contracted to p / n * ((1 + bg) - bg / n).  Returns inner_mask.
+FFB_HD bool sample_pos_unbound(const float o[3], const float d[3], float t, float bg_len, float p[3]) {
+  float n = 0.0f;
+  for (int k = 0; k < 3; ++k) {
+    p[k] = FFB_ADD(o[k], FFB_MUL(d[k], t));
+    n = fmaxf(n, fabsf(p[k]));
+  }
+  if (n <= 1.0f) return true;
+  // `self.bg_len / norm` on a Python float is Tensor.__rtruediv__ = norm.reciprocal() * bg_len
+  const float s = FFB_SUB((float)(1.0 + (double)bg_len), FFB_MUL(FFB_DIV(1.0f, n), bg_len));
+  for (int k = 0; k < 3; ++k) p[k] = FFB_MUL(FFB_DIV(p[k], n), s);
+  return false;
+}
+
 // AlphaGridMask.sample_alpha (FactorFields.py:103-110) on a 0/1 volume, ATen trilinear order, zeros padding,
 // align_corners=True.
 FFB_HD float alpha_lookup(const uint8_t* vol, const int size[3] /*W,H,D*/, const float amin[3], const float ainv[3],

@@ -4,9 +4,11 @@
 namespace ffb {
 
 __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n,
-                                                  float g_scale, float* __restrict__ loss, float* __restrict__ g_pred) {
+                                                  float g_scale, const float* __restrict__ g_scale_dev, float* __restrict__ loss,
+                                                  float* __restrict__ g_pred) {
   float s = 0.0f;
   const float inv_n = 1.0f / (float)n;
+  if (g_scale_dev) g_scale *= __ldg(g_scale_dev);     // e.g. the decaying loss scale of the regression drivers
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = pred[i] - target[i];
     s += d * d;
@@ -110,15 +112,32 @@ __global__ void adam_hyper_kernel(double* __restrict__ lr, long long* __restrict
   }
 }
 
+// value *= factor (double, like the Python scalar `loss_scale *= lr_factor` of scripts/2D_regression.ipynb cell 4 /
+// sdf_regression.ipynb cell 2); the fp32 copy is what a captured graph's loss kernel reads.
+__global__ void scalar_decay_kernel(double* __restrict__ value, double factor, float* __restrict__ out_f32) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double v = *value * factor;
+  *value = v;
+  if (out_f32) *out_f32 = (float)v;
+}
+
 }  // namespace ffb
 
 using namespace ffb;
 
 extern "C" {
 
-int ffb_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float g_scale, float* loss, float* g_pred, void* stream) {
+int ffb_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float g_scale, const float* g_scale_dev, float* loss,
+                    float* g_pred, void* stream) {
   FFB_REQUIRE(pred && target && loss && n > 0, "bad argument");
-  mse_kernel<<<blocks_for(n, 256, sm_count() * 4), 256, 0, (cudaStream_t)stream>>>(pred, target, n, g_scale, loss, g_pred);
+  mse_kernel<<<blocks_for(n, 256, sm_count() * 4), 256, 0, (cudaStream_t)stream>>>(pred, target, n, g_scale, g_scale_dev, loss, g_pred);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_scalar_decay(double* d_value, double factor, float* d_out_f32, void* stream) {
+  FFB_REQUIRE(d_value, "null argument");
+  scalar_decay_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_value, factor, d_out_f32);
   FFB_LAUNCHED();
   return FFB_OK;
 }

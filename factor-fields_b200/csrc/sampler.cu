@@ -1,5 +1,6 @@
 // sampler.cu — ray sampling + alpha-mask stream compaction.
-// Replaces FactorFields.sample_point (FactorFields.py:586-602), AlphaGridMask.sample_alpha (:103-110) and
+// Replaces FactorFields.sample_point (FactorFields.py:586-602), sample_point_ndc (:575-584), sample_point_unbound
+// (:604-633), AlphaGridMask.sample_alpha (:103-110) and
 // the boolean-mask gathers of forward (:864-867, :874) — which in the reference materialise dense
 // [rays, samples, 3] tensors, call nonzero()/index() and sync the host on `.any()`.
 //
@@ -20,13 +21,42 @@ struct RaySetup {
   float tmin;
 };
 
+// interpx of sample s: marched from the box entry (mode 0) or read from the per-call table shared by all rays (modes 1, 2)
+__device__ __forceinline__ float sample_z(const ffb_sampler_desc& D, const RaySetup& r, int s, float jit, bool train) {
+  return D.mode == FFB_SAMPLE_BOUNDED ? sample_t(r.tmin, D.step_size, s, jit, train) : __ldg(D.z_table + s);
+}
+
+// forward differences of interpx (FactorFields.py:850 unbounded: last = previous; :854-856 NDC: last 0, times |d|; :861 last 0)
+__device__ __forceinline__ float sample_dist(const ffb_sampler_desc& D, const RaySetup& r, int s, float t, float jit, bool train,
+                                             float dnorm) {
+  if (D.mode == FFB_SAMPLE_UNBOUND) {
+    if (s + 1 < D.n_samples) return FFB_SUB(__ldg(D.z_table + s + 1), t);
+    return D.n_samples > 1 ? FFB_SUB(t, __ldg(D.z_table + s - 1)) : 0.0f;
+  }
+  if (s + 1 >= D.n_samples) return 0.0f;
+  const float dz = FFB_SUB(sample_z(D, r, s + 1, jit, train), t);
+  return D.mode == FFB_SAMPLE_NDC ? FFB_MUL(dz, dnorm) : dz;
+}
+
 __device__ __forceinline__ bool sample_valid(const ffb_sampler_desc& D, const RaySetup& r, int s, float jit, bool train, float p[3],
-                                             float* t_out) {
-  const float t = sample_t(r.tmin, D.step_size, s, jit, train);
+                                             float* t_out, bool* inner_out = nullptr) {
+  const float t = sample_z(D, r, s, jit, train);
   if (t_out) *t_out = t;
+  if (D.mode == FFB_SAMPLE_UNBOUND) {
+    // every sample is kept; the alpha mask only prunes samples inside the unit cube (:864-867 with ray_valid = ones)
+    const bool inner = sample_pos_unbound(r.o, r.d, t, D.bg_len, p);
+    if (inner_out) *inner_out = inner;
+    if (inner && D.alpha_volume) return alpha_lookup(D.alpha_volume, D.alpha_size, D.alpha_aabb_min, D.alpha_inv_size, p) > D.alpha_thres;
+    return true;
+  }
   bool ok = sample_pos(r.o, r.d, t, D.aabb_min, D.aabb_max, p);
+  if (inner_out) *inner_out = ok;
   if (ok && D.alpha_volume) ok = alpha_lookup(D.alpha_volume, D.alpha_size, D.alpha_aabb_min, D.alpha_inv_size, p) > D.alpha_thres;
   return ok;
+}
+
+__device__ __forceinline__ float dir_norm(const RaySetup& r) {
+  return sqrtf(FFB_ADD(FFB_ADD(FFB_MUL(r.d[0], r.d[0]), FFB_MUL(r.d[1], r.d[1])), FFB_MUL(r.d[2], r.d[2])));
 }
 
 __device__ __forceinline__ void load_ray(const float* __restrict__ rays, int64_t r, RaySetup& rs) {
@@ -45,7 +75,7 @@ __global__ void __launch_bounds__(256) sample_count_kernel(ffb_sampler_desc D, c
   for (int64_t r = warp; r < R; r += nwarps) {
     RaySetup rs;
     load_ray(rays, r, rs);
-    rs.tmin = ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max);
+    rs.tmin = D.mode == FFB_SAMPLE_BOUNDED ? ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max) : 0.0f;
     const bool train = jitter != nullptr;
     const float jit = train ? jitter[r] : 0.0f;
     int cnt = 0;
@@ -74,9 +104,10 @@ __global__ void __launch_bounds__(256) sample_fill_kernel(ffb_sampler_desc D, co
   for (int64_t r = warp; r < R; r += nwarps) {
     RaySetup rs;
     load_ray(rays, r, rs);
-    rs.tmin = tmin ? tmin[r] : ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max);
+    rs.tmin = D.mode != FFB_SAMPLE_BOUNDED ? 0.0f : (tmin ? tmin[r] : ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max));
     const bool train = jitter != nullptr;
     const float jit = train ? jitter[r] : 0.0f;
+    const float dnorm = D.mode == FFB_SAMPLE_NDC ? dir_norm(rs) : 1.0f;
     int64_t base = offsets[r];
     for (int s0 = 0; s0 < D.n_samples; s0 += 32) {
       const int s = s0 + lane;
@@ -92,11 +123,7 @@ __global__ void __launch_bounds__(256) sample_fill_kernel(ffb_sampler_desc D, co
           if (ray_id) ray_id[i] = (int32_t)r;
           if (sample_id) sample_id[i] = s;
           if (z) z[i] = t;
-          if (dist) {
-            // dists = cat(z[1:] - z[:-1], 0)  (FactorFields.py:861)
-            const float tn = sample_t(rs.tmin, D.step_size, s + 1, jit, train);
-            dist[i] = (s + 1 < D.n_samples) ? FFB_SUB(tn, t) : 0.0f;
-          }
+          if (dist) dist[i] = sample_dist(D, rs, s, t, jit, train, dnorm);
         }
       }
       base += __popc(m);
@@ -106,19 +133,26 @@ __global__ void __launch_bounds__(256) sample_fill_kernel(ffb_sampler_desc D, co
 
 __global__ void __launch_bounds__(256) sample_dense_kernel(ffb_sampler_desc D, const float* __restrict__ rays,
                                                            const float* __restrict__ jitter, int64_t R, uint8_t* __restrict__ mask,
-                                                           float* __restrict__ z) {
+                                                           float* __restrict__ z, float* __restrict__ pts) {
   const int64_t total = R * D.n_samples;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / D.n_samples;
     const int s = (int)(t % D.n_samples);
     RaySetup rs;
     load_ray(rays, r, rs);
-    rs.tmin = ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max);
+    rs.tmin = D.mode == FFB_SAMPLE_BOUNDED ? ray_tmin(rs.o, rs.d, D.aabb_min, D.aabb_max) : 0.0f;
     const bool train = jitter != nullptr;
     float p[3], tt;
-    const bool ok = sample_valid(D, rs, s, train ? jitter[r] : 0.0f, train, p, &tt);
-    mask[t] = ok ? 1 : 0;
+    bool inner;
+    const bool ok = sample_valid(D, rs, s, train ? jitter[r] : 0.0f, train, p, &tt, &inner);
+    // the reference's sample_point* return the in-box / inner mask; with an alpha volume attached this is ray_valid
+    mask[t] = (D.alpha_volume ? ok : inner) ? 1 : 0;
     if (z) z[t] = tt;
+    if (pts) {
+      pts[t * 3 + 0] = p[0];
+      pts[t * 3 + 1] = p[1];
+      pts[t * 3 + 2] = p[2];
+    }
   }
 }
 
@@ -289,6 +323,8 @@ static int check_sampler(const ffb_sampler_desc* d) {
   FFB_REQUIRE(d, "null descriptor");
   FFB_REQUIRE(d->n_samples > 0, "n_samples must be positive");
   if (d->alpha_volume) FFB_REQUIRE(d->alpha_size[0] > 0 && d->alpha_size[1] > 0 && d->alpha_size[2] > 0, "bad alpha volume size");
+  FFB_REQUIRE(d->mode >= FFB_SAMPLE_BOUNDED && d->mode <= FFB_SAMPLE_UNBOUND, "unknown sampling mode");
+  if (d->mode != FFB_SAMPLE_BOUNDED) FFB_REQUIRE(d->z_table, "z_table is required for the NDC / unbounded sampling modes");
   return FFB_OK;
 }
 
@@ -339,12 +375,12 @@ int ffb_sample_fill(const ffb_sampler_desc* h_desc, const float* rays, const flo
 }
 
 int ffb_sample_dense(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter, int64_t R, uint8_t* mask, float* z,
-                     void* stream) {
+                     float* pts, void* stream) {
   int rc = check_sampler(h_desc);
   if (rc) return rc;
   FFB_REQUIRE(rays && mask, "null argument");
   if (R <= 0) return FFB_OK;
-  sample_dense_kernel<<<blocks_for(R * h_desc->n_samples, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, rays, jitter, R, mask, z);
+  sample_dense_kernel<<<blocks_for(R * h_desc->n_samples, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*h_desc, rays, jitter, R, mask, z, pts);
   FFB_LAUNCHED();
   return FFB_OK;
 }
@@ -373,7 +409,7 @@ int ffb_sample_dense_host(const ffb_sampler_desc* h_desc, const float* h_rays, c
   if (h_z) FFB_CUDA(cudaMalloc(&d_z, sizeof(float) * R * S));
   FFB_CUDA(cudaMemcpyAsync(d_rays, h_rays, sizeof(float) * R * 6, cudaMemcpyHostToDevice, s));
   if (h_jitter) FFB_CUDA(cudaMemcpyAsync(d_jit, h_jitter, sizeof(float) * R, cudaMemcpyHostToDevice, s));
-  rc = ffb_sample_dense(h_desc, d_rays, d_jit, R, d_mask, d_z, s);
+  rc = ffb_sample_dense(h_desc, d_rays, d_jit, R, d_mask, d_z, nullptr, s);
   if (rc == FFB_OK) rc = check_cuda(cudaMemcpyAsync(h_mask, d_mask, R * S, cudaMemcpyDeviceToHost, s), "D2H mask");
   if (rc == FFB_OK && h_z) rc = check_cuda(cudaMemcpyAsync(h_z, d_z, sizeof(float) * R * S, cudaMemcpyDeviceToHost, s), "D2H z");
   if (rc == FFB_OK) rc = check_cuda(cudaStreamSynchronize(s), "sync");

@@ -510,9 +510,10 @@ class FactorFields(torch.nn.Module):
             return None
         return torch.rand(n_rays, 1)[:, 0].to(self.device)
 
-    def _sampler_desc(self, N_samples, with_alpha, alpha_thres=0.5):
+    def _sampler_desc(self, N_samples, with_alpha, alpha_thres=0.5, mode=ops.SAMPLE_BOUNDED, z_table=None):
         return ops.make_sampler_desc(self.aabb[:, :self.in_dim], self.stepSize, N_samples,
-                                     alpha=self.alphaMask if with_alpha else None, alpha_thres=alpha_thres)
+                                     alpha=self.alphaMask if with_alpha else None, alpha_thres=alpha_thres,
+                                     mode=mode, z_table=z_table, bg_len=getattr(self, 'bg_len', 0.0))
 
     def sample_point(self, rays_o, rays_d, is_train=True, N_samples=-1):
         """FactorFields.py:586-602 -> (rays_pts [R,S,3], interpx [R,S], ~mask_outbbox [R,S])"""
@@ -523,11 +524,50 @@ class FactorFields(torch.nn.Module):
         pts = rays[:, None, :3] + rays[:, None, 3:6] * z[..., None]
         return pts, z, mask
 
+    def _z_uniform(self, n, is_train):
+        """The per-SAMPLE uniforms of sample_point_ndc (:579, torch.rand_like on a [1,S] row) and sample_point_unbound
+        (:612); drawn from the CPU generator so that runs are reproducible against the reference's CPU path."""
+        return torch.rand(1, n)[0] if is_train else None
+
+    def _z_table_ndc(self, N_samples, is_train):
+        """interpx of FactorFields.py:577-580: a handful of host-evaluated scalars shared by all rays."""
+        near, far = self.cfg.dataset.near_far
+        interpx = torch.linspace(near, far, N_samples).unsqueeze(0)
+        u = self._z_uniform(N_samples, is_train)
+        if u is not None:
+            interpx += u[None] * ((far - near) / N_samples)
+        return interpx[0].contiguous().to(self.device)
+
+    def _z_table_unbound(self, N_samples, is_train):
+        """interpx of FactorFields.py:607-623: 3/4 of the samples linear in [0,2], 1/4 in inverse depth out to 32."""
+        N_inner, N_outer = 3 * N_samples // 4, N_samples // 4
+        b_inner = torch.linspace(0, 2, N_inner + 1)
+        b_outer = 2 / torch.linspace(1, 1 / 16, N_outer + 1)
+        rng = self._z_uniform(N_inner + N_outer, is_train)
+        if rng is not None:
+            interpx = torch.cat([b_inner[1:] * rng[:N_inner] + b_inner[:-1] * (1 - rng[:N_inner]),
+                                 b_outer[1:] * rng[N_inner:] + b_outer[:-1] * (1 - rng[N_inner:])])
+        else:
+            interpx = torch.cat([(b_inner[1:] + b_inner[:-1]) * 0.5, (b_outer[1:] + b_outer[:-1]) * 0.5])
+        return interpx.contiguous().to(self.device)
+
     def sample_point_ndc(self, rays_o, rays_d, is_train=True, N_samples=-1):
-        raise NotImplementedError('NDC sampling (FactorFields.py:575-584, llff only) is not on the bounded-scene hot path yet')
+        """FactorFields.py:575-584 -> (rays_pts [R,S,3], interpx [1,S], ~mask_outbbox [R,S])"""
+        N_samples = N_samples if N_samples > 0 else self.nSamples
+        rays = torch.cat([rays_o, rays_d], -1).to(self.device).float()
+        zt = self._z_table_ndc(N_samples, is_train)
+        mask, _, pts = ops.sample_dense(self._sampler_desc(N_samples, False, mode=ops.SAMPLE_NDC, z_table=zt), rays, None,
+                                        want_z=False, want_pts=True)
+        return pts, zt[None], mask
 
     def sample_point_unbound(self, rays_o, rays_d, is_train=True, N_samples=-1):
-        raise NotImplementedError('unbounded sampling (FactorFields.py:604-633, 360_v2 only) is not on the bounded-scene hot path yet')
+        """FactorFields.py:604-633 -> (contracted rays_pts [R,S,3], interpx [1,S], inner_mask [R,S])"""
+        N_samples = N_samples if N_samples > 0 else self.nSamples
+        rays = torch.cat([rays_o, rays_d], -1).to(self.device).float()
+        zt = self._z_table_unbound(N_samples, is_train)
+        mask, _, pts = ops.sample_dense(self._sampler_desc(zt.numel(), False, mode=ops.SAMPLE_UNBOUND, z_table=zt), rays, None,
+                                        want_z=False, want_pts=True)
+        return pts, zt[None], mask
 
     def normalize_coord(self, xyz_sampled):
         """FactorFields.py:635-637"""
@@ -710,15 +750,23 @@ class FactorFields(torch.nn.Module):
 
     # ---- the render step (FactorFields.py:843-898) ----------------------------------------------------
     def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1):
-        if self.is_unbound or ndc_ray:
-            raise NotImplementedError('only bounded, non-NDC scenes are on the CUDA hot path (FactorFields.py:859-861)')
         if not rays_chunk.is_cuda:
             raise RuntimeError('rays must be on the CUDA device (renderer.render_ray does the host->device copy)')
         N_samples = N_samples if N_samples > 0 else self.nSamples
         rays = rays_chunk[:, :6].contiguous().float()
-        jitter = self._jitter(rays.shape[0], is_train)
         lazy = bool(getattr(self, 'lazy_counts', False)) and not (self._coeff_is_mlp() or self._basis_is_mlp())
-        samp = ops.sample_compact(self._sampler_desc(N_samples, self.alphaMask is not None), rays, jitter, lazy=lazy)
+        with_alpha = self.alphaMask is not None
+        if self.is_unbound:     # :847-850
+            zt = self._z_table_unbound(N_samples, is_train)
+            N_samples = zt.numel()   # 3N//4 + N//4 can be below N
+            samp = ops.sample_compact(self._sampler_desc(N_samples, with_alpha, mode=ops.SAMPLE_UNBOUND, z_table=zt), rays, None, lazy=lazy)
+        elif ndc_ray:           # :851-857; the appearance MLP sees unit view directions
+            zt = self._z_table_ndc(N_samples, is_train)
+            samp = ops.sample_compact(self._sampler_desc(N_samples, with_alpha, mode=ops.SAMPLE_NDC, z_table=zt), rays, None, lazy=lazy)
+            samp['rays'] = torch.cat([rays[:, :3], rays[:, 3:6] / torch.norm(rays[:, 3:6], dim=-1, keepdim=True)], -1).contiguous()
+        else:                   # :858-861
+            jitter = self._jitter(rays.shape[0], is_train)
+            samp = ops.sample_compact(self._sampler_desc(N_samples, with_alpha), rays, jitter, lazy=lazy)
         self.last_stats = {'n_valid': samp['n_valid'], 'n_candidates': rays.shape[0] * N_samples}
 
         if not (white_bg or (is_train and torch.rand((1,)) < 0.5)):

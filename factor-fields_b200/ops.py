@@ -377,8 +377,24 @@ class MLPFunction(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------
 # Sampling + compaction (no gradient)
 # --------------------------------------------------------------------------------------------------
-def make_sampler_desc(aabb, step_size, n_samples, alpha=None, alpha_thres=0.5):
+SAMPLE_BOUNDED, SAMPLE_NDC, SAMPLE_UNBOUND = 0, 1, 2
+# bf16 parts per operand of the appearance MLP forward (3: ~3e-7 relative.  With 2 parts (~5e-6) enough ReLU decisions flip
+# against the reference that hidden-layer weight gradients differ by 5e-4 — measured, scratch/diag_relu_flip.py)
+APPEARANCE_TERMS = 3
+
+
+def make_sampler_desc(aabb, step_size, n_samples, alpha=None, alpha_thres=0.5, mode=SAMPLE_BOUNDED, z_table=None, bg_len=0.0):
+    """mode / z_table: FFB_SAMPLE_* of include/ffb200.h; z_table is the device [n_samples] interpx row of
+    sample_point_ndc / sample_point_unbound (the descriptor keeps a reference so the buffer outlives the launches)."""
     d = nv.SamplerDesc()
+    d.mode, d.bg_len = int(mode), float(bg_len)
+    if mode != SAMPLE_BOUNDED:
+        if z_table is None or not z_table.is_cuda or z_table.dtype != torch.float32 or z_table.numel() != int(n_samples):
+            raise RuntimeError('NDC / unbounded sampling needs a CUDA float32 z_table with n_samples entries')
+        d._keep = z_table.contiguous()
+        d.z_table = d._keep.data_ptr()
+    else:
+        d.z_table = 0
     lo, hi = host_list(aabb)
     for k in range(3):
         d.aabb_min[k], d.aabb_max[k] = lo[k], hi[k]
@@ -439,14 +455,17 @@ def sample_compact(desc, rays, jitter, lazy=False):
 
 
 @torch.no_grad()
-def sample_dense(desc, rays, jitter, want_z=True):
+def sample_dense(desc, rays, jitter, want_z=True, want_pts=False):
     _dev_check(rays)
     rays = rays.contiguous().float()
     R, S = rays.shape[0], desc.n_samples
     mask = _empty((R, S), rays, torch.uint8)
     z = _empty((R, S), rays) if want_z else None
+    pts = _empty((R, S, 3), rays) if want_pts else None
     nv.check(nv.lib().ffb_sample_dense(C.byref(desc), nv.ptr(rays), nv.ptr(jitter, allow_none=True), C.c_int64(R),
-                                       nv.ptr(mask, torch.uint8), nv.ptr(z, allow_none=True), nv.stream()))
+                                       nv.ptr(mask, torch.uint8), nv.ptr(z, allow_none=True), nv.ptr(pts, allow_none=True), nv.stream()))
+    if want_pts:
+        return mask.bool(), z, pts
     return mask.bool(), z
 
 
@@ -511,7 +530,7 @@ class RenderComposite(torch.autograd.Function):
                 for l, (W, b) in enumerate(layers):
                     act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
                     kinds.append(act)
-                    h = _linear_fwd(h, W, b, act, a_dev, terms=2)   # colours: 5e-6 is ample (bar 1e-4), half the MMAs
+                    h = _linear_fwd(h, W, b, act, a_dev, terms=APPEARANCE_TERMS)
                     acts.append(h)
             rgb = h
         else:
@@ -663,14 +682,20 @@ def adam_multi(table, chunk_tensor, chunk_start, chunk, hyper_d, beta1, beta2, e
 
 
 @torch.no_grad()
-def mse_fwd_bwd(pred, target, g_scale=1.0, loss=None):
-    """-> (loss [1] device tensor, g_pred)"""
+def scalar_decay(value_d, factor, out_f32=None):
+    """value_d [1] float64 (device) *= factor; out_f32 [1] float32 receives the rounded copy."""
+    nv.check(nv.lib().ffb_scalar_decay(nv.ptr(value_d, torch.float64), C.c_double(factor), nv.ptr(out_f32, allow_none=True), nv.stream()))
+
+
+@torch.no_grad()
+def mse_fwd_bwd(pred, target, g_scale=1.0, loss=None, g_scale_dev=None):
+    """-> (loss [1] device tensor, g_pred); g_scale_dev: optional device float32 scalar multiplied into g_pred."""
     pred, target = pred.contiguous(), target.contiguous()
     if loss is None:
         loss = torch.zeros(1, device=pred.device)
     else:
         loss.zero_()
     g = torch.empty_like(pred)
-    nv.check(nv.lib().ffb_mse_fwd_bwd(nv.ptr(pred), nv.ptr(target), C.c_int64(pred.numel()), C.c_float(g_scale), nv.ptr(loss), nv.ptr(g),
-                                      nv.stream()))
+    nv.check(nv.lib().ffb_mse_fwd_bwd(nv.ptr(pred), nv.ptr(target), C.c_int64(pred.numel()), C.c_float(g_scale), nv.ptr(g_scale_dev, allow_none=True),
+                                      nv.ptr(loss), nv.ptr(g), nv.stream()))
     return loss, g

@@ -270,6 +270,131 @@ class TrainStep:
         self.lr_d.copy_(torch.tensor(lrs, dtype=torch.float64))
 
 
+class RegressStep(TrainStep):
+    """One optimisation step of the reference's regression loops — 2-D image (scripts/2D_regression.ipynb cell 4), SDF
+    (scripts/sdf_regression.ipynb cell 2) and image set (scripts/2D_set_regression.py:120-142):
+
+        feats, _ = model.get_coding(x);  y = model.linear_mat(feats, is_train);  loss = mean((y - target)^2)
+        (loss * loss_scale).backward();  Adam step;  loss_scale *= 0.1 ** (1 / n_iter)   [scale decays instead of the lr]
+
+    as ONE replayable CUDA graph (field-query kernel -> fused MLP -> MSE -> MLP backward -> scatter -> multi-tensor
+    Adam), with the loss scale kept in device memory.  x [B, d] are coordinates in aabb units (pixel centres /
+    [0, 640]^3 points / (x, y, image+0.5)), target [B, out_dim].  `step` returns the UNSCALED loss like the notebooks print."""
+
+    def __init__(self, model, param_groups, batch, x_dim, out_dim, loss_scale_decay=1.0, is_train=False, betas=(0.9, 0.99),
+                 eps=1e-8, group=None, use_graph=True, warmup=2):
+        super().__init__(model, param_groups, batch, n_samples=1, betas=betas, eps=eps, lr_decay=1.0, group=group,
+                         use_graph=use_graph, warmup=warmup)
+        model.lazy_counts = False
+        self.is_train, self.loss_scale_decay = bool(is_train), float(loss_scale_decay)
+        self.rays_s = torch.zeros(self.B, int(x_dim), device=self.dev)         # coordinates
+        self.target_s = torch.zeros(self.B, int(out_dim), device=self.dev)
+        self.scale_d = torch.ones(1, dtype=torch.float64, device=self.dev)     # loss_scale (a Python double in the notebooks)
+        self.scale_f = torch.ones(1, dtype=torch.float32, device=self.dev)
+
+    def _render_backward(self):
+        from . import ops as _ops
+        m = self.model
+        self.bucket.flat.zero_()
+        _ops.scalar_decay(self.scale_d, self.loss_scale_decay, self.scale_f)    # `loss_scale *= lr_factor` opens the iteration
+        _ops.set_grad_arena(self.arena)
+        try:
+            feats, _ = m.get_coding(self.rays_s)
+            y = m.linear_mat(feats, is_train=self.is_train)
+            _, g_y = _ops.mse_fwd_bwd(y.reshape(self.B, -1), self.target_s, loss=self.loss_s, g_scale_dev=self.scale_f)
+            grads = torch.autograd.grad([y], self.params, grad_outputs=[g_y.view_as(y)], allow_unused=True)
+        finally:
+            _ops.set_grad_arena(None)
+        for k, g in enumerate(grads):
+            if g is not None:
+                v = self.bucket.view(k)
+                if g.data_ptr() != v.data_ptr():
+                    v.copy_(g)
+
+    def _capture(self):
+        st = (self.scale_d.clone(), self.scale_f.clone())
+        super()._capture()                      # the warm-up passes advanced the loss scale; captured replays start from `st`
+        self.scale_d.copy_(st[0]); self.scale_f.copy_(st[1])
+
+    def step(self, x, target):
+        """x [B, d], target [B, out_dim]: host (ideally pinned) or device fp32 tensors -> loss (1-element device tensor)."""
+        if x.shape[0] != self.B:
+            raise RuntimeError(f'RegressStep was built for batches of {self.B} points, got {x.shape[0]}')
+        self._check_params()
+        if self.graph is None:
+            self._capture()
+        self.rays_s.copy_(x, non_blocking=True)
+        self.target_s.copy_(target.reshape(self.B, -1), non_blocking=True)
+        if not self.graph:
+            self._body()
+        elif len(self.graph) == 1:
+            self.graph[0].replay()
+        else:
+            self.graph[0].replay()
+            self._all_reduce()
+            self.graph[1].replay()
+        return self.loss_s
+
+    def snapshot(self):
+        return super().snapshot() + (self.scale_d.clone(), self.scale_f.clone())
+
+    @torch.no_grad()
+    def restore(self, snap):
+        super().restore(snap[:5])
+        self.scale_d.copy_(snap[5]); self.scale_f.copy_(snap[6])
+
+
+@torch.no_grad()
+def evaluate_field(model, coords, chunk=10240, is_train=False):
+    """Dense evaluation of the regressed signal (eval_img of scripts/2D_regression.ipynb cell 1, eval_sdf /
+    cal_l1_iou of scripts/sdf_regression.ipynb cell 1): model.linear_mat(model.get_coding(x)) over `coords` [N, d]
+    (host or device) in chunks; returns a device tensor [N, out_dim]."""
+    out = []
+    for c in torch.split(coords, chunk, dim=0):
+        feats, _ = model.get_coding(c.to(model.device, non_blocking=True).float())
+        out.append(model.linear_mat(feats, is_train=is_train))
+    return torch.cat(out)
+
+
+def regression(cfg, model, coords, targets, n_iters=None, batch_size=None, index_fn=None, scale_loss=None, log=None,
+               use_graph=True):
+    """The regression drivers of the reference (scripts/2D_regression.ipynb, sdf_regression.ipynb,
+    2D_set_regression.py) on a GPU-resident sample set: coords [N, d] / targets [N, out_dim] are moved to the device once
+    (the notebooks' 8-worker DataLoader + per-step H2D copy is replaced by a device gather), every step draws
+    `idx = torch.randint(0, N, (batch,))` on the CPU generator exactly like sdf_regression.ipynb cell 2 (or calls
+    `index_fn(step)` -> LongTensor), and runs one RegressStep.  scale_loss: True for the image / sdf notebooks (loss *
+    0.1**(k/n_iter)), False for the image set script (its scaling line is commented out); default by cfg.defaults.mode.
+    Returns dict(loss=[per step], steps, seconds)."""
+    import time
+    t = cfg.training
+    n_iters = int(n_iters if n_iters is not None else t.n_iters)
+    B = int(batch_size if batch_size is not None else t.batch_size)
+    if scale_loss is None:
+        scale_loss = cfg.defaults.mode != 'images'
+    dev = model.device
+    coords_d = coords.to(dev).float().contiguous()
+    targets_d = targets.to(dev).float().reshape(coords.shape[0], -1).contiguous()
+    N = coords_d.shape[0]
+    decay = 0.1 ** (1.0 / n_iters) if scale_loss else 1.0
+    rs = RegressStep(model, model.get_optparam_groups(t.lr_small, t.lr_large), batch=B, x_dim=coords_d.shape[1],
+                     out_dim=targets_d.shape[1], loss_scale_decay=decay, is_train=True, use_graph=use_graph)
+    losses = []
+    loss_hist = torch.zeros(n_iters, device=dev)
+    torch.cuda.synchronize(dev)
+    t0 = time.time()
+    for it in range(n_iters):
+        idx = index_fn(it) if index_fn is not None else torch.randint(0, N, (B,))
+        idx = idx.to(dev, non_blocking=True)
+        loss = rs.step(coords_d.index_select(0, idx), targets_d.index_select(0, idx))
+        loss_hist[it:it + 1].copy_(loss)          # no host sync per step; the notebooks read the loss only to print it
+        if log is not None and it % 100 == 0:
+            log(f'Iteration {it:05d}: loss_dist = {float(loss.item()):.8f}')
+    torch.cuda.synchronize(dev)
+    seconds = time.time() - t0
+    losses = loss_hist.tolist()
+    return dict(loss=losses, steps=n_iters, seconds=seconds, step=rs)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Training-loop host (train_per_scene.py:89-234 `reconstruction`): same schedule, same optimiser bookkeeping, same RNG
 # consumption (numpy permutation sampler + one torch CPU uniform per ray), with the per-step work in TrainStep.

@@ -224,6 +224,13 @@ int ffb_render_input_bwd(const float* feat, int32_t ld_feat, const int32_t* app_
  * Ray sampling + alpha-mask stream compaction: sample_point (:586-602), AlphaGridMask.sample_alpha
  * (:103-110) and the boolean-mask indexing of forward (:864-867,874).
  * ------------------------------------------------------------------------------------------- */
+enum {
+  FFB_SAMPLE_BOUNDED = 0, /* sample_point (:586-602): march from the box entry with step_size, keep in-box samples */
+  FFB_SAMPLE_NDC = 1,     /* sample_point_ndc (:575-584): interpx from z_table, keep in-box samples, dists * |d| (:854-856) */
+  FFB_SAMPLE_UNBOUND = 2  /* sample_point_unbound (:604-633): interpx from z_table, inf-norm contraction of the points
+                             outside the unit cube, every sample kept (:863), last dist repeats the previous (:850) */
+};
+
 typedef struct ffb_sampler_desc {
   float aabb_min[3], aabb_max[3];
   float step_size;              /* self.stepSize (:697), an fp32 value */
@@ -233,6 +240,9 @@ typedef struct ffb_sampler_desc {
   float alpha_aabb_min[3];
   float alpha_inv_size[3];      /* AlphaGridMask.invgridSize (:98) */
   float alpha_thres;            /* > thres keeps the sample: 0.5 in forward (:866), 0 in filtering (:833) */
+  int32_t mode;                 /* FFB_SAMPLE_* */
+  float bg_len;                 /* self.bg_len (:250), FFB_SAMPLE_UNBOUND only */
+  const float* z_table;         /* device [n_samples]: the interpx row shared by all rays (:578-580, :611-623); NULL in mode 0 */
 } ffb_sampler_desc;
 
 /* Pass 1: counts[r] = number of valid samples of ray r; tmin[r] = entry distance.
@@ -246,9 +256,10 @@ int ffb_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t R, v
 int ffb_sample_fill(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter,
                     const float* tmin, const int32_t* offsets, int64_t R, int64_t cap, float* xyz,
                     int32_t* ray_id, int32_t* sample_id, float* z, float* dist, void* stream);
-/* Dense variant used by parity tests / filtering_rays: mask [R, S] (uint8), z [R,S] or NULL. */
+/* Dense variant behind the sample_point* methods and the parity tests: mask [R,S] (uint8; in-box / inner mask, or
+ * ray_valid when an alpha volume is attached), z [R,S] or NULL, pts [R,S,3] or NULL (contracted in mode 2). */
 int ffb_sample_dense(const ffb_sampler_desc* h_desc, const float* rays, const float* jitter, int64_t R,
-                     uint8_t* mask, float* z, void* stream);
+                     uint8_t* mask, float* z, float* pts, void* stream);
 /* sample_alpha (:103-110) for arbitrary points: out [n] float. */
 int ffb_alpha_sample(const ffb_sampler_desc* h_desc, const float* xyz, int64_t n, float* out, void* stream);
 
@@ -290,9 +301,12 @@ int ffb_density_alpha(const ffb_composite_desc* h_desc, const float* feat0, int3
  * Train-step glue: loss (train_per_scene.py:158) and Adam (:124-132,160-162,170-171).
  * ------------------------------------------------------------------------------------------- */
 /* loss[0] += mean((pred-target)^2) over n elements (loss must be zeroed by the caller);
- * g_pred = 2 (pred-target)/n * g_scale. */
-int ffb_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float g_scale, float* loss,
-                    float* g_pred, void* stream);
+ * g_pred = 2 (pred-target)/n * g_scale * (g_scale_dev ? *g_scale_dev : 1): g_scale_dev is an optional DEVICE
+ * scalar, e.g. the decaying loss scale of scripts/2D_regression.ipynb cell 4 / sdf_regression.ipynb cell 2. */
+int ffb_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float g_scale,
+                    const float* g_scale_dev, float* loss, float* g_pred, void* stream);
+/* *d_value *= factor in double (the notebooks' `loss_scale *= lr_factor`); *d_out_f32 = (float)*d_value if given. */
+int ffb_scalar_decay(double* d_value, double factor, float* d_out_f32, void* stream);
 /* torch.optim.Adam semantics (no amsgrad, no weight decay), fp32; step is 1-based. grad_scale
  * multiplies g first (1/world after a sum all-reduce). */
 int ffb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

@@ -505,6 +505,70 @@ def sample_point(aabb, stepSize, rays_o, rays_d, N_samples, jitter=None):
     return pts, interpx, ~out
 
 
+def ndc_interpx(near, far, N_samples, uniform=None):
+    """:577-580 — linspace(near, far, N) (+ uniform [N] * (far-near)/N when training), fp32."""
+    interpx = _linspace(near, far, N_samples)
+    if uniform is not None:
+        interpx = (interpx + (_f(uniform) * f32((far - near) / N_samples)).astype(np.float32)).astype(np.float32)
+    return interpx
+
+
+def _linspace(start, end, steps):
+    """torch.linspace for float32 on the CPU (ATen cpu/RangeFactoriesKernel.cpp, third-party): step = (end-start)/
+    (steps-1) in fp32; element i is fma(step, i, start) for i < steps//2 and fma(-step, steps-1-i, end) otherwise
+    (the compiled kernel contracts the multiply-add; step*i is exact in fp64, so fp64 evaluation + one rounding
+    reproduces it — checked here against torch.linspace on 300 random (start, end, steps))."""
+    if steps == 1:
+        return np.array([start], np.float32)
+    start, end = f32(start), f32(end)
+    step = f32((end - start) / f32(steps - 1))
+    i = np.arange(steps)
+    lo = (np.float64(start) + np.float64(step) * i).astype(np.float32)
+    hi = (np.float64(end) - np.float64(step) * (steps - 1 - i)).astype(np.float32)
+    return np.where(i < steps // 2, lo, hi).astype(np.float32)
+
+
+def sample_point_ndc(aabb, interpx, rays_o, rays_d):
+    """:575-584 with interpx [S] given (ndc_interpx) -> pts [R,S,3], z [1,S], in-box mask [R,S]."""
+    aabb, o, d = _f(aabb), _f(rays_o), _f(rays_d)
+    z = _f(interpx)[None]
+    pts = (o[:, None, :] + (d[:, None, :] * z[..., None]).astype(np.float32)).astype(np.float32)
+    out = ((aabb[0] > pts) | (pts > aabb[1])).any(-1)
+    return pts, z, ~out
+
+
+def unbound_interpx(N_samples, uniform=None):
+    """:607-623 — bin edges linspace(0,2,Ni+1) and 2/linspace(1,1/16,No+1); a uniform point (training) or the
+    midpoint (evaluation) of every bin."""
+    Ni, No = 3 * N_samples // 4, N_samples // 4
+    bi = _linspace(0, 2, Ni + 1)
+    bo = (f32(2) / _linspace(1, 1 / 16, No + 1)).astype(np.float32)
+    if uniform is not None:
+        u = _f(uniform)
+        one = f32(1)
+        a = ((bi[1:] * u[:Ni]).astype(np.float32) + (bi[:-1] * (one - u[:Ni]).astype(np.float32)).astype(np.float32)).astype(np.float32)
+        b = ((bo[1:] * u[Ni:]).astype(np.float32) + (bo[:-1] * (one - u[Ni:]).astype(np.float32)).astype(np.float32)).astype(np.float32)
+    else:
+        a = ((bi[1:] + bi[:-1]).astype(np.float32) * f32(0.5)).astype(np.float32)
+        b = ((bo[1:] + bo[:-1]).astype(np.float32) * f32(0.5)).astype(np.float32)
+    return np.concatenate([a, b]).astype(np.float32)
+
+
+def sample_point_unbound(bg_len, interpx, rays_o, rays_d):
+    """:625-633 -> contracted pts [R,S,3], z [1,S], inner mask [R,S]."""
+    o, d = _f(rays_o), _f(rays_d)
+    z = _f(interpx)[None]
+    pts = (o[:, None, :] + (d[:, None, :] * z[..., None]).astype(np.float32)).astype(np.float32)
+    norm = np.abs(pts).max(-1, keepdims=True)
+    inner = norm <= 1
+    with np.errstate(divide='ignore', invalid='ignore'):
+        # `self.bg_len / norm` is Tensor.__rtruediv__ = norm.reciprocal() * bg_len
+        s = (f32(1 + bg_len) - ((f32(1) / norm).astype(np.float32) * f32(bg_len)).astype(np.float32)).astype(np.float32)
+        con = ((pts / norm).astype(np.float32) * s).astype(np.float32)
+    pts = np.where(inner, pts, con).astype(np.float32)
+    return pts, z, inner[..., 0]
+
+
 def sample_alpha(alpha_volume, aabb, xyz):
     """AlphaGridMask.sample_alpha (:103-110); alpha_volume [D,H,W] float 0/1."""
     aabb = _f(aabb)
@@ -542,13 +606,33 @@ class RenderOracle:
             return np.where(x > f32(20), f32(1), sigmoid(x)).astype(np.float32)
         return (x > 0).astype(np.float32)
 
-    def forward(self, rays, N_samples, jitter=None, white_bg=True, want_cache=False):
+    def forward(self, rays, N_samples, jitter=None, white_bg=True, want_cache=False, mode='bounded'):
+        """mode 'bounded' (jitter [R], :858-861), 'ndc' (jitter = uniform [S], rspec near_far; :851-857) or
+        'unbound' (jitter = uniform [3S//4 + S//4], rspec bg_len; :847-850)."""
         rays = _f(rays)
         o, viewdirs = rays[:, :3], rays[:, 3:6]
-        pts, z, inner = sample_point(self.r['aabb'], self.r['stepSize'], o, viewdirs, N_samples, jitter)
-        R, S = z.shape
-        dists = np.concatenate([z[:, 1:] - z[:, :-1], np.zeros_like(z[:, :1])], -1).astype(np.float32)
-        valid = inner.copy()
+        if mode == 'unbound':
+            pts, z, inner = sample_point_unbound(self.r['bg_len'], unbound_interpx(N_samples, jitter), o, viewdirs)
+            dists = np.concatenate([z[:, 1:] - z[:, :-1], z[:, -1:] - z[:, -2:-1]], -1).astype(np.float32)
+            R, S = o.shape[0], z.shape[1]
+            valid = np.ones((R, S), bool)
+            dists = np.broadcast_to(dists, (R, S))
+            z = np.broadcast_to(z, (R, S))
+        elif mode == 'ndc':
+            near, far = self.r['near_far']
+            pts, z, inner = sample_point_ndc(self.r['aabb'], ndc_interpx(near, far, N_samples, jitter), o, viewdirs)
+            dists = np.concatenate([z[:, 1:] - z[:, :-1], np.zeros_like(z[:, :1])], -1).astype(np.float32)
+            norm = np.sqrt((viewdirs * viewdirs).sum(-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+            dists = (dists * norm).astype(np.float32)
+            viewdirs = (viewdirs / norm).astype(np.float32)
+            R, S = dists.shape
+            z = np.broadcast_to(z, (R, S))
+            valid = inner.copy()
+        else:
+            pts, z, inner = sample_point(self.r['aabb'], self.r['stepSize'], o, viewdirs, N_samples, jitter)
+            R, S = z.shape
+            dists = np.concatenate([z[:, 1:] - z[:, :-1], np.zeros_like(z[:, :1])], -1).astype(np.float32)
+            valid = inner.copy()
         if self.alpha is not None:
             a = sample_alpha(self.alpha['volume'], self.alpha['aabb'], pts[inner]) > f32(0.5)
             valid[inner] = a

@@ -100,3 +100,62 @@ class TorchPort:
         loss.backward()
         self.opt.step()
         return float(loss)
+
+
+class RegressPort:
+    """The reference's regression step for grid x grid fields (scripts/2D_regression.ipynb cell 4, sdf_regression.ipynb
+    cell 2, 2D_set_regression.py:120-142) restated with the torch CPU operators it calls:
+    get_coding (FactorFields.py:425-434, 467-490, 523-527) -> linear_mat (:144-159) -> MSE * loss_scale -> Adam.
+
+    state: reference-layout numpy state_dict; aabb [2, d(+1)] as `self.aabb`; in_dim 2 or 3; `images` mode when the
+    coefficient tensor has one more spatial axis than in_dim (x[..., -1] selects the image slab, :287, :469-470)."""
+
+    def __init__(self, state, aabb, freq_bands, in_dim, coef_mode='bilinear', basis_mode='bilinear', lr_small=0.001, lr_large=0.02,
+                 loss_scale_decay=1.0):
+        self.p = {k: torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(v)).float()) for k, v in state.items()}
+        self.aabb = torch.tensor(np.asarray(aabb), dtype=torch.float32)
+        self.freq = torch.tensor(np.asarray(freq_bands), dtype=torch.float32)
+        self.in_dim, self.coef_mode, self.basis_mode = in_dim, coef_mode, basis_mode
+        self.n_basis = len([k for k in state if k.startswith('basises.')])
+        self.n_layers = len([k for k in state if k.startswith('linear_mat.backbone.') and k.endswith('.weight')])
+        small = [v for k, v in self.p.items() if k.startswith('linear_mat')]
+        large = [v for k, v in self.p.items() if k.startswith(('coeffs', 'basises'))]
+        self.opt = torch.optim.Adam([{'params': small, 'lr': lr_small}, {'params': large, 'lr': lr_large}], betas=(0.9, 0.99))
+        self.loss_scale, self.decay = 1.0, loss_scale_decay
+
+    def get_coding(self, x):
+        N, dim = x.shape
+        inv = 2.0 / (self.aabb[1] - self.aabb[0])
+        pts = ((x - self.aabb[0]) * inv - 1).view([1, -1] + [1] * (dim - 1) + [dim])
+        coeff = F.grid_sample(self.p['coeffs.0'], pts, mode=self.coef_mode, align_corners=False, padding_mode='border').view(-1, N).t()
+        xb = x[..., :self.in_dim]
+        ab = self.aabb[:, :self.in_dim]
+        scale = max(ab[1] - ab[0])[..., None] / self.freq                               # grid_mapping, sawtooth (:11-22)
+        local = ((xb - ab[0])[..., None] % scale / (scale / 2) - 1).clamp(-1., 1.)
+        xyz = local.view(1, *([1] * (self.in_dim - 1)), -1, self.in_dim, self.freq.numel())
+        bs = [F.grid_sample(self.p[f'basises.{i}'], xyz[..., i], mode=self.basis_mode, align_corners=True).view(-1, N).T
+              for i in range(self.n_basis)]
+        return torch.cat(bs, dim=-1) * coeff, coeff
+
+    def linear_mat(self, h, dropout_keep=None):
+        if dropout_keep is not None:                                                    # F.dropout(p=0.1) with a given mask
+            h = h * dropout_keep * (1.0 / 0.9)
+        for l in range(self.n_layers):
+            h = F.linear(h, self.p[f'linear_mat.backbone.{l}.weight'], self.p.get(f'linear_mat.backbone.{l}.bias'))
+            if l != self.n_layers - 1:
+                h = F.relu(h)
+        return h
+
+    def predict(self, x):
+        with torch.no_grad():
+            return self.linear_mat(self.get_coding(x)[0])
+
+    def train_step(self, x, target):
+        self.loss_scale *= self.decay
+        y = self.linear_mat(self.get_coding(x)[0])
+        loss_dist = torch.mean((y.reshape(target.shape) - target) ** 2)
+        loss = loss_dist * self.loss_scale
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return float(loss_dist.detach())

@@ -120,7 +120,30 @@ def blender_like_rays(R, seed, radius=4.0 / 1.5):
     return rays
 
 
-def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, is_train=True):
+def ndc_like_rays(R, seed):
+    """Rays shaped like dataLoader/ray_utils.py ndc_rays_blender output (llff): origins on the z=-1 plane,
+    directions with z = 2 (not unit length, so the |d| scaling of :854-856 matters)."""
+    rng = np.random.RandomState(seed)
+    rays = np.zeros((R, 6), np.float32)
+    rays[:, 0:2] = rng.uniform(-1.2, 1.2, (R, 2))
+    rays[:, 2] = -1.0
+    rays[:, 3:5] = rng.uniform(-0.6, 0.6, (R, 2))
+    rays[:, 5] = 2.0
+    return rays
+
+
+def inside_out_rays(R, seed):
+    """360-style rays: camera centres inside the unit cube, unit directions all around (the far samples leave the
+    cube and get contracted, :625-631)."""
+    rng = np.random.RandomState(seed)
+    rays = np.zeros((R, 6), np.float32)
+    rays[:, :3] = rng.uniform(-0.6, 0.6, (R, 3))
+    d = rng.normal(size=(R, 3))
+    rays[:, 3:] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    return rays
+
+
+def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, is_train=True, mode='bounded'):
     cfg, m = build('nerf.yaml', aabb, ov, seed)
     with torch.no_grad():  # make the density field non-trivial at init (density_shift = -10)
         m.linear_mat.backbone[0].weight.mul_(10.0)
@@ -132,29 +155,46 @@ def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, i
     if with_alpha:
         g = torch.Generator().manual_seed(seed + 5)
         vol = (torch.rand(24, 20, 28, generator=g) > 0.35).float()
-        m.alphaMask = AlphaGridMask('cpu', m.aabb, vol)
-    rays = torch.from_numpy(blender_like_rays(R, seed + 4))
-    rays[0, 3:] = torch.tensor([0.0, 0.0, -1.0])  # exercises the d == 0 -> 1e-6 branch (:588)
-    rays[0, :3] = torch.tensor([0.1, -0.2, 2.5])
+        m.alphaMask = AlphaGridMask('cpu', m.inward_aabb, vol)
+    if mode == 'ndc':
+        rays = torch.from_numpy(ndc_like_rays(R, seed + 4))
+    elif mode == 'unbound':
+        rays = torch.from_numpy(inside_out_rays(R, seed + 4))
+    else:
+        rays = torch.from_numpy(blender_like_rays(R, seed + 4))
+        rays[0, 3:] = torch.tensor([0.0, 0.0, -1.0])  # exercises the d == 0 -> 1e-6 branch (:588)
+        rays[0, :3] = torch.tensor([0.1, -0.2, 2.5])
     target = torch.rand(R, 3, generator=torch.Generator().manual_seed(seed + 6))
     torch.manual_seed(seed + 7)
-    jitter = torch.rand(R, 1)          # same stream as torch.rand_like(rng[:, [0]]) at :595
+    if mode == 'ndc':
+        jitter = torch.rand(1, N_samples).t()      # same stream as torch.rand_like(interpx [1,S]) at :579
+    elif mode == 'unbound':
+        jitter = torch.rand(3 * N_samples // 4 + N_samples // 4)[:, None]   # torch.rand((N_inner+N_outer), device=cpu) :612
+    else:
+        jitter = torch.rand(R, 1)          # same stream as torch.rand_like(rng[:, [0]]) at :595
     torch.manual_seed(seed + 7)
-    rgb_map, depth_map, coeffs = m(rays, white_bg=True, is_train=is_train, ndc_ray=False, N_samples=N_samples)
+    rgb_map, depth_map, coeffs = m(rays, white_bg=True, is_train=is_train, ndc_ray=(mode == 'ndc'), N_samples=N_samples)
     loss = torch.mean((rgb_map - target) ** 2)
     params = list(m.named_parameters())
     grads = torch.autograd.grad(loss, [p for _, p in params], allow_unused=True)
     # intermediate facts, recomputed with the same jitter
     torch.manual_seed(seed + 7)
     with torch.no_grad():
-        pts, z, inner = m.sample_point(rays[:, :3], rays[:, 3:6], is_train=is_train, N_samples=N_samples)
-        valid = inner.clone()
+        sampler = {'bounded': m.sample_point, 'ndc': m.sample_point_ndc, 'unbound': m.sample_point_unbound}[mode]
+        pts, z, inner = sampler(rays[:, :3], rays[:, 3:6], is_train=is_train, N_samples=N_samples)
+        valid = torch.ones_like(inner) if mode == 'unbound' else inner.clone()
         if m.alphaMask is not None:
             valid[inner.clone()] = m.alphaMask.sample_alpha(pts[inner]) > 0.5
         feats, _ = m.get_coding(pts[valid])
         feat = m.linear_mat(feats)
         sigma = torch.zeros(pts.shape[:-1]); sigma[valid] = m.basis2density(feat[..., 0])
-        dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), -1)
+        if mode == 'unbound':
+            dists = torch.cat((z[:, 1:] - z[:, :-1], z[:, -1:] - z[:, -2:-1]), -1)
+        else:
+            dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), -1)
+        if mode == 'ndc':
+            dists = dists * torch.norm(rays[:, 3:6], dim=-1, keepdim=True)
+        z = z.expand(pts.shape[:-1])
         from models.FactorFields import raw2alpha
         alpha, weight, _ = raw2alpha(sigma, dists * cfg.renderer.distance_scale)
         app = valid & (weight > cfg.renderer.rayMarch_weight_thres)
@@ -164,7 +204,13 @@ def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, i
                depth_map=depth_map.detach().numpy(), coeffs=coeffs.detach().numpy(), loss=loss.detach().numpy(),
                inner_mask=np.packbits(inner.numpy()), ray_valid=np.packbits(valid.numpy()),
                app_mask=np.packbits(app.numpy()), z=z.numpy(), weight=weight.numpy(), sigma=sigma.numpy(),
-               n_valid=np.array(int(valid.sum())), n_app=np.array(int(app.sum())))
+               n_valid=np.array(int(valid.sum())), n_app=np.array(int(app.sum())), mode=mode,
+               pts_sum=pts.double().sum((0, 1)).numpy())
+    if mode == 'ndc':
+        out['near_far'] = np.array(cfg.dataset.near_far, np.float64)
+    if mode == 'unbound':
+        out['bg_len'] = np.array(m.bg_len)
+        out['render_aabb'] = m.aabb.numpy()
     if with_alpha:
         out['alpha_volume'] = m.alphaMask.alpha_volume[0, 0].numpy()
         out['alpha_aabb'] = m.alphaMask.aabb.numpy()
@@ -279,6 +325,15 @@ if __name__ == '__main__':
         render_case('train', SMALL, CUBE)
         render_case('train_alpha', SMALL, BOX, with_alpha=True, seed=13)
         render_case('eval_alpha', SMALL, BOX, with_alpha=True, seed=17, is_train=False)
+    if not only or 'render_ndc' in only:
+        NDC_BOX = [[-1.5, -1.67, -1.0], [1.5, 1.67, 1.0]]      # dataLoader/llff.py scene_bbox
+        ndc = {**SMALL, 'dataset.near_far': [0.0, 1.0], 'dataset.ndc_ray': 1}
+        render_case('ndc_train', ndc, NDC_BOX, seed=19, mode='ndc')
+        render_case('ndc_eval_alpha', ndc, NDC_BOX, seed=23, mode='ndc', with_alpha=True, is_train=False)
+    if not only or 'render_unbound' in only:
+        unb = {**SMALL, 'dataset.is_unbound': True, 'renderer.fea2denseAct': 'relu'}   # configs/360_v2.yaml
+        render_case('unbound_train', unb, CUBE, seed=29, mode='unbound', N_samples=90)
+        render_case('unbound_eval_alpha', unb, CUBE, seed=31, mode='unbound', with_alpha=True, is_train=False, N_samples=90)
     if not only or 'sampler' in only:
         sampler_case()
     if not only or 'mlp' in only:

@@ -63,6 +63,12 @@ def test_config_loader_and_overrides():
     assert cfg.renderer.rayMarch_weight_thres == 1e-3 and isinstance(cfg.renderer.rayMarch_weight_thres, float)
     assert cfg.model.basis_type == 'vm' and cfg.training.n_iters == 100 and cfg.model.basis_dims == [18]
     assert cfg.training.lr_large == 0.02 and cfg.model.T_basis == 0      # inherited from defaults.yaml
+    # dot-list values carry YAML semantics like OmegaConf.from_cli (train_per_scene.py:245): booleans, null, exponents
+    cfg = ffb200.load_cfg('image_set.yaml', ['model.with_dropout=false', 'defaults.ckpt=null', 'renderer.alphaMask_thres=4e-2',
+                                             'dataset.is_unbound=true'])
+    assert cfg.model.with_dropout is False and cfg.defaults.ckpt is None and cfg.renderer.alphaMask_thres == 0.04
+    assert cfg.dataset.is_unbound is True
+    assert ffb200.load_cfg('360_v2.yaml').dataset.is_unbound is True and ffb200.load_cfg('360_v2.yaml').renderer.fea2denseAct == 'relu'
 
 
 @pytest.mark.parametrize('name', H.field_cases())

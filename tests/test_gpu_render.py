@@ -65,9 +65,11 @@ def _unpack(bits, shape):
     return np.unpackbits(bits)[:int(np.prod(shape))].reshape(shape).astype(bool)
 
 
-@pytest.mark.parametrize('name', ['train', 'train_alpha', 'eval_alpha'])
+@pytest.mark.parametrize('name', ['train', 'train_alpha', 'eval_alpha', 'ndc_train', 'ndc_eval_alpha', 'unbound_train',
+                                  'unbound_eval_alpha'])
 def test_render_golden(name):
-    """forward(): bit-exact sample indices / counts; rgb, depth, coeffs, loss and every parameter gradient within 1e-4."""
+    """forward(): bit-exact sample indices / counts; rgb, depth, coeffs, loss and every parameter gradient within 1e-4.
+    Bounded (sample_point), NDC (sample_point_ndc) and unbounded (sample_point_unbound) scenes."""
     from ffb200.models.FactorFields import AlphaGridMask
     from ffb200.renderer import render_ray
     from tests import gpu_helpers as G
@@ -79,12 +81,22 @@ def test_render_golden(name):
     is_train = bool(g['is_train'])
     S = int(g['N_samples'])
     R = g['rays'].shape[0]
-    if is_train:
-        m._jitter = lambda n, tr: G.t(g['jitter']) if tr else None      # inject the reference's random numbers
+    mode = str(g['mode']) if 'mode' in g else 'bounded'
+    if is_train:                                                           # inject the reference's random numbers
+        m._jitter = lambda n, tr: G.t(g['jitter']) if tr else None
+        m._z_uniform = lambda n, tr: torch.from_numpy(g['jitter']) if tr else None
     rays_host = torch.from_numpy(g['rays'])                                # host rays: render_ray does the H2D copy
-    out = render_ray(rays_host, m, chunk=4096, N_samples=S, white_bg=True, is_train=is_train, device='cuda')
+    out = render_ray(rays_host, m, chunk=4096, N_samples=S, ndc_ray=(mode == 'ndc'), white_bg=True, is_train=is_train, device='cuda')
     rgb_map, depth_map = out[0], out[1]
     aux = m.last_aux
+    S = g['z'].shape[1]                                                    # unbounded: 3S//4 + S//4 samples
+    # --- the public sample_point* methods: same masks / interpx / points as the reference's
+    sampler = {'bounded': m.sample_point, 'ndc': m.sample_point_ndc, 'unbound': m.sample_point_unbound}[mode]
+    pts, zz, inner = sampler(G.t(g['rays'][:, :3]), G.t(g['rays'][:, 3:6]), is_train=is_train, N_samples=int(g['N_samples']))
+    assert np.array_equal(np.packbits(G.npy(inner)), g['inner_mask'])
+    assert np.array_equal(np.broadcast_to(G.npy(zz), (R, S)), g['z'])
+    if 'pts_sum' in g:
+        assert np.allclose(G.npy(pts).astype(np.float64).sum((0, 1)), g['pts_sum'], rtol=1e-9, atol=1e-9)
     # --- bit-exact decisions
     valid_ref = _unpack(g['ray_valid'], (R, S))
     rr, ss = np.nonzero(valid_ref)

@@ -71,19 +71,30 @@ def test_sampler_bit_exact():
 def _render_oracle(g):
     spec = H.oracle_spec(g)
     fo = O.FieldOracle(spec, H.oracle_params(g))
+    ov = H.load_ref_cfg(g)[1]
     rspec = dict(aabb=g['fact.aabb'], stepSize=g['fact.stepSize'], distance_scale=25.0, density_shift=-10.0,
-                 fea2denseAct='softplus', rayMarch_weight_thres=1e-3, view_pe=6, fea_pe=2)
+                 fea2denseAct=ov.get('renderer.fea2denseAct', 'softplus'), rayMarch_weight_thres=1e-3, view_pe=6, fea_pe=2)
+    if 'near_far' in g:
+        rspec['near_far'] = g['near_far'].tolist()
+    if 'bg_len' in g:
+        rspec['bg_len'] = float(g['bg_len'])
     mlps = dict(linear_mat=H._layers(g, 'param.linear_mat'), renderModule=H._layers(g, 'param.renderModule'))
     alpha = dict(volume=g['alpha_volume'], aabb=g['alpha_aabb']) if 'alpha_volume' in g else None
     return O.RenderOracle(fo, rspec, mlps, alpha)
 
 
-@pytest.mark.parametrize('name', ['train', 'train_alpha', 'eval_alpha'])
+RENDER_CASES = ['train', 'train_alpha', 'eval_alpha', 'ndc_train', 'ndc_eval_alpha', 'unbound_train', 'unbound_eval_alpha']
+
+
+@pytest.mark.parametrize('name', RENDER_CASES)
 def test_render_forward_backward(name):
     g = H.golden('render_' + name)
     ro = _render_oracle(g)
     jitter = g['jitter'] if bool(g['is_train']) else None
-    out = ro.forward(g['rays'], int(g['N_samples']), jitter, white_bg=True, want_cache=True)
+    mode = str(g['mode']) if 'mode' in g else 'bounded'
+    out = ro.forward(g['rays'], int(g['N_samples']), jitter, white_bg=True, want_cache=True, mode=mode)
+    if 'pts_sum' in g:
+        assert np.allclose(out['pts'].astype(np.float64).sum((0, 1)), g['pts_sum'], rtol=1e-9, atol=1e-9)
     # bit-exact decisions
     assert np.array_equal(np.packbits(out['ray_valid']), g['ray_valid'])
     assert int(out['ray_valid'].sum()) == int(g['n_valid'])
@@ -129,6 +140,27 @@ def test_torch_port():
     assert abs(float(loss.detach()) - float(g['loss'])) < 1e-7
     gc, = torch.autograd.grad(loss, [tp.p['coeffs.0']])
     assert H.rel_err(gc.numpy(), g['grad.coeffs.0']) < 1e-5
+
+
+@pytest.mark.parametrize('name,coef_mode,basis_mode', [('image', 'nearest', 'nearest'), ('image_bilinear', 'bilinear', 'bilinear'),
+                                                       ('sdf', 'bilinear', 'bilinear'), ('image_set', 'bilinear', 'bilinear')])
+def test_regress_port(name, coef_mode, basis_mode):
+    """oracle/torch_port.RegressPort (reference side of the regression-driver parity tests and the CPU baseline of the
+    image / sdf bench workloads) against the reference's golden field vectors: features, coefficients, MLP output and
+    the field gradients of sum(feats * G)."""
+    import torch
+    from oracle.torch_port import RegressPort
+    g = H.golden('field_' + name)
+    state = {k[len('param.'):]: v for k, v in g.items() if k.startswith('param.')}
+    rp = RegressPort(state, g['fact.aabb'], g['fact.freq_bands'], int(g['fact.in_dim']), coef_mode, basis_mode)
+    x = torch.from_numpy(g['x'])
+    feats, coeff = rp.get_coding(x)
+    assert H.rel_err(feats.detach().numpy(), g['feats']) < 1e-6 and H.rel_err(coeff.detach().numpy(), g['coeff']) < 1e-6
+    assert H.rel_err(rp.linear_mat(feats).detach().numpy(), g['linear_mat_out']) < 1e-6
+    keys = [k for k in rp.p if k.startswith(('coeffs', 'basises'))]
+    grads = torch.autograd.grad((feats * torch.from_numpy(g['G'])).sum(), [rp.p[k] for k in keys])
+    for k, gr in zip(keys, grads):
+        assert H.rel_err(gr.numpy(), g['grad.' + k]) < 1e-5, k
 
 
 def test_bench_workload_matches_reference_shapes():
