@@ -361,8 +361,214 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Regression workloads (BASELINE.md §1 holds the notebooks' recorded rates for image and sdf)
+# ------------------------------------------------------------------------------------------------------------
+REGRESS = {
+    # name: (yaml, aabb, batch, x_dim, out_dim, B_fwd, B_bwd, MLP flop/query, published queries/s, source)
+    'image': ('image.yaml', [[0., 0.], [1024., 1024.]], 102400, 2, 3, 1736, 4032, 18816, 11.1e6, 'scripts/2D_regression.ipynb:140 (108.54 it/s x 102400, unstated GPU, incl. DataLoader)'),
+    'sdf': ('sdf.yaml', [[0., 0., 0.], [640., 640., 640.]], 40960, 3, 1, 1236, 3528, 36, 13.3e6, 'scripts/sdf_regression.ipynb:215-302 (316.7-333.2 it/s x 40960, unstated GPU)'),
+    'image_set': ('image_set.yaml', [[0, 0, 0], [256, 256, 800]], 40960, 3, 3, 5196, 14400, 18816, None, None),
+}
+
+
+def regress_inputs(name, n, seed):
+    """Synthetic seeded sample points of the workload's shape: pixel centres / uniform points / (pixel centre, image+0.5)."""
+    yaml_, aabb, B, xd, od = REGRESS[name][:5]
+    rng = np.random.RandomState(seed)
+    hi = np.array(aabb[1], np.float64)
+    if name == 'sdf':
+        x = rng.uniform(0, hi, (n, 3))
+    else:
+        x = np.floor(rng.uniform(0, hi, (n, xd))) + 0.5
+    t = rng.uniform(0, 1, (n, od)) if name != 'sdf' else rng.uniform(-0.5, 0.5, (n, od))
+    return x.astype(np.float32), t.astype(np.float32)
+
+
+def regress_cpu_leg(name, state, model_facts, n, steps):
+    import torch
+    from oracle.torch_port import RegressPort
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    yaml_ = REGRESS[name][0]
+    mode = 'nearest' if name == 'image' else 'bilinear'
+    rp = RegressPort(state, model_facts['aabb'], model_facts['freq_bands'], model_facts['in_dim'], mode, mode, 0.002, 0.002, 1.0)
+    x, t = regress_inputs(name, n * (steps + 1), 7)
+    x, t = torch.from_numpy(x), torch.from_numpy(t)
+    rp.train_step(x[:n], t[:n])
+    t0 = time.perf_counter()
+    for i in range(1, steps + 1):
+        rp.train_step(x[i * n:(i + 1) * n], t[i * n:(i + 1) * n])
+    dt = time.perf_counter() - t0
+    return n * steps / dt, cores, f'{n} points x {steps} steps of the same workload (oracle/torch_port.RegressPort, torch CPU, {cores} threads)'
+
+
+def run_regress(args):
+    """`--workload image|sdf|image_set`: one regression train step (get_coding -> linear_mat -> MSE -> backward -> Adam) per
+    step; metric = field queries/s.  Not the headline (BASELINE.json's metric is the nerf.yaml step): an extra line for the
+    2-D / SDF / image-set drivers, whose notebooks hold the reference's only recorded rates."""
+    name = args.workload
+    yaml_, aabb, B, xd, od, b_fwd, b_bwd, mlp_flop, published, pub_src = REGRESS[name]
+    rank = int(os.environ.get('RANK', '0'))
+    metric, unit = f'{name}_regression_field_queries_per_s', 'queries/s'
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        import torch
+        import ffb200
+        from ffb200.models.FactorFields import field_shapes
+        cfg = ffb200.load_cfg(yaml_)
+        if name == 'image_set':
+            aabb = [[0, 0, 0], [256, 256, 16]]      # 16 of the 800 coefficient slabs: per-query cost does not depend on the slab count
+        sh = field_shapes(cfg, aabb)
+        state = W.regress_state(cfg, sh, seed=0)
+        facts = dict(aabb=sh['aabb'].numpy(), freq_bands=sh['freq_bands'].numpy(), in_dim=sh['in_dim'])
+        n = 8192
+        val, cores, sample = regress_cpu_leg(name, state, facts, n, max(args.steps, 2))
+        line = {'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': n / val * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': f'{yaml_} regression step', 'points_per_step': n},
+                'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample},
+                'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+        print(json.dumps(line), flush=True)
+        return
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('FFB_BENCH_WATCHDOG_S', '300')), exit=True)
+    import torch
+    import torch.distributed as dist
+    import ffb200
+    from ffb200 import native as nv
+    from ffb200.models.FactorFields import FactorFields
+    from ffb200.train import RegressStep
+    world, local = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(20211202)
+    cfg = ffb200.load_cfg(yaml_, ['model.with_dropout=false'] if args.no_dropout else [])
+    cfg.dataset.aabb = aabb
+    model = FactorFields(cfg, f'cuda:{local}')
+    with torch.no_grad():      # mid-training-like factors (coef_init is a constant; the kernels' cost does not depend on the values)
+        for p in model.coeffs:
+            p.add_(0.05 * torch.randn_like(p))
+    nb = 8
+    x_np, t_np = regress_inputs(name, B * nb, 100 + rank)
+    x_h, t_h = torch.from_numpy(x_np).pin_memory(), torch.from_numpy(t_np).pin_memory()
+    x_d, t_d = x_h.to(dev), t_h.to(dev)
+    rs = RegressStep(model, model.get_optparam_groups(cfg.training.lr_small, cfg.training.lr_large), batch=B, x_dim=xd, out_dim=od,
+                     loss_scale_decay=0.1 ** (1.0 / cfg.training.n_iters) if name != 'image_set' else 1.0, is_train=True)
+    state = {'i': 0}
+
+    def sl():
+        b = state['i'] % nb
+        state['i'] += 1
+        return slice(b * B, (b + 1) * B)
+
+    def step_resident():
+        s = sl()
+        return rs.step(x_d[s], t_d[s])
+
+    def step_e2e():
+        s = sl()
+        return float(rs.step(x_h[s], t_h[s]).item())
+
+    def step_profile():
+        s = sl()
+        rs.rays_s.copy_(x_d[s]); rs.target_s.copy_(t_d[s])
+        rs._body()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    snap = None
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    snap = rs.snapshot()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_resident, args.steps)
+    rs.restore(snap)
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if clocks else None
+    step_profile()
+    torch.cuda.synchronize()
+    l0 = nv.launch_count()
+    nv.profile_begin()
+    P = 5
+    for _ in range(P):
+        step_profile()
+    sec = {k: v[0] / P for k, v in nv.profile_end().items()}
+    launches_per_step = (nv.launch_count() - l0) // P
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    alg = {'field_fwd': B * b_fwd, 'field_bwd': B * b_bwd}
+    kern = {}
+    for k, ms in sec.items():
+        kern[k] = {'ms_per_step': round(ms, 4)}
+        if k in alg:
+            kern[k]['achieved_GBps'] = round(alg[k] / (ms * 1e-3) / 1e9, 1)
+            kern[k]['frac_hbm'] = round(alg[k] / (ms * 1e-3) / 1e9 / pk['hbm'], 4)
+    dom = max(('field_fwd', 'field_bwd'), key=lambda k: sec.get(k, 0.0))
+    ach = alg[dom] / (sec[dom] * 1e-3) / 1e9
+    n_params = sum(p.numel() for p in model.parameters())
+    line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': (value / published) if published else None, 'baseline_source': pub_src, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{yaml_} regression train step (get_coding -> linear_mat -> MSE -> backward -> Adam), batch {B} points, '
+                                   f'aabb {aabb}, {n_params:,} params, synthetic seeded points/targets',
+                       'points_per_gpu_per_step': B, 'cuda_graph': True, 'launches_per_step': launches_per_step,
+                       'l2': 'the factors are L2-resident (as in training); per-step activations stream through HBM; no explicit flush'},
+            'e2e': {'value': e2e, 'unit': unit, 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': B * (xd + od) * 4, 'd2h_bytes_per_step': 4,
+                    'api': 'ffb200.train.RegressStep.step(host x, host target) -> loss.item()  [one CUDA-graph launch per step]'},
+            'gpu_launches': launches_per_step * args.steps,
+            'roofline': {'kernel': dom, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 4),
+                         'traffic': None, 'peak_source': pk['src'], 'algorithmic_bytes_per_launch': alg[dom], 'queries_per_launch': B,
+                         'launch_ms': round(sec[dom], 4), 'share_of_step': round(sec[dom] / (ms_total / args.steps), 4)},
+            'kernels': kern, 'clocks': clk}
+    if world == 1 and not args.no_cpu_baseline:
+        from ffb200.models.FactorFields import field_shapes
+        cpu_aabb = [[0, 0, 0], [256, 256, 16]] if name == 'image_set' else aabb
+        sh = field_shapes(cfg, cpu_aabb)
+        v, cores, sample = regress_cpu_leg(name, W.regress_state(cfg, sh, seed=0),
+                                           dict(aabb=sh['aabb'].numpy(), freq_bands=sh['freq_bands'].numpy(), in_dim=sh['in_dim']), 8192, 2)
+        line['cpu_baseline'] = {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample}
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
+    faulthandler.cancel_dump_traceback_later()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='nerf', choices=['nerf'] + list(REGRESS), help='nerf (the headline, default) or a regression driver')
+    ap.add_argument('--no-dropout', action='store_true', help='image_set: disable F.dropout on the MLP input')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
@@ -377,7 +583,9 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}', '--master-addr', '127.0.0.1',
                '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.impl == 'reference':
+    if args.workload != 'nerf':
+        run_regress(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

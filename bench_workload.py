@@ -73,3 +73,22 @@ def step_size():
     """update_renderParams at gridSize 128^3, aabb +-1, step_ratio 0.5 (FactorFields.py:693-697), fp32."""
     units = np.float32(2.0) / np.float32(127.0)
     return np.float32(np.float32(units) * np.float32(0.5))
+
+
+def regress_state(cfg, shapes, seed=0):
+    """Seeded synthetic state (reference state_dict names / layout) for the regression workloads of bench.py's CPU leg:
+    `shapes` = ffb200.models.FactorFields.field_shapes(cfg, aabb).  Grid coefficient + grid bases + linear_mat."""
+    rng = np.random.RandomState(seed)
+    d = int(shapes['in_dim'])
+    dims = list(cfg.model.basis_dims)
+    width = sum(dims)
+    sd = {'coeffs.0': (cfg.model.coef_init + 0.05 * rng.randn(1, width, *[int(r) for r in shapes['coeff_reso']])).astype(np.float32)}
+    for i, (c, r) in enumerate(zip(dims, shapes['basis_reso'])):
+        sd[f'basises.{i}'] = (0.3 * rng.randn(1, c, *([int(r)] * d))).astype(np.float32)
+    L, H, out = int(cfg.model.num_layers), int(cfg.model.hidden_dim), int(cfg.model.out_dim)
+    for l in range(L):
+        fi, fo = (width if l == 0 else H), (out if l == L - 1 else H)
+        sd[f'linear_mat.backbone.{l}.weight'] = _uniform(rng, (fo, fi), fi)
+        if l != L - 1:
+            sd[f'linear_mat.backbone.{l}.bias'] = _uniform(rng, (fo,), fi)
+    return sd

@@ -194,7 +194,10 @@ __device__ __forceinline__ float fast_msize(const FastParams& P) {
 // parks its 32 coefficient / basis rows in shared memory and streams the contiguous 32*W-float chunk out with
 // coalesced 8-byte stores, forming feats = coeff * basis on the way.  The warp-wide barrier costs more overlap than
 // the partially-written sectors of the direct per-lane row stores.
-template <int DB, int DC, bool NEAR_B, bool NEAR_C, int NT, int MINB, bool STAGE>
+// LPAR (small batches: the regression drivers' 40-100 k points leave most of the 148 SMs without work at one thread per
+// query): one thread per (query, level) — consecutive lanes take the levels of one query, so a query's row segments are
+// still written by neighbouring lanes; the coefficient taps are recomputed per level (ALU only).
+template <int DB, int DC, bool NEAR_B, bool NEAR_C, int NT, int MINB, bool STAGE, bool LPAR = false>
 __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, const float* __restrict__ x, int64_t n,
                                                             const int32_t* __restrict__ n_dev, float* __restrict__ feats,
                                                             float* __restrict__ coeff, float* __restrict__ basis) {
@@ -208,11 +211,14 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
     sC = reinterpret_cast<float*>(fwd_stage) + (size_t)(threadIdx.x >> 5) * 64 * W;
     sB = sC + 32 * W;
   }
-  const int64_t n_chunks = (n + 31) / 32;
+  const int64_t n_items = LPAR ? n * P.n_levels : n;
+  const int64_t n_chunks = (n_items + 31) / 32;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t k = warp0; k < n_chunks; k += nwarps) {
-    const int64_t i = k * 32 + lane;
-    if (i < n) {
+    const int64_t item = k * 32 + lane;
+    const int64_t i = LPAR ? item / P.n_levels : item;
+    const int l_begin = LPAR ? (int)(item % P.n_levels) : 0, l_end = LPAR ? l_begin + 1 : P.n_levels;
+    if (item < n_items) {
       float xr[3];
       for (int d = 0; d < P.xdim; ++d) xr[d] = x[i * P.xdim + d];
       TapSet<DC, NEAR_C> tc;
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
       float* frow = feats ? feats + i * W : nullptr;
       float* crow = STAGE ? sC + lane * W : (coeff ? coeff + i * W : nullptr);
       float* brow = STAGE ? sB + lane * W : (basis ? basis + i * W : nullptr);
-      for (int l = 0; l < P.n_levels; ++l) {
+      for (int l = l_begin; l < l_end; ++l) {
         const FastLevel L = P.lv[l];
         TapSet<DB, NEAR_B> tb;
         basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
@@ -352,14 +358,18 @@ __device__ __forceinline__ void scatter_row(float* __restrict__ grad, int W, con
   }
 }
 
-template <int DB, int DC, bool NEAR_B, bool NEAR_C, int AGGW, int NT, int MINB>
+template <int DB, int DC, bool NEAR_B, bool NEAR_C, int AGGW, int NT, int MINB, bool LPAR = false>
 __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_kernel(const FastParams P, const FastGrads G, const float* __restrict__ x,
                                                                   int64_t n, const int32_t* __restrict__ n_dev,
                                                                   const float* __restrict__ g_feats, const float* __restrict__ g_coeff,
                                                                   const float* __restrict__ coeff, const float* __restrict__ basis) {
+  static_assert(!(LPAR && AGGW > 0), "the level-parallel variant scatters the coefficient gradient level by level");
   n = resolve_n(n, n_dev);
   const float msize = fast_msize(P);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t n_items = LPAR ? n * P.n_levels : n;
+  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = LPAR ? item / P.n_levels : item;
+    const int l_begin = LPAR ? (int)(item % P.n_levels) : 0, l_end = LPAR ? l_begin + 1 : P.n_levels;
     float xr[3];
     for (int k = 0; k < P.xdim; ++k) xr[k] = x[i * P.xdim + k];
     const float* gf = g_feats ? g_feats + i * P.W : nullptr;
@@ -389,7 +399,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_kernel(const FastPara
       scatter_row<DC, NEAR_C, (AGGW > 0 ? AGGW : 2)>(G.c, P.W, tc, gacc);
     }
 #pragma unroll 1
-    for (int l = 0; l < P.n_levels; ++l) {
+    for (int l = l_begin; l < l_end; ++l) {
       const FastLevel L = P.lv[l];
       if (!G.b[l] && (AGGW > 0 || !G.c)) continue;
       TapSet<DB, NEAR_B> tb;
@@ -480,10 +490,17 @@ using namespace ffb;
 static int g_fwd_cfg = 1;   // 0: 128 threads, compiler-chosen registers   1: 128 x >=8 CTAs/SM   2: 128 x >=6   3: 256 x >=4
 static int g_fwd_stage = 0; // 1: narrow rows leave through shared memory as coalesced chunks
 static int g_bwd_cfg = 1;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)
+static int g_lpar = 1;      // 1: batches of at most LPAR_MAX_ITEMS (query, level) pairs use the level-parallel kernels
+constexpr int64_t LPAR_MAX_ITEMS = 148 * 2048 * 3;   // ~3 full waves of resident threads; above that one thread per query wins
 
 template <int DB, int DC, bool NB, bool NC, int NT, int MINB>
 static void launch_fwd_cfg(const FastParams& P, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
                            cudaStream_t s) {
+  if (n * P.n_levels <= LPAR_MAX_ITEMS && g_lpar) {      // small batch: one thread per (query, level)
+    fast_fwd_kernel<DB, DC, NB, NC, NT, MINB, false, true><<<blocks_for(n * P.n_levels, NT, (int64_t)sm_count() * 64), NT, 0, s>>>(
+        P, x, n, n_dev, feats, coeff, basis);
+    return;
+  }
   const unsigned grid = blocks_for(n, NT, (int64_t)sm_count() * 64);
   if (P.W <= 32 && g_fwd_stage) {
     const size_t smem = (size_t)(NT / 32) * 64 * P.W * sizeof(float);
@@ -508,6 +525,11 @@ template <int DB, int DC, bool NB, bool NC>
 static void launch_bwd(const FastParams& P, const FastGrads& G, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
                        const float* g_coeff, const float* coeff, const float* basis, cudaStream_t s) {
   const int64_t cap = (int64_t)sm_count() * 64;
+  if (coeff && basis && g_bwd_cfg != 0 && n * P.n_levels <= LPAR_MAX_ITEMS && g_lpar) {
+    fast_bwd_saved_kernel<DB, DC, NB, NC, 0, 128, 6, true><<<blocks_for(n * P.n_levels, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff,
+                                                                                                            coeff, basis);
+    return;
+  }
   if (coeff && basis && g_bwd_cfg != 0) {
     if (P.W <= 24)
       fast_bwd_saved_kernel<DB, DC, NB, NC, 24, 128, 6><<<blocks_for(n, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis);
@@ -546,6 +568,7 @@ int ffb_set_tuning(const char* key, int value) {
   if (!strcmp(key, "field_fwd_cfg")) g_fwd_cfg = value;
   else if (!strcmp(key, "field_bwd_cfg")) g_bwd_cfg = value;
   else if (!strcmp(key, "field_fwd_stage")) g_fwd_stage = value;
+  else if (!strcmp(key, "field_level_parallel")) g_lpar = value;
   else { set_error("ffb_set_tuning: unknown key %s", key); return FFB_EINVAL; }
   return FFB_OK;
 }
