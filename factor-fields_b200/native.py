@@ -98,6 +98,8 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.ffb_last_error.restype = C.c_char_p
         _lib.ffb_launch_count.restype = C.c_uint64
+        _lib.ffb_rgbmlp_workspace_bytes.restype = C.c_int64
+        _lib.ffb_rgbmlp_stream_bytes.restype = C.c_int64
         if _lib.ffb_abi_version() != 1:
             raise RuntimeError('libffb200.so ABI version mismatch')
     return _lib

@@ -521,17 +521,44 @@ class RenderComposite(torch.autograd.Function):
         if Na > 0:
             nv.check(lib.ffb_composite_app_fill(nv.ptr(weight), C.c_float(cdesc.weight_thres), nv.i32p(offsets), nv.i32p(app_offsets),
                                                 C.c_int64(R), nv.i32p(app_idx), nv.stream()))
-            inp = _empty((Na, Win), feat)
-            nv.check(lib.ffb_render_input_fwd(nv.ptr(feat), ld, nv.ptr(rays), nv.i32p(samp['ray_id']), nv.i32p(app_idx), nv.ptr(inp),
-                                              C.c_int64(Na), nv.i32p(a_dev), Cf, view_pe, fea_pe, nv.stream()))
-            h = inp
-            acts.append(h)
-            with nv.section('rgbmlp_fwd'):
-                for l, (W, b) in enumerate(layers):
-                    act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
-                    kinds.append(act)
-                    h = _linear_fwd(h, W, b, act, a_dev, terms=APPEARANCE_TERMS)
-                    acts.append(h)
+            ws_bytes = 0
+            if len(layers) == 3 and tuple(has_bias) == (True, True, False) and layers[2][0].shape[0] == 3 \
+                    and layers[1][0].shape[0] == layers[1][0].shape[1] == layers[0][0].shape[0] and layers[0][0].shape[1] == Win \
+                    and (lazy or Na >= 1024):
+                ws_bytes = int(lib.ffb_rgbmlp_workspace_bytes(Cf, layers[0][0].shape[0], view_pe, fea_pe))
+            if ws_bytes > 0:
+                # whole appearance MLP in one tcgen05 kernel (mlp_rgb.cu).  For the backward kernel it leaves the ReLU
+                # decision bits and bf16 operand streams of x / h1 / h2 (already in the layout the TMA engine feeds to the MMAs)
+                (W1, b1), (W2, b2), (W3, _) = layers
+                need_bwd = any(ctx.needs_input_grad)
+                ws = torch.empty(ws_bytes, device=feat.device, dtype=torch.uint8)
+                h = _empty((Na, 3), feat)
+                bits = sx = sh1 = sh2 = None
+                if need_bwd:
+                    bits = torch.empty((Na, 16), device=feat.device, dtype=torch.int16)
+                    nbx, nbh = (int(lib.ffb_rgbmlp_stream_bytes(Cf, view_pe, fea_pe, C.c_int64(Na), w)) for w in (0, 1))
+                    sx = torch.empty(nbx, device=feat.device, dtype=torch.uint8)
+                    sh1 = torch.empty(nbh, device=feat.device, dtype=torch.uint8)
+                    sh2 = torch.empty(nbh, device=feat.device, dtype=torch.uint8)
+                vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+                with nv.section('rgbmlp_fwd'):
+                    nv.check(lib.ffb_rgbmlp_pack(nv.ptr(W1), nv.ptr(b1), nv.ptr(W2), nv.ptr(W3), vp(ws), Cf, view_pe, fea_pe, nv.stream()))
+                    nv.check(lib.ffb_rgbmlp_fwd(nv.ptr(feat), ld, nv.ptr(rays), nv.i32p(samp['ray_id']), nv.i32p(app_idx), vp(ws), nv.ptr(b2),
+                                                nv.ptr(h), vp(bits), None, None, None, vp(sx), vp(sh1), vp(sh2), C.c_int64(Na),
+                                                nv.i32p(a_dev), Cf, view_pe, fea_pe, nv.stream()))
+                acts, kinds = [ws, bits, sx, sh1, sh2], 'fused'
+            else:
+                inp = _empty((Na, Win), feat)
+                nv.check(lib.ffb_render_input_fwd(nv.ptr(feat), ld, nv.ptr(rays), nv.i32p(samp['ray_id']), nv.i32p(app_idx), nv.ptr(inp),
+                                                  C.c_int64(Na), nv.i32p(a_dev), Cf, view_pe, fea_pe, nv.stream()))
+                h = inp
+                acts.append(h)
+                with nv.section('rgbmlp_fwd'):
+                    for l, (W, b) in enumerate(layers):
+                        act = 1 if l != len(layers) - 1 else 2   # ReLU ... sigmoid (FactorFields.py:197-202)
+                        kinds.append(act)
+                        h = _linear_fwd(h, W, b, act, a_dev, terms=APPEARANCE_TERMS)
+                        acts.append(h)
             rgb = h
         else:
             rgb = _empty((0, 3), feat)
@@ -578,9 +605,21 @@ class RenderComposite(torch.autograd.Function):
             i += 2 if hb else 1
         flat = []
         if Na > 0:
-            with nv.section('rgbmlp_bwd'):
-                g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn, ctx.a_dev)
             Cf = ld - 1
+            if ctx.kinds == 'fused':
+                ws, bits, sx, sh1, sh2 = acts
+                (W1, b1), (W2, b2), (W3, _) = layers
+                grads = [(_grad_like(W) if nw else None, _grad_like(b) if (b is not None and nb) else None)
+                         for (W, b), (nw, nb) in zip(layers, pn)]
+                g_in = _empty((Na, W1.shape[1]), feat)
+                vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+                with nv.section('rgbmlp_bwd'):
+                    nv.check(lib.ffb_rgbmlp_bwd(nv.ptr(g_rgb), nv.ptr(rgb), vp(bits), vp(sx), vp(sh1), vp(sh2), vp(ws), nv.ptr(W3), nv.ptr(g_in),
+                                                vp(grads[0][0]), vp(grads[0][1]), vp(grads[1][0]), vp(grads[1][1]), vp(grads[2][0]),
+                                                C.c_int64(Na), nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
+            else:
+                with nv.section('rgbmlp_bwd'):
+                    g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn, ctx.a_dev)
             nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(Na),
                                               nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
             for (gW, gb), hb in zip(grads, ctx.has_bias):

@@ -221,6 +221,37 @@ int ffb_render_input_bwd(const float* feat, int32_t ld_feat, const int32_t* app_
                          int32_t feape, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused appearance MLP (MLPRender_Fea.forward, FactorFields.py:188-203, on the shaded samples of
+ * forward :879-885): input assembly + 3 layers + sigmoid in one tcgen05 kernel (mlp_rgb.cu).
+ * Shape: hidden width 128, 3 layers (bias, bias, none), 3 outputs.
+ * ------------------------------------------------------------------------------------------- */
+/* Bytes of the packed-weight workspace, or 0 when the shape is not eligible (callers then use the per-layer ops). */
+int64_t ffb_rgbmlp_workspace_bytes(int32_t Cf, int32_t hidden, int32_t view_pe, int32_t fea_pe);
+/* Split W1 [128, K0] (+ b1 as an extra column), W2 [128,128], W3 [3,128] into bf16 operand slices (once per step). */
+int ffb_rgbmlp_pack(const float* W1, const float* b1, const float* W2, const float* W3, void* workspace,
+                    int32_t Cf, int32_t view_pe, int32_t fea_pe, void* stream);
+/* rgb [n,3] = MLPRender_Fea(viewdirs = rays[ray_id[i], 3:6], features = feat[i, 1:1+Cf]) for i = app_idx[j] (NULL:
+ * identity).  relu_bits [n,16] uint16 (optional): ReLU decisions of both hidden layers for the backward pass.
+ * x_out [n,K0] / h1_out / h2_out [n,128] (optional): fp32 copies of the MLP input and hidden activations.
+ * stream_x / stream_h1 / stream_h2 (all or none): bf16 operand streams of the same activations for ffb_rgbmlp_bwd,
+ * ffb_rgbmlp_stream_bytes(.., n, which) bytes each (which: 0 = x, 1 = h1 / h2). */
+int ffb_rgbmlp_fwd(const float* feat, int32_t ld_feat, const float* rays, const int32_t* ray_id,
+                   const int32_t* app_idx, const void* workspace, const float* b2, float* rgb,
+                   uint16_t* relu_bits, float* x_out, float* h1_out, float* h2_out, void* stream_x,
+                   void* stream_h1, void* stream_h2, int64_t n, const int32_t* n_dev, int32_t Cf,
+                   int32_t view_pe, int32_t fea_pe, void* stream);
+int64_t ffb_rgbmlp_stream_bytes(int32_t Cf, int32_t view_pe, int32_t fea_pe, int64_t n, int32_t which);
+/* Backward of the same MLP (the autograd of FactorFields.py:188-203): g_rgb [n,3] = dL/d rgb, rgb = the forward
+ * output.  Writes g_x [n,K0] (gradient w.r.t. the assembled input; ffb_render_input_bwd folds it onto the features)
+ * and ACCUMULATES gW1 [128,K0], gb1, gW2 [128,128], gb2, gW3 [3,128] (any may be NULL).  workspace: the one
+ * ffb_rgbmlp_pack filled for this step's weights; W3: the fp32 colour-head weight. */
+int ffb_rgbmlp_bwd(const float* g_rgb, const float* rgb, const uint16_t* relu_bits, const void* stream_x,
+                   const void* stream_h1, const void* stream_h2, const void* workspace, const float* W3,
+                   float* g_x, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, int64_t n,
+                   const int32_t* n_dev, int32_t Cf, int32_t view_pe, int32_t fea_pe, void* stream);
+int ffb_set_fused_rgbmlp(int enabled);
+
+/* ---------------------------------------------------------------------------------------------
  * Ray sampling + alpha-mask stream compaction: sample_point (:586-602), AlphaGridMask.sample_alpha
  * (:103-110) and the boolean-mask indexing of forward (:864-867,874).
  * ------------------------------------------------------------------------------------------- */

@@ -143,3 +143,110 @@ def test_fused_mlp2_matches_per_layer_path():
     nv.lib().ffb_set_fused_mlp(1)
     for a, b in zip(*outs):
         assert float((a - b).abs().max() / b.abs().max()) < 3e-5
+
+
+def _rgb_reference(feat, viewdirs, W1, b1, W2, b2, W3, view_pe, fea_pe):
+    """MLPRender_Fea.forward (FactorFields.py:188-203) in float64."""
+    def pe(p, freqs):
+        fb = 2.0 ** torch.arange(freqs, dtype=torch.float64, device=p.device)
+        pts = (p[..., None] * fb).reshape(p.shape[0], -1)
+        return torch.cat([torch.sin(pts), torch.cos(pts)], -1)
+    f, v = feat.double(), viewdirs.double()
+    x = torch.cat([f, v, pe(f, fea_pe), pe(v, view_pe)], -1)
+    h1 = torch.relu(x @ W1.double().T + b1.double())
+    h2 = torch.relu(h1 @ W2.double().T + b2.double())
+    return x, h1, h2, torch.sigmoid(h2 @ W3.double().T)
+
+
+@pytest.mark.parametrize('n,use_idx', [(128 * 7 + 5, True), (40000, True), (3000, False)])
+def test_fused_appearance_mlp_forward(n, use_idx):
+    """mlp_rgb.cu: gather + input assembly + 3 layers + sigmoid in one tcgen05 kernel vs a float64 restatement of
+    MLPRender_Fea; the fp32 activation copies and the ReLU decision bits it hands to the backward pass as well."""
+    from ffb200 import native as nv
+    lib = nv.lib()
+    Cf, Hd, vpe, fpe = 31, 128, 6, 2
+    K0 = 3 + Cf + 6 * vpe + 2 * fpe * Cf
+    wsb = int(lib.ffb_rgbmlp_workspace_bytes(Cf, Hd, vpe, fpe))
+    assert wsb > 0
+    torch.manual_seed(n)
+    Nv, R = (3 * n, 500) if use_idx else (n, n)
+    feat = torch.randn(Nv, Cf + 1, device='cuda')
+    rays = torch.randn(R, 6, device='cuda')
+    rays[:, 3:] = torch.nn.functional.normalize(rays[:, 3:], dim=-1)
+    ray_id = torch.randint(0, R, (Nv,), device='cuda', dtype=torch.int32) if use_idx else None
+    app_idx = torch.sort(torch.randperm(Nv, device='cuda')[:n])[0].to(torch.int32) if use_idx else None
+    W1 = torch.randn(Hd, K0, device='cuda') / K0 ** 0.5
+    b1 = torch.randn(Hd, device='cuda') * 0.1
+    W2 = torch.randn(Hd, Hd, device='cuda') / Hd ** 0.5
+    b2 = torch.randn(Hd, device='cuda') * 0.1
+    W3 = torch.randn(3, Hd, device='cuda') / Hd ** 0.5
+    ws = torch.empty(wsb, device='cuda', dtype=torch.uint8)
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    rgb = torch.full((n, 3), -1.0, device='cuda')
+    bits = torch.zeros(n, 16, device='cuda', dtype=torch.int16)
+    x_o, h1_o, h2_o = torch.zeros(n, K0, device='cuda'), torch.zeros(n, Hd, device='cuda'), torch.zeros(n, Hd, device='cuda')
+    s = nv.stream()
+    _call(lib, 'ffb_rgbmlp_pack', P(W1), P(b1), P(W2), P(W3), P(ws), Cf, vpe, fpe, s)
+    _call(lib, 'ffb_rgbmlp_fwd', P(feat), Cf + 1, P(rays), P(ray_id), P(app_idx), P(ws), P(b2), P(rgb), P(bits), P(x_o), P(h1_o), P(h2_o),
+          None, None, None, C.c_int64(n), None, Cf, vpe, fpe, s)
+    torch.cuda.synchronize()
+    sel = app_idx.long() if use_idx else torch.arange(n, device='cuda')
+    vd = rays[ray_id.long()[sel], 3:] if use_idx else rays[:, 3:]
+    x, h1, h2, ref = _rgb_reference(feat[sel, 1:], vd, W1, b1, W2, b2, W3, vpe, fpe)
+    rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max())
+    assert rel(x_o, x) < 2e-6, rel(x_o, x)
+    assert rel(h1_o, h1) < 3e-6, rel(h1_o, h1)
+    assert rel(h2_o, h2) < 3e-6, rel(h2_o, h2)
+    assert rel(rgb, ref) < 3e-6, rel(rgb, ref)
+    # decision bits == sign of the activations the kernel itself produced
+    shifts = torch.arange(16, device='cuda', dtype=torch.int32)
+    unpack = lambda w: ((w.to(torch.int32)[..., None] >> shifts) & 1).reshape(n, -1).bool()
+    assert torch.equal(unpack(bits[:, :8]), h1_o > 0) and torch.equal(unpack(bits[:, 8:]), h2_o > 0)
+
+
+@pytest.mark.parametrize('n', [128 * 3 + 17, 30000])
+def test_fused_appearance_mlp_backward(n):
+    """mlp_rgb.cu backward (operand streams from the forward kernel, weight gradients accumulated in TMEM) vs float64
+    autograd of MLPRender_Fea: input gradient and all five parameter gradients."""
+    from ffb200 import native as nv
+    lib = nv.lib()
+    Cf, Hd, vpe, fpe = 31, 128, 6, 2
+    K0 = 3 + Cf + 6 * vpe + 2 * fpe * Cf
+    torch.manual_seed(n + 1)
+    feat = torch.randn(n, Cf + 1, device='cuda')
+    rays = torch.randn(n, 6, device='cuda')
+    W1 = torch.randn(Hd, K0, device='cuda') / K0 ** 0.5
+    b1 = torch.randn(Hd, device='cuda') * 0.1
+    W2 = torch.randn(Hd, Hd, device='cuda') / Hd ** 0.5
+    b2 = torch.randn(Hd, device='cuda') * 0.1
+    W3 = torch.randn(3, Hd, device='cuda') / Hd ** 0.5
+    g_rgb = torch.randn(n, 3, device='cuda')
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    ws = torch.empty(int(lib.ffb_rgbmlp_workspace_bytes(Cf, Hd, vpe, fpe)), device='cuda', dtype=torch.uint8)
+    nbx, nbh = (int(lib.ffb_rgbmlp_stream_bytes(Cf, vpe, fpe, C.c_int64(n), w)) for w in (0, 1))
+    sx, sh1, sh2 = (torch.empty(b, device='cuda', dtype=torch.uint8) for b in (nbx, nbh, nbh))
+    rgb = torch.empty(n, 3, device='cuda')
+    bits = torch.zeros(n, 16, device='cuda', dtype=torch.int16)
+    s = nv.stream()
+    _call(lib, 'ffb_rgbmlp_pack', P(W1), P(b1), P(W2), P(W3), P(ws), Cf, vpe, fpe, s)
+    _call(lib, 'ffb_rgbmlp_fwd', P(feat), Cf + 1, P(rays), None, None, P(ws), P(b2), P(rgb), P(bits), None, None, None, P(sx), P(sh1), P(sh2),
+          C.c_int64(n), None, Cf, vpe, fpe, s)
+    g_x = torch.zeros(n, K0, device='cuda')
+    gW1, gb1, gW2, gb2, gW3 = (torch.zeros_like(t) for t in (W1, b1, W2, b2, W3))
+    _call(lib, 'ffb_rgbmlp_bwd', P(g_rgb), P(rgb), P(bits), P(sx), P(sh1), P(sh2), P(ws), P(W3), P(g_x), P(gW1), P(gb1), P(gW2), P(gb2), P(gW3),
+          C.c_int64(n), None, Cf, vpe, fpe, s)
+    torch.cuda.synchronize()
+    # float64 reference of the backward pass, with the ReLU decisions the forward kernel recorded (a hidden unit within
+    # rounding distance of zero may be decided differently in float64; its sample's g_x row then differs by a whole term)
+    x, h1, h2, y = _rgb_reference(feat[:, 1:], rays[:, 3:], W1, b1, W2, b2, W3, vpe, fpe)
+    shifts = torch.arange(16, device='cuda', dtype=torch.int32)
+    unpack = lambda w: ((w.to(torch.int32)[..., None] >> shifts) & 1).reshape(n, -1).double()
+    m1, m2 = unpack(bits[:, :8]), unpack(bits[:, 8:])
+    assert float((m1 != (h1 > 0)).double().mean()) < 1e-4 and float((m2 != (h2 > 0)).double().mean()) < 1e-4
+    g3 = g_rgb.double() * y * (1 - y)
+    G2 = (g3 @ W3.double()) * m2
+    G1 = (G2 @ W2.double()) * m1
+    ref = [G1 @ W1.double(), G1.T @ x, G1.sum(0), G2.T @ h1, G2.sum(0), g3.T @ h2]
+    rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max())
+    for name, got, want in zip(['g_x', 'gW1', 'gb1', 'gW2', 'gb2', 'gW3'], [g_x, gW1, gb1, gW2, gb2, gW3], ref):
+        assert rel(got, want) < 5e-5, (name, rel(got, want))
