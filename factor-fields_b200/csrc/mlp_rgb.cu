@@ -19,14 +19,16 @@
 namespace ffb {
 
 constexpr int RGB_H = 128;               // hidden width of both layers
-constexpr int RGB_WORKERS = 256;         // threads of the 8 worker warps
-constexpr int RGB_THREADS = 320;         // + MMA warp + producer warp
+constexpr int RGB_WORKERS = 512;         // forward: threads of the 16 worker warps (the kernel is bound by per-warp instruction latency)
+constexpr int RGB_THREADS = RGB_WORKERS + 64;   // + MMA warp + producer warp
+constexpr int RGB_B_WORKERS = 512;       // backward: 16 worker warps as well
+constexpr int RGB_B_THREADS = RGB_B_WORKERS + 64;
 constexpr int RGB_NSLOT = 4;
 constexpr uint32_t RGB_SLICE = 4096;     // one K=16 slice of a 128-row operand tile, one bf16 part
 constexpr uint32_t RGB_SLOT = 3 * RGB_SLICE;
 constexpr uint32_t RGB_W3_PART = 16 * RGB_H * 2;   // W3 tile: 16 rows (3 used) x 128 cols
 constexpr int RGB_MAXQ = 10;             // channel quads per row: Cf + 3 <= 40
-constexpr int RGB_NPRE = 2 * RGB_MAXQ;   // prefetched raw values per lane (2 row groups per warp)
+constexpr int RGB_NPRE = RGB_MAXQ;       // prefetched raw values per lane (one 8-row group per worker warp)
 
 struct RgbShape {
   int Cf, view_pe, fea_pe;
@@ -158,6 +160,15 @@ __device__ __forceinline__ void a_store3(uint8_t* sA, uint32_t szA, int r, int c
   for (int t = 0; t < 3; ++t) *reinterpret_cast<__nv_bfloat16*>(p + (size_t)t * szA) = parts[t];
 }
 
+// two adjacent columns (c even) of one row: one 4-byte store per part
+__device__ __forceinline__ void a_store3_pair(uint8_t* sA, uint32_t szA, int r, int c, float v0, float v1) {
+  uint32_t w[3];
+  split2_packed<3>(v0, v1, w);
+  uint8_t* p = sA + a_off(r, c);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) *reinterpret_cast<uint32_t*>(p + (size_t)t * szA) = w[t];
+}
+
 __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const RgbShape S = a.S;
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
   uint64_t* w3_full = mma_done + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w3_full + 1);
 
-  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  if (warp == RGB_WORKERS / 32) tmem_alloc(tmem_slot, 256);
   if (tid == 0) {
     for (int i = 0; i < RGB_NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(a_ready, 1);
@@ -189,22 +200,26 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
   const uint32_t d1 = tmem, d2 = tmem + RGB_H, d3 = tmem;           // D3 re-uses D1's first columns (D1 is consumed by then)
   const int64_t n_tiles = (n + 127) / 128;
   const int n_slices = S.n1 + RGB_H / 16;                            // ring traffic per tile: W1 slices then W2 slices
+  const int rot1 = (int)(blockIdx.x % (unsigned)S.n1), rot2 = (int)(blockIdx.x % (unsigned)(RGB_H / 16));
 
-  if (warp == 9) {
+  if (warp == RGB_WORKERS / 32 + 1) {
     // ---------------- producer: W3 once, then the same (W1, W2) slice sequence for every tile of this CTA
     if (lane == 0 && (int64_t)blockIdx.x < n_tiles) {
       mbar_expect_tx(w3_full, 3 * RGB_W3_PART);
       bulk_g2s(sW3, a.wpack + (size_t)n_slices * RGB_SLOT, 3 * RGB_W3_PART, w3_full);   // == wpack + fwd bytes - W3 tile
+      // Every CTA walks the K slices of a layer in its own rotation (the sum over slices is order-free): the 148 CTAs run
+      // in near lockstep, and without the rotation they all pull the same L2 lines at the same moment.
       uint32_t seq = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int s = 0; s < n_slices; ++s, ++seq) {
+        for (int q = 0; q < n_slices; ++q, ++seq) {
+          const int s = q < S.n1 ? (q + rot1) % S.n1 : S.n1 + (q - S.n1 + rot2) % (RGB_H / 16);
           const uint32_t slot = seq % RGB_NSLOT, use = seq / RGB_NSLOT;
           if (use > 0) mbar_wait(empty + slot, (use - 1) & 1);
           mbar_expect_tx(full + slot, RGB_SLOT);
           bulk_g2s(sRing + slot * RGB_SLOT, a.wpack + (size_t)s * RGB_SLOT, RGB_SLOT, full + slot);
         }
     }
-  } else if (warp == 8) {
+  } else if (warp == RGB_WORKERS / 32) {
     // ---------------- MMA issuer
     if (lane == 0 && (int64_t)blockIdx.x < n_tiles) {
       const uint32_t aA = smem_u32(sA), aRing = smem_u32(sRing), aW3 = smem_u32(sW3);
@@ -218,12 +233,13 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
           tc_fence_after();
           const int ns = layer == 0 ? S.n1 : RGB_H / 16;
           const uint32_t dst = layer == 0 ? d1 : d2;
-          for (int s = 0; s < ns; ++s, ++seq) {
+          for (int q = 0; q < ns; ++q, ++seq) {
+            const int s = (q + (layer == 0 ? rot1 : rot2)) % ns;       // the slice the producer put in this slot
             const uint32_t slot = seq % RGB_NSLOT, use = seq / RGB_NSLOT;
             mbar_wait(full + slot, use & 1);
             tc_fence_after();
             const uint32_t wb = aRing + slot * RGB_SLOT;
-            uint32_t acc = s > 0 ? 1u : 0u;
+            uint32_t acc = q > 0 ? 1u : 0u;
 #pragma unroll
             for (int ta = 0; ta < 3; ++ta)
 #pragma unroll
@@ -257,7 +273,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
     }
   } else {
     // ---------------- workers: input assembly and the three epilogues
-    const int rloc = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int rloc = (warp & 3) * 32 + lane, quarter = warp >> 2;      // TMEM lane quarter = warp % 4; column blocks by warp / 4
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int C = S.Cf, nch = C + 3;
     const int oV = C, oPF = C + 3, oPV = C + 3 + 2 * S.fea_pe * C;
@@ -265,20 +281,14 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
     float pre[RGB_NPRE];
     // raw MLP inputs of this lane's (row, channel) items: feat[app_idx[j], 1 + ch] or the ray's view direction
     auto load_raw = [&](int64_t row0) {
-      int64_t src[2], ray[2];
-#pragma unroll
-      for (int gsel = 0; gsel < 2; ++gsel) {
-        const int64_t j = row0 + (2 * warp + gsel) * 8 + (lane >> 2);
-        src[gsel] = j < n ? (a.app_idx ? (int64_t)__ldg(a.app_idx + j) : j) : -1;
-      }
-#pragma unroll
-      for (int gsel = 0; gsel < 2; ++gsel) ray[gsel] = src[gsel] < 0 ? -1 : (a.ray_id ? (int64_t)__ldg(a.ray_id + src[gsel]) : src[gsel]);
+      const int64_t j = row0 + warp * 8 + (lane >> 2);
+      const int64_t src = j < n ? (a.app_idx ? (int64_t)__ldg(a.app_idx + j) : j) : -1;
+      const int64_t ray = src < 0 ? -1 : (a.ray_id ? (int64_t)__ldg(a.ray_id + src) : src);
 #pragma unroll
       for (int k = 0; k < RGB_NPRE; ++k) {
-        const int gsel = k / RGB_MAXQ, cq = k % RGB_MAXQ, ch = cq * 4 + (lane & 3);
+        const int ch = k * 4 + (lane & 3);
         pre[k] = 0.0f;
-        if (cq < ncq && ch < nch && src[gsel] >= 0)
-          pre[k] = ch < C ? __ldg(a.feat + src[gsel] * a.ld_feat + 1 + ch) : __ldg(a.rays + ray[gsel] * 6 + 3 + (ch - C));
+        if (k < ncq && ch < nch && src >= 0) pre[k] = ch < C ? __ldg(a.feat + src * a.ld_feat + 1 + ch) : __ldg(a.rays + ray * 6 + 3 + (ch - C));
       }
     };
     uint32_t ph_m = 0;
@@ -288,13 +298,12 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
       // --- X tile: [features | viewdirs | sin/cos PE of both | 1 (bias column) | 0 padding]; rows beyond n are zero
       // Work item = (8-row group, 4 consecutive channels); lane = (row in group, channel in quad).  The shared-memory bank of
       // tile element (r, c) is 4 (r % 8) + (c % 8) / 2, so the 32 lanes of a warp hit 32 different banks (or the two halves
-      // of one word) for the identity columns and for every octave of the sin / cos blocks.  A warp owns row groups
-      // 2 warp and 2 warp + 1; the raw values were fetched into registers while the previous tile was in the tensor pipe.
+      // of one word) for the identity columns and for every octave of the sin / cos blocks.  Worker warp w owns row group
+      // w; the raw values were fetched into registers while the previous tile was in the tensor pipe.
 #pragma unroll
       for (int k = 0; k < RGB_NPRE; ++k) {
-        const int gsel = k / RGB_MAXQ, cq = k % RGB_MAXQ;
-        const int r = (2 * warp + gsel) * 8 + (lane >> 2), ch = cq * 4 + (lane & 3);
-        if (cq >= ncq || ch >= nch) continue;
+        const int r = warp * 8 + (lane >> 2), ch = k * 4 + (lane & 3);
+        if (k >= ncq || ch >= nch) continue;
         const int64_t j = row0 + r;
         const bool live = j < n;
         const float v = pre[k];
@@ -309,13 +318,24 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
         if (a.x_out && live) a.x_out[j * S.K0 + o_id] = v;
         float sa, ca;
         sincosf(v, &sa, &ca);
-        for (int kk = 0; kk < pe; ++kk) {
-          a_store3(sA, szA, r, o_sin + kk, live ? sa : 0.0f);
-          a_store3(sA, szA, r, o_cos + kk, live ? ca : 0.0f);
-          if (a.x_out && live) { a.x_out[j * S.K0 + o_sin + kk] = sa; a.x_out[j * S.K0 + o_cos + kk] = ca; }
+        if (!live) sa = ca = 0.0f;       // rows beyond n are all-zero (doubling keeps them zero)
+        const bool pairs = ((pe | o_sin | o_cos) & 1) == 0;     // octaves (2k, 2k+1) share a 4-byte word
+        for (int kk = 0; kk < pe; kk += 2) {
           const float s2 = 2.0f * sa * ca, c2 = (ca - sa) * (ca + sa);     // exact angle doubling for the next octave
-          sa = s2;
-          ca = c2;
+          if (pairs) {
+            a_store3_pair(sA, szA, r, o_sin + kk, sa, s2);
+            a_store3_pair(sA, szA, r, o_cos + kk, ca, c2);
+          } else {
+            a_store3(sA, szA, r, o_sin + kk, sa);
+            a_store3(sA, szA, r, o_cos + kk, ca);
+            if (kk + 1 < pe) { a_store3(sA, szA, r, o_sin + kk + 1, s2); a_store3(sA, szA, r, o_cos + kk + 1, c2); }
+          }
+          if (a.x_out && live) {
+            a.x_out[j * S.K0 + o_sin + kk] = sa; a.x_out[j * S.K0 + o_cos + kk] = ca;
+            if (kk + 1 < pe) { a.x_out[j * S.K0 + o_sin + kk + 1] = s2; a.x_out[j * S.K0 + o_cos + kk + 1] = c2; }
+          }
+          sa = 2.0f * s2 * c2;
+          ca = (c2 - s2) * (c2 + s2);
         }
       }
       for (int it = tid; it < 128 * (S.K0p - S.K0); it += RGB_WORKERS) {
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
         // the staged X tile, parts 0 and 1, re-laid as row slices for the backward kernel; a thread copies exactly the
         // chunks of its row that its own epilogue will overwrite later (plus its share of the columns beyond 128)
         for (int c8 = 0; c8 < S.K0p / 8; ++c8) {
-          if (((c8 >> 1) & 1) != half) continue;
+          if (((c8 >> 1) & 3) != quarter) continue;
 #pragma unroll
           for (int t = 0; t < 2; ++t)
             *reinterpret_cast<uint4*>(stream_ptr(a.sx, S.K0p, tile, rloc, c8, t)) = *reinterpret_cast<const uint4*>(sA + (size_t)t * szA + a_off(rloc, c8 * 8));
@@ -345,13 +365,19 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
         const uint32_t src = layer == 0 ? d1 : d2;
         float* hout = layer == 0 ? a.h1_out : a.h2_out;
         uint8_t* sh = layer == 0 ? a.sh1 : a.sh2;
-        for (int c0 = half * 16; c0 < RGB_H; c0 += 32) {
+        for (int c0 = quarter * 16; c0 < RGB_H; c0 += 64) {
           float v[16];
           tmem_ld16(src + lane_base + (uint32_t)c0, v);
           uint32_t bits = 0;
+          if (layer == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.b2 + c0 + i));
+              v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            if (layer == 1) v[i] += __ldg(a.b2 + c0 + i);
             bits |= (v[i] > 0.0f ? 1u : 0u) << i;
             v[i] = fmaxf(v[i], 0.0f);
           }
@@ -363,7 +389,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
             }
           }
           uint4 parts[3];
-          split8_parts<3>(v, parts);
+          split8_packed<3>(v, parts);
           uint8_t* p = sA + a_off(rloc, c0);
 #pragma unroll
           for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4*>(p + (size_t)t * szA) = parts[t];
@@ -371,7 +397,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
             *reinterpret_cast<uint4*>(stream_ptr(sh, RGB_H, tile, rloc, c0 >> 3, 0)) = parts[0];
             *reinterpret_cast<uint4*>(stream_ptr(sh, RGB_H, tile, rloc, c0 >> 3, 1)) = parts[1];
           }
-          split8_parts<3>(v + 8, parts);
+          split8_packed<3>(v + 8, parts);
           p = sA + a_off(rloc, c0 + 8);
 #pragma unroll
           for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4*>(p + (size_t)t * szA) = parts[t];
@@ -389,7 +415,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
       mbar_wait(mma_done, ph_m);
       ph_m ^= 1;
       tc_fence_after();
-      if (half == 0) {
+      if (quarter == 0) {
         float v[16];
         tmem_ld16(d3 + lane_base, v);
         if (row < n) {
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == RGB_WORKERS / 32) {
     __syncwarp();
     tmem_dealloc(tmem, 256);
   }
@@ -423,7 +449,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
 // accumulators stay in TMEM across every tile of the persistent CTA and are flushed once with atomics.
 // TMEM columns: gW1|gb1 [0, K0p)   gW2 [208, 336)   gW3 [336, 352)   gb2 [352, 368)   scratch (G2 W2, then g_x halves) [368, 496)
 // =============================================================================================================
-constexpr int RGB_B_NSLOT = 6;
+constexpr int RGB_B_NSLOT = 10;
 constexpr uint32_t RGB_B_SLOT = 13312;          // largest ring item: an X slice, 2 parts x 26 chunks x 256 B
 constexpr uint32_t RGB_G_PART = 128 * RGB_H * 2;  // one part of the G tile
 
@@ -441,7 +467,7 @@ struct RgbBwdArgs {
 
 __device__ __forceinline__ void g_store2(uint8_t* sG, int r, int c0, const float v[8]) {
   uint4 parts[2];
-  split8_parts<2>(v, parts);
+  split8_packed<2>(v, parts);
   uint8_t* p = sG + a_off(r, c0);
   *reinterpret_cast<uint4*>(p) = parts[0];
   *reinterpret_cast<uint4*>(p + RGB_G_PART) = parts[1];
@@ -454,7 +480,7 @@ __device__ __forceinline__ void mma2(uint32_t d, uint32_t idesc, bool accumulate
   umma_f16(d, da(1), db(0), idesc, 1u);
 }
 
-__global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArgs a) {
+__global__ void __launch_bounds__(RGB_B_THREADS, 1) rgb_bwd_kernel(const RgbBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const RgbShape S = a.S;
   const int64_t n = resolve_n(a.n, a.n_dev);
@@ -471,7 +497,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
   uint64_t* mma_done = a_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
 
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == RGB_B_WORKERS / 32) tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
     for (int i = 0; i < RGB_B_NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(a_ready, 1);
@@ -492,8 +518,9 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
   const uint8_t* wW2 = a.wpack;
   const uint8_t* wW1a = a.wpack + (size_t)8 * 2 * 4096;
   const uint8_t* wW1b = a.wpack + (size_t)8 * 2 * 4096 * 2;
+  const int rot = (int)(blockIdx.x & 7u);
 
-  if (warp == 9) {
+  if (warp == RGB_B_WORKERS / 32 + 1) {
     // ---------------- producer: 48 ring items per tile, in the order the MMA warp consumes them
     if (lane == 0) {
       uint32_t seq = 0;
@@ -510,17 +537,17 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         const uint8_t* tx = a.sx + (size_t)tile * rgb_stream_tile(xcols);
         for (int s = 0; s < 8; ++s) put(th2 + (size_t)s * 2 * pH, 2 * pH);
         for (int s = 0; s < 8; ++s) {
-          put(wW2 + (size_t)s * 8192, 8192);
+          put(wW2 + (size_t)((s + rot) & 7) * 8192, 8192);        // weight slices in this CTA's own rotation (see rgb_fwd_kernel)
           put(th1 + (size_t)s * 2 * pH, 2 * pH);
         }
         for (int s = 0; s < 8; ++s) {
-          put(wW1a + (size_t)s * 8192, 8192);
+          put(wW1a + (size_t)((s + rot) & 7) * 8192, 8192);
           put(tx + (size_t)s * 2 * pX, 2 * pX);
         }
-        for (int s = 0; s < 8; ++s) put(wW1b + (size_t)s * 2 * pW1b, 2 * pW1b);
+        for (int s = 0; s < 8; ++s) put(wW1b + (size_t)((s + rot) & 7) * 2 * pW1b, 2 * pW1b);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == RGB_B_WORKERS / 32) {
     // ---------------- MMA issuer
     if (lane == 0) {
       const uint32_t aG = smem_u32(sG), aG3 = smem_u32(sG3), aOnes = smem_u32(sOnes), aRing = smem_u32(sRing);
@@ -557,7 +584,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         }
         for (int s = 0; s < 8; ++s) {
           uint32_t b = take();                                    // scratch[r, j1] = sum_j2 G2[r, j2] W2[j2, j1]
-          mma2(dS, id_gh, s > 0, [&](int t) { return gk(t, s); }, [&](int t) { return make_desc(b + t * 4096u, 2048u, 128u); });
+          mma2(dS, id_gh, s > 0, [&](int t) { return gk(t, (s + rot) & 7); }, [&](int t) { return make_desc(b + t * 4096u, 2048u, 128u); });
           release();
           b = take();                                             // gW2[j2, j1] += sum_r G2[r, j2] h1[r, j1]
           mma2(dW2, id_w2, any || s > 0, [&](int t) { return gmn(t, s); }, [&](int t) { return make_desc(b + t * pH, 128u, 256u); });
@@ -572,7 +599,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         tc_fence_after();
         for (int s = 0; s < 8; ++s) {
           uint32_t b = take();                                    // scratch[r, k] = sum_j1 G1[r, j1] W1[j1, k], k < 128
-          mma2(dS, id_gh, s > 0, [&](int t) { return gk(t, s); }, [&](int t) { return make_desc(b + t * 4096u, 2048u, 128u); });
+          mma2(dS, id_gh, s > 0, [&](int t) { return gk(t, (s + rot) & 7); }, [&](int t) { return make_desc(b + t * 4096u, 2048u, 128u); });
           release();
           b = take();                                             // gW1|gb1[j1, k] += sum_r G1[r, j1] [x | 1][r, k]
           mma2(dW1, id_w1, any || s > 0, [&](int t) { return gmn(t, s); }, [&](int t) { return make_desc(b + t * pX, 128u, 256u); });
@@ -585,7 +612,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         tc_fence_after();
         for (int s = 0; s < 8; ++s) {
           const uint32_t b = take();
-          mma2(dS, id_gxb, s > 0, [&](int t) { return gk(t, s); }, [&](int t) { return make_desc(b + t * pW1b, (uint32_t)nb * 16u, 128u); });
+          mma2(dS, id_gxb, s > 0, [&](int t) { return gk(t, (s + rot) & 7); }, [&](int t) { return make_desc(b + t * pW1b, (uint32_t)nb * 16u, 128u); });
           release();
         }
         umma_commit(mma_done);
@@ -594,7 +621,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
     }
   } else {
     // ---------------- workers
-    const int rloc = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int rloc = (warp & 3) * 32 + lane, quarter = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph_m = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -609,7 +636,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
           g3[c] = a.g_rgb[row * 3 + c] * y * (1.0f - y);
         }
       }
-      if (half == 0) {
+      if (quarter == 0) {
         float v[8] = {g3[0], g3[1], g3[2], 0.f, 0.f, 0.f, 0.f, 0.f};
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         uint4 parts[2];
@@ -620,7 +647,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         *reinterpret_cast<uint4*>(sG3 + a_off(rloc, 8)) = parts[0];
         *reinterpret_cast<uint4*>(sG3 + 4096 + a_off(rloc, 8)) = parts[1];
       }
-      for (int c0 = half * 16; c0 < RGB_H; c0 += 32) {
+      for (int c0 = quarter * 16; c0 < RGB_H; c0 += 64) {
         const uint32_t bits = live ? (uint32_t)a.bits[row * 16 + 8 + (c0 >> 4)] : 0u;
         float v[16];
 #pragma unroll
@@ -633,13 +660,13 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         g_store2(sG, rloc, c0 + 8, v + 8);
       }
       proxy_fence();
-      named_sync(1, RGB_WORKERS);
+      named_sync(1, RGB_B_WORKERS);
       if (tid == 0) mbar_arrive(a_ready);
       // G1 = scratch .* [h1 > 0]
       mbar_wait(mma_done, ph_m);
       ph_m ^= 1;
       tc_fence_after();
-      for (int c0 = half * 16; c0 < RGB_H; c0 += 32) {
+      for (int c0 = quarter * 16; c0 < RGB_H; c0 += 64) {
         const uint32_t bits = live ? (uint32_t)a.bits[row * 16 + (c0 >> 4)] : 0u;
         float v[16];
         tmem_ld16(dS + lane_base + (uint32_t)c0, v);
@@ -650,13 +677,13 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
       }
       tc_fence_before();
       proxy_fence();
-      named_sync(1, RGB_WORKERS);
+      named_sync(1, RGB_B_WORKERS);
       if (tid == 0) mbar_arrive(a_ready);
       // g_x columns [0, 128)
       mbar_wait(mma_done, ph_m);
       ph_m ^= 1;
       tc_fence_after();
-      for (int c0 = half * 16; c0 < 128; c0 += 32) {
+      for (int c0 = quarter * 16; c0 < 128; c0 += 64) {
         float v[16];
         tmem_ld16(dS + lane_base + (uint32_t)c0, v);
         if (live) {
@@ -665,13 +692,13 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         }
       }
       tc_fence_before();
-      named_sync(1, RGB_WORKERS);
+      named_sync(1, RGB_B_WORKERS);
       if (tid == 0) mbar_arrive(a_ready);
       // g_x columns [128, K0)
       mbar_wait(mma_done, ph_m);
       ph_m ^= 1;
       tc_fence_after();
-      for (int c0 = half * 16; c0 < nb; c0 += 32) {
+      for (int c0 = quarter * 16; c0 < nb; c0 += 64) {
         float v[16];
         tmem_ld16(dS + lane_base + (uint32_t)c0, v);
         if (live) {
@@ -681,14 +708,14 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
         }
       }
       tc_fence_before();
-      named_sync(1, RGB_WORKERS);     // scratch drained and G1 consumed before the next tile's G2 / a_ready
+      named_sync(1, RGB_B_WORKERS);     // scratch drained and G1 consumed before the next tile's G2 / a_ready
     }
     // ---- flush the weight gradients (accumulator row = TMEM lane): wait for the last tile's MMAs first (they were all
     // committed to mma_done, which this thread has already waited on for every phase)
     if ((int64_t)blockIdx.x < n_tiles) {
       tc_fence_after();
       const int m = rloc;
-      for (int c0 = half * 16; c0 < xcols; c0 += 32) {            // gW1 | gb1: lane j1, column k
+      for (int c0 = quarter * 16; c0 < xcols; c0 += 64) {            // gW1 | gb1: lane j1, column k
         float v[16];
         tmem_ld16(dW1 + lane_base + (uint32_t)c0, v);
 #pragma unroll
@@ -699,7 +726,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
           else if (k == S.K0 && a.gb1) atomicAdd(a.gb1 + m, v[i]);
         }
       }
-      for (int c0 = half * 16; c0 < RGB_H; c0 += 32) {            // gW2: lane j2, column j1
+      for (int c0 = quarter * 16; c0 < RGB_H; c0 += 64) {            // gW2: lane j2, column j1
         float v[16];
         tmem_ld16(dW2 + lane_base + (uint32_t)c0, v);
         if (a.gW2) {
@@ -708,7 +735,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
             if (v[i] != 0.0f) atomicAdd(a.gW2 + (size_t)m * RGB_H + c0 + i, v[i]);
         }
       }
-      if (half == 0) {
+      if (quarter == 0) {
         float v[16];
         tmem_ld16(dW3 + lane_base, v);                             // gW3: lane j2, column c
         if (a.gW3) {
@@ -723,7 +750,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_bwd_kernel(const RgbBwdArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == RGB_B_WORKERS / 32) {
     __syncwarp();
     tmem_dealloc(tmem, 512);
   }
@@ -833,7 +860,7 @@ int ffb_rgbmlp_bwd(const float* g_rgb, const float* rgb, const uint16_t* relu_bi
   }
   const int64_t tiles = (n + 127) / 128;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  rgb_bwd_kernel<<<grid, RGB_THREADS, smem, (cudaStream_t)stream>>>(a);
+  rgb_bwd_kernel<<<grid, RGB_B_THREADS, smem, (cudaStream_t)stream>>>(a);
   FFB_LAUNCHED();
   return FFB_OK;
 }

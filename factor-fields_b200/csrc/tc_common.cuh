@@ -103,6 +103,30 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 out[TERMS]) {
   }
 }
 
+// Two fp32 values -> TERMS packed bf16x2 words (low half = a): one cvt.rn.bf16x2 per part, residuals by integer
+// re-expansion of the halves (bf16 -> fp32 is a 16-bit shift) — the same round-to-nearest parts as split_bf16.
+template <int TERMS>
+__device__ __forceinline__ void split2_packed(float a, float b, uint32_t out[TERMS]) {
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&p);
+    out[t] = w;
+    if (t + 1 < TERMS) {
+      a -= __uint_as_float(w << 16);
+      b -= __uint_as_float(w & 0xffff0000u);
+    }
+  }
+}
+template <int TERMS>
+__device__ __forceinline__ void split8_packed(const float x[8], uint4 out[TERMS]) {
+  uint32_t w[4][TERMS];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split2_packed<TERMS>(x[2 * i], x[2 * i + 1], w[i]);
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) out[t] = make_uint4(w[0][t], w[1][t], w[2][t], w[3][t]);
+}
+
 // 8 consecutive fp32 values -> one 16-byte chunk (8 bf16) per part
 template <int TERMS>
 __device__ __forceinline__ void split8_parts(const float x[8], uint4 out[TERMS]) {
