@@ -384,10 +384,10 @@ __global__ void __launch_bounds__(256) render_input_fwd_kernel(const float* __re
 }
 
 __global__ void render_input_bwd_kernel(const float* __restrict__ feat, int ld_feat, const int32_t* __restrict__ app_idx,
-                                        const float* __restrict__ g_in, float* __restrict__ g_feat, int64_t n,
+                                        const float* __restrict__ g_in, int ld_gin, float* __restrict__ g_feat, int64_t n,
                                         const int32_t* __restrict__ n_dev, int C, int viewpe, int feape) {
   n = resolve_n(n, n_dev);
-  const int W = 3 + C + 6 * viewpe + 2 * feape * C;
+  const int W = ld_gin > 0 ? ld_gin : 3 + C + 6 * viewpe + 2 * feape * C;      // row stride of g_in
   const int oPF = C + 3;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * C; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = t / C;
@@ -534,12 +534,12 @@ int ffb_render_input_fwd(const float* feat, int32_t ld_feat, const float* rays, 
   return FFB_OK;
 }
 
-int ffb_render_input_bwd(const float* feat, int32_t ld_feat, const int32_t* app_idx, const float* g_in, float* g_feat, int64_t n,
-                         const int32_t* n_dev, int32_t C, int32_t viewpe, int32_t feape, void* stream) {
+int ffb_render_input_bwd(const float* feat, int32_t ld_feat, const int32_t* app_idx, const float* g_in, int32_t ld_gin, float* g_feat,
+                         int64_t n, const int32_t* n_dev, int32_t C, int32_t viewpe, int32_t feape, void* stream) {
   FFB_REQUIRE(feat && g_in && g_feat && C > 0, "bad argument");
   if (n <= 0) return FFB_OK;
-  render_input_bwd_kernel<<<blocks_for(n * C, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(feat, ld_feat, app_idx, g_in, g_feat, n,
-                                                                                              n_dev, C, viewpe, feape);
+  render_input_bwd_kernel<<<blocks_for(n * C, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(feat, ld_feat, app_idx, g_in, ld_gin, g_feat,
+                                                                                              n, n_dev, C, viewpe, feape);
   FFB_LAUNCHED();
   return FFB_OK;
 }

@@ -52,14 +52,10 @@ __device__ __forceinline__ void stage_tile(uint8_t* dst, uint32_t part_bytes, ui
       const int it = it0 + b;
       if (it < items) {
         uint8_t* p = dst + (uint32_t)(it % nchunks) * sc + (uint32_t)(it / nchunks) * TILE_SR + (uint32_t)rr * 16u + (uint32_t)q * 4u;
+        uint32_t w[TERMS];
+        split2_packed<TERMS>(v[b].x, v[b].y, w);
 #pragma unroll
-        for (int t = 0; t < TERMS; ++t) {
-          const __nv_bfloat16 a = __float2bfloat16_rn(v[b].x), c = __float2bfloat16_rn(v[b].y);
-          v[b].x -= __bfloat162float(a);
-          v[b].y -= __bfloat162float(c);
-          __nv_bfloat162 ac = __halves2bfloat162(a, c);
-          *reinterpret_cast<uint32_t*>(p + (uint32_t)t * part_bytes) = *reinterpret_cast<uint32_t*>(&ac);
-        }
+        for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint32_t*>(p + (uint32_t)t * part_bytes) = w[t];
       }
     }
   }
@@ -86,14 +82,10 @@ __device__ __forceinline__ void tile_store(float2 v[NB], uint8_t* dst, uint32_t 
     const int it = warp + nwarps * b;
     if (it < items) {
       uint8_t* p = dst + (uint32_t)(it % nchunks) * sc + (uint32_t)(it / nchunks) * TILE_SR + (uint32_t)rr * 16u + (uint32_t)q * 4u;
+      uint32_t w[TERMS];
+      split2_packed<TERMS>(v[b].x, v[b].y, w);
 #pragma unroll
-      for (int t = 0; t < TERMS; ++t) {
-        const __nv_bfloat16 a = __float2bfloat16_rn(v[b].x), c = __float2bfloat16_rn(v[b].y);
-        v[b].x -= __bfloat162float(a);
-        v[b].y -= __bfloat162float(c);
-        __nv_bfloat162 ac = __halves2bfloat162(a, c);
-        *reinterpret_cast<uint32_t*>(p + (uint32_t)t * part_bytes) = *reinterpret_cast<uint32_t*>(&ac);
-      }
+      for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint32_t*>(p + (uint32_t)t * part_bytes) = w[t];
     }
   }
 }
@@ -102,7 +94,7 @@ __device__ __forceinline__ void tile_store(float2 v[NB], uint8_t* dst, uint32_t 
 template <int TERMS>
 __device__ __forceinline__ void store_row8(uint8_t* dst, uint32_t part_bytes, uint32_t sc, int r, int c0, const float v[8]) {
   uint4 parts[TERMS];
-  split8_parts<TERMS>(v, parts);
+  split8_packed<TERMS>(v, parts);
   uint8_t* p = dst + (uint32_t)(c0 >> 3) * sc + (uint32_t)(r >> 3) * TILE_SR + (uint32_t)(r & 7) * 16u;
 #pragma unroll
   for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint4*>(p + (uint32_t)t * part_bytes) = parts[t];

@@ -459,12 +459,18 @@ struct RgbBwdArgs {
   const uint8_t* sx; const uint8_t* sh1; const uint8_t* sh2;   // forward streams
   const uint8_t* wpack;                     // backward part of the workspace (rgb_pack_bwd_kernel)
   const float* W3;                          // [3, 128] fp32
-  float* g_x;                               // [n, K0]
+  float* g_x; int ld_gx;                    // [n, ld_gx], ld_gx >= K0 and a multiple of 4 (16-byte aligned rows)
   float* gW1; float* gb1; float* gW2; float* gb2; float* gW3;   // accumulated into (atomics)
   int64_t n; const int32_t* n_dev;
   RgbShape S;
 };
 
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void g_store2(uint8_t* sG, int r, int c0, const float v[8]) {
   uint4 parts[2];
   split8_packed<2>(v, parts);
@@ -686,9 +692,9 @@ __global__ void __launch_bounds__(RGB_B_THREADS, 1) rgb_bwd_kernel(const RgbBwdA
       for (int c0 = quarter * 16; c0 < 128; c0 += 64) {
         float v[16];
         tmem_ld16(dS + lane_base + (uint32_t)c0, v);
-        if (live) {
+        if (live) {       // 64 contiguous bytes per lane
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) *reinterpret_cast<float2*>(a.g_x + row * S.K0 + c0 + i) = make_float2(v[i], v[i + 1]);
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(a.g_x + row * a.ld_gx + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
       tc_fence_before();
@@ -703,8 +709,8 @@ __global__ void __launch_bounds__(RGB_B_THREADS, 1) rgb_bwd_kernel(const RgbBwdA
         tmem_ld16(dS + lane_base + (uint32_t)c0, v);
         if (live) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (128 + c0 + i < S.K0) a.g_x[row * S.K0 + 128 + c0 + i] = v[i];
+          for (int i = 0; i < 16; i += 4)
+            if (128 + c0 + i + 4 <= a.ld_gx) *reinterpret_cast<float4*>(a.g_x + row * a.ld_gx + 128 + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
       tc_fence_before();
@@ -718,21 +724,34 @@ __global__ void __launch_bounds__(RGB_B_THREADS, 1) rgb_bwd_kernel(const RgbBwdA
       for (int c0 = quarter * 16; c0 < xcols; c0 += 64) {            // gW1 | gb1: lane j1, column k
         float v[16];
         tmem_ld16(dW1 + lane_base + (uint32_t)c0, v);
+        const bool vec2 = a.gW1 && ((S.K0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.gW1) & 7) == 0);   // 8-byte aligned column pairs
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 16; i += 2) {
           const int k = c0 + i;
-          if (v[i] == 0.0f) continue;
-          if (k < S.K0) { if (a.gW1) atomicAdd(a.gW1 + (size_t)m * S.K0 + k, v[i]); }
-          else if (k == S.K0 && a.gb1) atomicAdd(a.gb1 + m, v[i]);
+          if (vec2 && k + 1 < S.K0) {
+            if (v[i] != 0.0f || v[i + 1] != 0.0f) red_add2(a.gW1 + (size_t)m * S.K0 + k, v[i], v[i + 1]);
+            continue;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (v[i + u] == 0.0f) continue;
+            if (k + u < S.K0) { if (a.gW1) atomicAdd(a.gW1 + (size_t)m * S.K0 + k + u, v[i + u]); }
+            else if (k + u == S.K0 && a.gb1) atomicAdd(a.gb1 + m, v[i + u]);
+          }
         }
       }
       for (int c0 = quarter * 16; c0 < RGB_H; c0 += 64) {            // gW2: lane j2, column j1
         float v[16];
         tmem_ld16(dW2 + lane_base + (uint32_t)c0, v);
         if (a.gW2) {
+          if ((reinterpret_cast<uintptr_t>(a.gW2) & 15) == 0) {      // 16-byte vector reductions: a quarter of the L2 atomics
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (v[i] != 0.0f) atomicAdd(a.gW2 + (size_t)m * RGB_H + c0 + i, v[i]);
+            for (int i = 0; i < 16; i += 4) red_add4(a.gW2 + (size_t)m * RGB_H + c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (v[i] != 0.0f) atomicAdd(a.gW2 + (size_t)m * RGB_H + c0 + i, v[i]);
+          }
         }
       }
       if (quarter == 0) {
@@ -841,16 +860,18 @@ int64_t ffb_rgbmlp_stream_bytes(int32_t Cf, int32_t view_pe, int32_t fea_pe, int
 }
 
 int ffb_rgbmlp_bwd(const float* g_rgb, const float* rgb, const uint16_t* relu_bits, const void* stream_x, const void* stream_h1,
-                   const void* stream_h2, const void* workspace, const float* W3, float* g_x, float* gW1, float* gb1, float* gW2,
-                   float* gb2, float* gW3, int64_t n, const int32_t* n_dev, int32_t Cf, int32_t view_pe, int32_t fea_pe, void* stream) {
+                   const void* stream_h2, const void* workspace, const float* W3, float* g_x, int32_t ld_gx, float* gW1, float* gb1,
+                   float* gW2, float* gb2, float* gW3, int64_t n, const int32_t* n_dev, int32_t Cf, int32_t view_pe, int32_t fea_pe,
+                   void* stream) {
   RgbBwdArgs a;
   FFB_REQUIRE(g_rgb && rgb && relu_bits && stream_x && stream_h1 && stream_h2 && workspace && W3 && g_x, "null argument");
   FFB_REQUIRE(rgb_shape(Cf, view_pe, fea_pe, &a.S), "appearance-MLP shape not eligible for the fused tensor-core path");
   FFB_REQUIRE(a.S.K0p > 128 && a.S.K0p <= 208, "fused backward expects 128 < padded input width <= 208");
+  FFB_REQUIRE(ld_gx >= a.S.K0 && (ld_gx & 3) == 0 && ((uintptr_t)g_x & 15) == 0, "g_x rows must be 16-byte aligned (ld_gx a multiple of 4, >= K0)");
   if (n <= 0) return FFB_OK;
   a.g_rgb = g_rgb; a.rgb = rgb; a.bits = relu_bits;
   a.sx = (const uint8_t*)stream_x; a.sh1 = (const uint8_t*)stream_h1; a.sh2 = (const uint8_t*)stream_h2;
-  a.wpack = (const uint8_t*)workspace + rgb_pack_fwd_bytes(a.S); a.W3 = W3; a.g_x = g_x;
+  a.wpack = (const uint8_t*)workspace + rgb_pack_fwd_bytes(a.S); a.W3 = W3; a.g_x = g_x; a.ld_gx = ld_gx;
   a.gW1 = gW1; a.gb1 = gb1; a.gW2 = gW2; a.gb2 = gb2; a.gW3 = gW3; a.n = n; a.n_dev = n_dev;
   const size_t smem = rgb_bwd_smem();
   static bool attr_done = false;

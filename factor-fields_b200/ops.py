@@ -611,16 +611,17 @@ class RenderComposite(torch.autograd.Function):
                 (W1, b1), (W2, b2), (W3, _) = layers
                 grads = [(_grad_like(W) if nw else None, _grad_like(b) if (b is not None and nb) else None)
                          for (W, b), (nw, nb) in zip(layers, pn)]
-                g_in = _empty((Na, W1.shape[1]), feat)
+                ld_gin = (W1.shape[1] + 3) // 4 * 4          # 16-byte aligned rows: the kernel writes them with vector stores
+                g_in = _empty((Na, ld_gin), feat)
                 vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
                 with nv.section('rgbmlp_bwd'):
                     nv.check(lib.ffb_rgbmlp_bwd(nv.ptr(g_rgb), nv.ptr(rgb), vp(bits), vp(sx), vp(sh1), vp(sh2), vp(ws), nv.ptr(W3), nv.ptr(g_in),
-                                                vp(grads[0][0]), vp(grads[0][1]), vp(grads[1][0]), vp(grads[1][1]), vp(grads[2][0]),
+                                                ld_gin, vp(grads[0][0]), vp(grads[0][1]), vp(grads[1][0]), vp(grads[1][1]), vp(grads[2][0]),
                                                 C.c_int64(Na), nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
             else:
                 with nv.section('rgbmlp_bwd'):
                     g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn, ctx.a_dev)
-            nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(Na),
+            nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), g_in.shape[1], nv.ptr(g_feat), C.c_int64(Na),
                                               nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
             for (gW, gb), hb in zip(grads, ctx.has_bias):
                 flat.append(gW)
@@ -677,7 +678,7 @@ class RenderMLP(torch.autograd.Function):
         n, ld = feat.shape
         g_feat = torch.zeros_like(feat)
         if n > 0:
-            nv.check(nv.lib().ffb_render_input_bwd(nv.ptr(feat), ld, None, nv.ptr(g_in), nv.ptr(g_feat), C.c_int64(n), None, ld - 1,
+            nv.check(nv.lib().ffb_render_input_bwd(nv.ptr(feat), ld, None, nv.ptr(g_in), 0, nv.ptr(g_feat), C.c_int64(n), None, ld - 1,
                                                    ctx.view_pe, ctx.fea_pe, nv.stream()))
         flat = []
         for (gW, gb), hb in zip(grads, ctx.has_bias):

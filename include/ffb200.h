@@ -215,10 +215,11 @@ int ffb_pe_concat_bwd(const float* x, const float* g, float* gx, int64_t n, cons
 int ffb_render_input_fwd(const float* feat, int32_t ld_feat, const float* rays, const int32_t* ray_id,
                          const int32_t* app_idx, float* out, int64_t n, const int32_t* n_dev,
                          int32_t C, int32_t viewpe, int32_t feape, void* stream);
-/* scatter of the gradient back: g_feat[i, 1:1+C] += d(features) (rows are unique -> plain add). */
+/* scatter of the gradient back: g_feat[i, 1:1+C] += d(features) (rows are unique -> plain add).
+ * ld_gin: row stride of g_in in floats (0 = the input width). */
 int ffb_render_input_bwd(const float* feat, int32_t ld_feat, const int32_t* app_idx, const float* g_in,
-                         float* g_feat, int64_t n, const int32_t* n_dev, int32_t C, int32_t viewpe,
-                         int32_t feape, void* stream);
+                         int32_t ld_gin, float* g_feat, int64_t n, const int32_t* n_dev, int32_t C,
+                         int32_t viewpe, int32_t feape, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused appearance MLP (MLPRender_Fea.forward, FactorFields.py:188-203, on the shaded samples of
@@ -242,13 +243,14 @@ int ffb_rgbmlp_fwd(const float* feat, int32_t ld_feat, const float* rays, const 
                    int32_t view_pe, int32_t fea_pe, void* stream);
 int64_t ffb_rgbmlp_stream_bytes(int32_t Cf, int32_t view_pe, int32_t fea_pe, int64_t n, int32_t which);
 /* Backward of the same MLP (the autograd of FactorFields.py:188-203): g_rgb [n,3] = dL/d rgb, rgb = the forward
- * output.  Writes g_x [n,K0] (gradient w.r.t. the assembled input; ffb_render_input_bwd folds it onto the features)
+ * output.  Writes g_x [n, ld_gx] (ld_gx >= K0, a multiple of 4: 16-byte row alignment for vector stores; gradient
+ * w.r.t. the assembled input; ffb_render_input_bwd folds it onto the features)
  * and ACCUMULATES gW1 [128,K0], gb1, gW2 [128,128], gb2, gW3 [3,128] (any may be NULL).  workspace: the one
  * ffb_rgbmlp_pack filled for this step's weights; W3: the fp32 colour-head weight. */
 int ffb_rgbmlp_bwd(const float* g_rgb, const float* rgb, const uint16_t* relu_bits, const void* stream_x,
                    const void* stream_h1, const void* stream_h2, const void* workspace, const float* W3,
-                   float* g_x, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, int64_t n,
-                   const int32_t* n_dev, int32_t Cf, int32_t view_pe, int32_t fea_pe, void* stream);
+                   float* g_x, int32_t ld_gx, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
+                   int64_t n, const int32_t* n_dev, int32_t Cf, int32_t view_pe, int32_t fea_pe, void* stream);
 int ffb_set_fused_rgbmlp(int enabled);
 
 /* ---------------------------------------------------------------------------------------------

@@ -45,8 +45,8 @@ for tag, outs in [('fwd (rgb only)', (None,) * 7), ('fwd + bits', (bits,) + (Non
                                             C.c_int64(n), None, Cf, vpe, fpe, s))
     print('%-28s %.1f us  (%.1f us per 128-row tile per SM)' % (tag, timeit(f), timeit(f) / max(1, (n + 127) // 128 / 148)))
 g_rgb = torch.randn(n, 3, device='cuda')
-g_x = torch.empty(n, K0, device='cuda')
+g_x = torch.empty(n, 196, device='cuda')
 gW1, gb1, gW2, gb2, gW3 = (torch.zeros_like(t) for t in (W1, b1, W2, b2, W3))
-fb = lambda: nv.check(lib.ffb_rgbmlp_bwd(P(g_rgb), P(rgb), P(bits), P(sx), P(sh1), P(sh2), P(ws), P(W3), P(g_x), P(gW1), P(gb1), P(gW2), P(gb2),
+fb = lambda: nv.check(lib.ffb_rgbmlp_bwd(P(g_rgb), P(rgb), P(bits), P(sx), P(sh1), P(sh2), P(ws), P(W3), P(g_x), 196, P(gW1), P(gb1), P(gW2), P(gb2),
                                          P(gW3), C.c_int64(n), None, Cf, vpe, fpe, s))
 print('%-28s %.1f us' % ('bwd', timeit(fb)))

@@ -231,10 +231,12 @@ def test_fused_appearance_mlp_backward(n):
     _call(lib, 'ffb_rgbmlp_pack', P(W1), P(b1), P(W2), P(W3), P(ws), Cf, vpe, fpe, s)
     _call(lib, 'ffb_rgbmlp_fwd', P(feat), Cf + 1, P(rays), None, None, P(ws), P(b2), P(rgb), P(bits), None, None, None, P(sx), P(sh1), P(sh2),
           C.c_int64(n), None, Cf, vpe, fpe, s)
-    g_x = torch.zeros(n, K0, device='cuda')
+    ld_gx = (K0 + 3) // 4 * 4
+    g_x = torch.zeros(n, ld_gx, device='cuda')
     gW1, gb1, gW2, gb2, gW3 = (torch.zeros_like(t) for t in (W1, b1, W2, b2, W3))
-    _call(lib, 'ffb_rgbmlp_bwd', P(g_rgb), P(rgb), P(bits), P(sx), P(sh1), P(sh2), P(ws), P(W3), P(g_x), P(gW1), P(gb1), P(gW2), P(gb2), P(gW3),
-          C.c_int64(n), None, Cf, vpe, fpe, s)
+    _call(lib, 'ffb_rgbmlp_bwd', P(g_rgb), P(rgb), P(bits), P(sx), P(sh1), P(sh2), P(ws), P(W3), P(g_x), ld_gx, P(gW1), P(gb1), P(gW2), P(gb2),
+          P(gW3), C.c_int64(n), None, Cf, vpe, fpe, s)
+    g_x = g_x[:, :K0]
     torch.cuda.synchronize()
     # float64 reference of the backward pass, with the ReLU decisions the forward kernel recorded (a hidden unit within
     # rounding distance of zero may be decided differently in float64; its sample's g_x row then differs by a whole term)
