@@ -29,6 +29,7 @@ WORKLOAD = ('nerf.yaml train step (fwd+bwd+Adam): 4096 rays x 443 samples/ray, a
             'synthetic Blender-shaped rays, seeded synthetic mid-training weights (bench_workload.make_state)')
 # algorithmic bytes per field query for nerf.yaml (fp32 storage)
 B_FWD, B_BWD = 1236, 3528
+B_BWD_OWN = 12 + 72 + 144 + 2 * 1152      # x + upstream gradient row + saved coeff/basis rows + read-modify-write scatter
 FLOP_LINEAR_MAT, FLOP_RGB = 6400, 83200
 
 
@@ -48,7 +49,7 @@ class ClockSampler:
         self.idx = gpu_index
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
-            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i', str(gpu_index)],
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20', '-i', str(gpu_index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -339,6 +340,12 @@ def run_ours(args):
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['src'],
                 'algorithmic_bytes_per_launch': alg[dom], 'queries_per_launch': n_valid, 'launch_ms': round(sec[dom], 4),
                 'share_of_step': round(sec[dom] / (ms_total / args.steps), 4)}
+    if dom == 'field_bwd':
+        # SURVEY's 3 528 B/query counts a re-gather of the texels (1 152 B) that the saved-row design replaces by 144 B of
+        # streamed coefficient / basis rows: with the bytes this kernel is designed to move (12 + 72 + 144 + 2*1152) the fraction is
+        own = n_valid * B_BWD_OWN
+        roofline['frac_own_design_bytes'] = round(own / (sec[dom] * 1e-3) / 1e9 / pk['hbm'], 4)
+        roofline['own_design_bytes_per_query'] = B_BWD_OWN
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
@@ -565,9 +572,113 @@ def run_regress(args):
         dist.destroy_process_group()
 
 
+def run_eval(args):
+    """`--workload nerf_eval`: forward-only rendering of 800x800 test images (renderer.py:29-98 `evaluation` without the image
+    writers): one step = one image = 640 000 rays through ffb200.renderer.render_ray, eval sampling (nSamples = 440, no jitter)."""
+    rank = int(os.environ.get('RANK', '0'))
+    metric, unit, H = 'nerf_eval_rays_per_s', 'rays/s', 800
+    n_rays = H * H
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        import torch
+        from oracle.torch_port import TorchPort
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        tp = TorchPort(W.make_state(0), W.AABB, W.FREQ_BANDS, W.step_size(), W.RCFG)
+        rays = torch.from_numpy(W.make_rays(1024 * (args.steps + 1), seed=1)[0])
+        with torch.no_grad():
+            tp.forward(rays[:1024], 440, None)
+            t0 = time.perf_counter()
+            for i in range(1, args.steps + 1):
+                tp.forward(rays[i * 1024:(i + 1) * 1024], 440, None)
+            dt = time.perf_counter() - t0
+        val = 1024 * args.steps / dt
+        line = {'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': {'workload': 'nerf.yaml forward-only render', 'rays_per_step': 1024},
+                'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
+                                 'sample': f'1024-ray chunks (the reference\'s evaluation chunk, renderer.py:50) x {args.steps}'},
+                'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+        print(json.dumps(line), flush=True)
+        return
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import ffb200
+    from ffb200 import native as nv
+    from ffb200.models.FactorFields import FactorFields
+    from ffb200.renderer import render_ray
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    cfg = ffb200.load_cfg('nerf.yaml')
+    cfg.dataset.aabb = W.AABB
+    model = FactorFields(cfg, f'cuda:{local}')
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in W.make_state(0).items()})
+    chunk = args.eval_chunk
+    imgs = [torch.from_numpy(W.make_rays(n_rays, seed=200 + i)[0]).pin_memory() for i in range(2)]
+    imgs_d = [r.to(dev) for r in imgs]
+    state = {'i': 0}
+
+    def step_resident():
+        state['i'] += 1
+        with torch.no_grad():
+            return render_ray(imgs_d[state['i'] % 2], model, chunk=chunk, N_samples=-1, white_bg=True, is_train=False, device=dev)[0]
+
+    def step_e2e():
+        state['i'] += 1
+        with torch.no_grad():
+            rgb, depth = render_ray(imgs[state['i'] % 2], model, chunk=chunk, N_samples=-1, white_bg=True, is_train=False, device=dev)
+        return rgb.cpu(), depth.cpu()                      # the reference moves both maps to the host per image (renderer.py:54)
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = nv.launch_count()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), nv.launch_count() - l0
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    ms, launches = timed(step_resident, args.steps)
+    for _ in range(3):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clk = clocks.stop()
+    nv.profile_begin()
+    step_resident()
+    sec = {k: v[0] for k, v in nv.profile_end().items()}
+    pk = peaks()
+    value, e2e = n_rays * args.steps / (ms * 1e-3), n_rays * args.steps / (ms_e2e * 1e-3)
+    n_valid = int(round(0.5439 * n_rays * model.nSamples))
+    line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'nerf.yaml forward-only render of 800x800 images ({n_rays} rays x {model.nSamples} samples, no jitter), '
+                                   f'render_ray chunks of {chunk} rays (the reference uses 1024 / 8192, renderer.py:50,124), bench_workload.make_state weights',
+                       'chunk': chunk, 'l2': 'each image streams ~6 GB of samples / features through HBM; parameters stay L2-resident'},
+            'e2e': {'value': e2e, 'unit': unit, 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': n_rays * 24, 'd2h_bytes_per_step': n_rays * 16,
+                    'api': 'ffb200.renderer.render_ray(host rays) -> rgb_map.cpu(), depth_map.cpu()'},
+            'gpu_launches': launches,
+            'roofline': {'kernel': 'field_fwd', 'bound': 'hbm', 'achieved': round(n_valid * B_FWD / (sec['field_fwd'] * 1e-3) / 1e9, 1), 'peak': pk['hbm'],
+                         'unit': 'GB/s', 'frac': round(n_valid * B_FWD / (sec['field_fwd'] * 1e-3) / 1e9 / pk['hbm'], 4), 'traffic': None,
+                         'peak_source': pk['src'], 'note': 'field forward summed over the chunks of one image; valid fraction taken from the train bench (0.544)',
+                         'launch_ms': round(sec['field_fwd'], 4), 'share_of_step': round(sec['field_fwd'] / (ms / args.steps), 4)},
+            'kernels': {k: {'ms_per_step': round(v, 4)} for k, v in sec.items()}, 'clocks': clk}
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--workload', default='nerf', choices=['nerf'] + list(REGRESS), help='nerf (the headline, default) or a regression driver')
+    ap.add_argument('--eval-chunk', type=int, default=65536)
+    ap.add_argument('--workload', default='nerf', choices=['nerf', 'nerf_eval'] + list(REGRESS), help='nerf (the headline, default) or a regression driver')
     ap.add_argument('--no-dropout', action='store_true', help='image_set: disable F.dropout on the MLP input')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -583,7 +694,9 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}', '--master-addr', '127.0.0.1',
                '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.workload != 'nerf':
+    if args.workload == 'nerf_eval':
+        run_eval(args)
+    elif args.workload != 'nerf':
         run_regress(args)
     elif args.impl == 'reference':
         run_reference(args)

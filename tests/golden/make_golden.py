@@ -77,8 +77,9 @@ def sample_x(m, cfg, N, seed):
     return x
 
 
-def field_case(name, cfgname, aabb, ov, N=301, seed=7):
+def field_case(name, cfgname, aabb, ov, N=301, seed=7, scene_idx=0):
     cfg, m = build(cfgname, aabb, ov, seed)
+    m.scene_idx = scene_idx          # multi-scene models ('reconstructions'): which scene's coefficients are sampled (:433-453)
     x = sample_x(m, cfg, N, seed + 2)
     feats, coeff = m.get_coding(x)
     g = torch.Generator().manual_seed(seed + 3)
@@ -86,7 +87,8 @@ def field_case(name, cfgname, aabb, ov, N=301, seed=7):
     params = [(n, p) for n, p in m.named_parameters() if n.startswith('coeffs') or n.startswith('basises')]
     grads = torch.autograd.grad((feats * G).sum(), [p for _, p in params], allow_unused=True) if params else []
     out = dict(cfgname=cfgname, overrides=json.dumps(ov), aabb_cfg=np.array(aabb, np.float64), x=x.numpy(),
-               G=G.numpy(), feats=feats.detach().numpy(), coeff=coeff.detach().numpy())
+               G=G.numpy(), feats=feats.detach().numpy(), coeff=coeff.detach().numpy(), scene_idx=np.array(scene_idx),
+               n_scene=np.array(int(m.n_scene)))
     for k, v in facts(m).items():
         out['fact.' + k] = v
     for (n, p), gr in zip(params, grads):
@@ -311,13 +313,19 @@ FIELD_CASES = {
                                                                      'model.total_params': 40000, 'model.with_dropout': False}),
 }
 
+# multi-scene models (configs/nerf_set.yaml: mode 'reconstructions', the scene count rides in aabb[1][-1])
+SET_BOX = [[-1.2, -0.7, -1.0, 0], [1.3, 0.9, 0.8, 3]]
+FIELD_CASES['nerf_set_grid'] = ('nerf.yaml', SET_BOX, {**SMALL, 'defaults.mode': 'reconstructions'})
+FIELD_CASES['nerf_set_vm'] = ('nerf.yaml', SET_BOX, {**SMALL, 'defaults.mode': 'reconstructions', 'model.coeff_type': 'vm', 'model.basis_type': 'vm'})
+SCENE_IDX = {'nerf_set_grid': 1, 'nerf_set_vm': 2}
+
 if __name__ == '__main__':
     only = sys.argv[1:]
     for name, (cfgname, aabb, ov) in FIELD_CASES.items():
         if only and name not in only:
             continue
         try:
-            field_case(name, cfgname, aabb, ov)
+            field_case(name, cfgname, aabb, ov, scene_idx=SCENE_IDX.get(name, 0))
         except Exception as e:  # a preset the reference itself cannot run is recorded, not hidden
             import traceback; traceback.print_exc()
             print('FAILED in reference:', name, repr(e), flush=True)

@@ -24,6 +24,9 @@ def build_model(g, device='cuda'):
     sd = {k[len('param.'):]: torch.from_numpy(np.ascontiguousarray(v)) for k, v in g.items() if k.startswith('param.')}
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
+    if 'scene_idx' in g:
+        m.scene_idx = int(g['scene_idx'])
+        m._plans = {}
     return cfg, m
 
 

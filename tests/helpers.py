@@ -41,8 +41,10 @@ def oracle_spec(g):
         sec, key = k.split('.')
         if sec == 'model' and key in md:
             md[key] = v
-    spec = dict(mode=ref_mode(cfgname), in_dim=int(g['fact.in_dim']), aabb=g['fact.aabb'],
+    spec = dict(mode=ov.get('defaults.mode', ref_mode(cfgname)), in_dim=int(g['fact.in_dim']), aabb=g['fact.aabb'],
                 freq_bands=g['fact.freq_bands'], basis_dims=g['fact.basis_dims'].tolist(), **md)
+    if 'n_scene' in g:
+        spec.update(n_scene=int(g['n_scene']), scene_idx=int(g['scene_idx']))
     return spec
 
 
