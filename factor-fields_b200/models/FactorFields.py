@@ -666,7 +666,14 @@ class FactorFields(torch.nn.Module):
         return alpha.view(shape)
 
     @torch.no_grad()
-    def getDenseAlpha(self, gridSize=None, times=16):
+    def getDenseAlpha(self, gridSize=None, times=16, sharded=True):
+        """FactorFields.py:730-755.  With torch.distributed initialised (and sharded=True) the lattice slices are sharded round-robin across
+        the ranks (16 x prod(gridSize) field queries per event) and the partial volumes are summed with one
+        all-reduce; every rank still draws the jitter of EVERY slice from the CPU generator, so the random stream — and
+        therefore the volume — is the one a single process produces."""
+        rank, world = 0, 1
+        if sharded and torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         gridSize = self.gridSize.tolist() if gridSize is None else gridSize
         aabbSize = self.inward_aabb[1] - self.inward_aabb[0]
         units = aabbSize / (torch.LongTensor(gridSize).to(self.device) - 1)
@@ -679,9 +686,14 @@ class FactorFields(torch.nn.Module):
         alpha = torch.zeros_like(dense_xyz[..., 0])
         for _ in range(times):
             for i in range(gridSize[2]):
-                shiftment = (torch.rand(dense_xyz[i].shape) * 2 - 1).to(self.device) * (units / 2 * 1.2) if times > 1 else 0.0
+                shiftment = torch.rand(dense_xyz[i].shape) if times > 1 else None       # drawn on every rank (same stream)
+                if i % world != rank:
+                    continue
+                shiftment = (shiftment * 2 - 1).to(self.device) * (units / 2 * 1.2) if times > 1 else 0.0
                 alpha[i] += self.compute_alpha((dense_xyz[i] + shiftment).view(-1, 3),
                                                stepSize * self.cfg.renderer.distance_scale).view((gridSize[1], gridSize[0]))
+        if world > 1:
+            torch.distributed.all_reduce(alpha, op=torch.distributed.ReduceOp.SUM)
         return alpha / times, dense_xyz
 
     @torch.no_grad()

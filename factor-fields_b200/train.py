@@ -14,6 +14,41 @@ def shard_slice(n, rank, world):
     return slice(start, start + base + (1 if rank < rem else 0))
 
 
+def _dist_world(group=None):
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+    return 0, 1
+
+
+def gather_rows(local, n_total, group=None):
+    """All ranks hold consecutive row shards (shard_slice order) of a [n_total, ...] tensor; returns the whole tensor on
+    every rank.  Shards may differ by one row, so they are padded to the largest for the fixed-size all-gather."""
+    rank, world = _dist_world(group)
+    if world == 1:
+        return local
+    per = (int(n_total) + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    torch.distributed.all_gather(out, pad, group=group)
+    return torch.cat([o[:shard_slice(n_total, r, world).stop - shard_slice(n_total, r, world).start] for r, o in enumerate(out)])
+
+
+@torch.no_grad()
+def render_sharded(rays, model, chunk=65536, N_samples=-1, white_bg=True, ndc_ray=False, group=None, render_fn=None):
+    """Evaluation render sharded by ray: rank r renders rows shard_slice(N, r, world) of `rays` [N, 6] (the
+    same tensor on every rank) and the rgb / depth maps are all-gathered, so every rank returns the full (rgb_map [N,3],
+    depth_map [N]) — what renderer.py:29-98 computes per test image on one device."""
+    from .renderer import render_ray
+    rank, world = _dist_world(group)
+    N = rays.shape[0]
+    sl = shard_slice(N, rank, world)
+    fn = render_fn or (lambda r: render_ray(r, model, chunk=chunk, N_samples=N_samples, ndc_ray=ndc_ray, white_bg=white_bg,
+                                            is_train=False, device=model.device))
+    rgb, depth = fn(rays[sl])
+    return gather_rows(rgb, N, group), gather_rows(depth, N, group)
+
+
 class GradBucket:
     """Flat fp32 buffer holding every gradient back to back (parameter storage order), so that one all-reduce per
     step covers grids + MLPs.  Device-agnostic torch code (tested with gloo on CPU)."""

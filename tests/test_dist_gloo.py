@@ -94,3 +94,30 @@ def test_shard_slice_covers_everything():
                 s = shard_slice(n, r, world)
                 got.extend(range(s.start, s.stop))
             assert got == list(range(n))
+
+
+def _worker_render(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import ffb200  # noqa: F401
+    from ffb200.train import gather_rows, render_sharded, shard_slice
+    N = 1001                                    # odd: the shards differ by one row
+    rays = torch.arange(N * 6, dtype=torch.float32).reshape(N, 6)
+    fake = lambda r: (r[:, :3] * 2.0 + 1.0, r[:, 3] - r[:, 0])      # stands in for render_ray on this rank's rows
+    rgb, depth = render_sharded(rays, None, render_fn=fake)
+    np.save(os.path.join(out_dir, f'rgb_{rank}.npy'), rgb.numpy())
+    np.save(os.path.join(out_dir, f'depth_{rank}.npy'), depth.numpy())
+    sl = shard_slice(N, rank, world)
+    assert torch.equal(gather_rows(rays[sl], N), rays)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_render_sharded_world2(tmp_path):
+    """Evaluation sharded by ray: every rank ends up with the full maps, equal to the unsharded render."""
+    world, port = 2, _free_port()
+    mp.start_processes(_worker_render, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method='spawn')
+    rays = torch.arange(1001 * 6, dtype=torch.float32).reshape(1001, 6)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f'rgb_{r}.npy'), (rays[:, :3] * 2.0 + 1.0).numpy())
+        assert np.array_equal(np.load(tmp_path / f'depth_{r}.npy'), (rays[:, 3] - rays[:, 0]).numpy())
