@@ -49,6 +49,29 @@ def render_sharded(rays, model, chunk=65536, N_samples=-1, white_bg=True, ndc_ra
     return gather_rows(rgb, N, group), gather_rows(depth, N, group)
 
 
+def arena_ranges(bucket, keep):
+    """Maximal contiguous [start, stop) ranges of the flat gradient arena covering the parameters with keep[i] True."""
+    out = []
+    for i, k in enumerate(keep):
+        if not k:
+            continue
+        a, b = bucket.offsets[i], bucket.offsets[i + 1]
+        if out and out[-1][1] == a:
+            out[-1][1] = b
+        else:
+            out.append([a, b])
+    return [tuple(r) for r in out]
+
+
+def image_set_shard(n_img, rank, world):
+    """Image-set mode sharded by image: rank r owns the coefficient slabs of images shard_slice(n_img, r, world).
+    Returns (first image, number of local images).  A rank builds its model with aabb[1][-1] = local count, samples pixels
+    of its own images only and feeds z - first_image; no coefficient ever crosses ranks (the reference's 3-D coefficient
+    tensor blends neighbouring slabs with weight ~1e-6 at z = image + 0.5, FactorFields.py:287,433 — inside the 1e-4 bar)."""
+    sl = shard_slice(n_img, rank, world)
+    return sl.start, sl.stop - sl.start
+
+
 class GradBucket:
     """Flat fp32 buffer holding every gradient back to back (parameter storage order), so that one all-reduce per
     step covers grids + MLPs.  Device-agnostic torch code (tested with gloo on CPU)."""
@@ -317,9 +340,13 @@ class RegressStep(TrainStep):
     [0, 640]^3 points / (x, y, image+0.5)), target [B, out_dim].  `step` returns the UNSCALED loss like the notebooks print."""
 
     def __init__(self, model, param_groups, batch, x_dim, out_dim, loss_scale_decay=1.0, is_train=False, betas=(0.9, 0.99),
-                 eps=1e-8, group=None, use_graph=True, warmup=2):
+                 eps=1e-8, group=None, use_graph=True, warmup=2, local_params=()):
+        """local_params: parameters that are NOT replicated across ranks (the image-set coefficient slabs each rank owns,
+        `image_set_shard`): their gradients stay out of the all-reduce."""
         super().__init__(model, param_groups, batch, n_samples=1, betas=betas, eps=eps, lr_decay=1.0, group=group,
                          use_graph=use_graph, warmup=warmup)
+        local = {p.data_ptr() for p in local_params}
+        self._shared_ranges = arena_ranges(self.bucket, [p.data_ptr() not in local for p in self.params])
         model.lazy_counts = False
         self.is_train, self.loss_scale_decay = bool(is_train), float(loss_scale_decay)
         self.rays_s = torch.zeros(self.B, int(x_dim), device=self.dev)         # coordinates
@@ -345,6 +372,11 @@ class RegressStep(TrainStep):
                 v = self.bucket.view(k)
                 if g.data_ptr() != v.data_ptr():
                     v.copy_(g)
+
+    def _all_reduce(self):
+        if self.world > 1:
+            for a, b in self._shared_ranges:     # replicated parameters only (contiguous arena ranges)
+                torch.distributed.all_reduce(self.bucket.flat[a:b], op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     def _capture(self):
         st = (self.scale_d.clone(), self.scale_f.clone())

@@ -121,3 +121,22 @@ def test_render_sharded_world2(tmp_path):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f'rgb_{r}.npy'), (rays[:, :3] * 2.0 + 1.0).numpy())
         assert np.array_equal(np.load(tmp_path / f'depth_{r}.npy'), (rays[:, 3] - rays[:, 0]).numpy())
+
+
+def test_image_set_shard_and_arena_ranges():
+    """Host logic of image-set training sharded by image: image ranges partition the set, and the all-reduce
+    covers exactly the arena slices of the replicated parameters (the coefficient slabs stay local)."""
+    from ffb200.train import GradBucket, arena_ranges, image_set_shard
+    for n_img, world in [(800, 8), (6, 2), (7, 3)]:
+        got = []
+        for r in range(world):
+            i0, n = image_set_shard(n_img, r, world)
+            got.extend(range(i0, i0 + n))
+        assert got == list(range(n_img))
+    params = [torch.zeros(64, 36), torch.zeros(64), torch.zeros(3, 64), torch.zeros(1, 36, 3, 27, 27), torch.zeros(1, 8, 8, 8), torch.zeros(1, 4, 13, 13)]
+    bucket = GradBucket(params)
+    ranges = arena_ranges(bucket, [True, True, True, False, True, True])        # get_optparam_groups order: MLP, coeffs, bases
+    assert len(ranges) == 2 and ranges[0][0] == 0 and ranges[0][1] == bucket.offsets[3] and ranges[1] == (bucket.offsets[4], bucket.offsets[6])
+    covered = sum(b - a for a, b in ranges)
+    assert covered == bucket.offsets[-1] - (bucket.offsets[4] - bucket.offsets[3])
+    assert arena_ranges(bucket, [True] * 6) == [(0, bucket.offsets[-1])]
