@@ -280,9 +280,9 @@ def run_ours(args):
     # field trains: more samples pass the weight threshold), so `e2e` differs from `value` only by the host boundary.
     snap = None if eager else ts.snapshot()
     first = state['i']
+    clocks = ClockSampler(local) if rank == 0 else None     # nvidia-smi needs ~0.1 s to start: launched before the warm-up (same load)
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    clocks = ClockSampler(local) if rank == 0 else None
     ms_total, launches = timed(step_resident, args.steps)
     n_valid, n_app = int(model.last_stats['n_valid']), int(model.last_stats['n_app'])
     if snap is not None:

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(ffb_composite_desc D
                                                             const float* __restrict__ trans, const float* __restrict__ weight,
                                                             const float* __restrict__ rgb, const int32_t* __restrict__ offsets,
                                                             const int32_t* __restrict__ app_offsets, int64_t R, float* __restrict__ g_rgb,
-                                                            float* __restrict__ g_feat0, int ld_g) {
+                                                            float* __restrict__ g_feat0, int ld_g, int zero_rest) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -193,7 +193,14 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(ffb_composite_desc D
         const float fac = FFB_ADD(FFB_SUB(1.0f, FFB_SUB(1.0f, e)), 1e-10f);
         const float g_alpha = gw * trans[i] - after / fac;
         const float g_sigma = g_alpha * e * delta;
-        g_feat0[i * ld_g] = g_sigma * density_act_grad(D, feat0[i * ld_feat]);
+        const float g0 = g_sigma * density_act_grad(D, feat0[i * ld_feat]);
+        if (zero_rest) {     // the whole gradient row: density column + zeros (the caller skips its memset of [Nv, ld_g])
+          float4* row = reinterpret_cast<float4*>(g_feat0 + i * ld_g);
+          row[0] = make_float4(g0, 0.f, 0.f, 0.f);
+          for (int q = 1; q < (ld_g >> 2); ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          g_feat0[i * ld_g] = g0;
+        }
       }
     }
   }
@@ -249,12 +256,13 @@ int ffb_composite_accum(const ffb_composite_desc* h_desc, const float* weight, c
 int ffb_composite_bwd(const ffb_composite_desc* h_desc, const float* g_rgb_map, const float* pre_clamp, const float* feat0,
                       int32_t ld_feat, const float* dist, const float* sigma, const float* trans, const float* weight,
                       const float* rgb, const int32_t* offsets, const int32_t* app_offsets, int64_t R, float* g_rgb, float* g_feat0,
-                      int32_t ld_g, void* stream) {
+                      int32_t ld_g, int32_t zero_rest, void* stream) {
   FFB_REQUIRE(h_desc && g_rgb_map && pre_clamp && feat0 && dist && sigma && trans && weight && offsets && app_offsets && g_feat0,
               "null argument");   // rgb / g_rgb may be NULL when no sample is shaded
+  FFB_REQUIRE(!zero_rest || ((ld_g & 3) == 0 && ((uintptr_t)g_feat0 & 15) == 0), "zero_rest needs 16-byte aligned gradient rows");
   if (R <= 0) return FFB_OK;
   composite_bwd_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(
-      *h_desc, g_rgb_map, pre_clamp, feat0, ld_feat, dist, sigma, trans, weight, rgb, offsets, app_offsets, R, g_rgb, g_feat0, ld_g);
+      *h_desc, g_rgb_map, pre_clamp, feat0, ld_feat, dist, sigma, trans, weight, rgb, offsets, app_offsets, R, g_rgb, g_feat0, ld_g, zero_rest);
   FFB_LAUNCHED();
   return FFB_OK;
 }

@@ -587,7 +587,8 @@ class RenderComposite(torch.autograd.Function):
         Nv, ld = feat.shape
         R = samp['rays'].shape[0]
         Na = ctx.Na
-        g_feat = torch.zeros_like(feat)
+        zero_rest = 1 if (ld % 4 == 0 and Nv > 0) else 0     # the composite kernel writes whole gradient rows: no memset of [Nv, ld]
+        g_feat = torch.empty_like(feat) if zero_rest else torch.zeros_like(feat)
         g_rgb = _empty((Na, 3), feat)
         g_rgb_map = g_rgb_map.contiguous()
         if Nv > 0:
@@ -596,7 +597,7 @@ class RenderComposite(torch.autograd.Function):
                                                nv.ptr(samp['dist']), nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight),
                                                nv.ptr(rgb) if Na > 0 else None,
                                                nv.i32p(samp['offsets']), nv.i32p(app_offsets), C.c_int64(R), nv.ptr(g_rgb) if Na > 0 else None,
-                                               nv.ptr(g_feat), ld, nv.stream()))
+                                               nv.ptr(g_feat), ld, zero_rest, nv.stream()))
         layers = _split_params(params, ctx.has_bias)
         needs = ctx.needs_input_grad[6:]
         pn, i = [], 0

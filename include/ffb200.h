@@ -320,12 +320,14 @@ int ffb_composite_app_fill(const float* weight, float weight_thres, const int32_
 int ffb_composite_accum(const ffb_composite_desc* h_desc, const float* weight, const float* z,
                         const float* rgb, const int32_t* offsets, const int32_t* app_offsets, int64_t R,
                         float* rgb_map, float* pre_clamp, float* acc, float* depth, void* stream);
-/* Backward: g_rgb_map [R,3] -> g_rgb [Na,3], g_feat0 (row stride ld_g; d loss / d density feature). */
+/* Backward: g_rgb_map [R,3] -> g_rgb [Na,3], g_feat0 (row stride ld_g; d loss / d density feature).
+ * zero_rest != 0: also zero columns 1..ld_g-1 of every valid sample's row (the caller then needs no memset of the
+ * [Nv, ld_g] gradient buffer before the appearance MLP adds its feature gradients). */
 int ffb_composite_bwd(const ffb_composite_desc* h_desc, const float* g_rgb_map, const float* pre_clamp,
                       const float* feat0, int32_t ld_feat, const float* dist, const float* sigma,
                       const float* trans, const float* weight, const float* rgb, const int32_t* offsets,
                       const int32_t* app_offsets, int64_t R, float* g_rgb, float* g_feat0, int32_t ld_g,
-                      void* stream);
+                      int32_t zero_rest, void* stream);
 /* compute_alpha (:710-727) tail: alpha[i] = 1 - exp(-basis2density(feat0[i]) * length). */
 int ffb_density_alpha(const ffb_composite_desc* h_desc, const float* feat0, int32_t ld_feat, float length,
                       int64_t n, const int32_t* n_dev, float* alpha, void* stream);
