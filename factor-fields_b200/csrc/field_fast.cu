@@ -439,6 +439,142 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_kernel(const FastPara
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Run-aggregated coefficient scatter.  Consecutive lanes are consecutive samples of a ray, and a ray takes ~8 steps
+// through one cell of the (coarse) coefficient grid, so most lanes of a warp add into the same 2^DC texels.  Each lane
+// parks its coefficient-gradient row, its corner weights and its cell in shared memory; the warp then splits the
+// (run of equal cells) x (corner) x (16-byte vector) items among its lanes: an item sums its run's contributions and
+// issues ONE vector reduction — ~6x fewer L2 reductions for the coefficient grid (40 -> ~7 per query at nerf.yaml).
+// The basis levels (fine grids, short runs) scatter per lane as in fast_bwd_saved_kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int AGG_G = 24;                 // gradient row (W <= 24)
+constexpr int AGG_STRIDE = AGG_G + 8 + 4 + 1;   // + corner weights + row bases + flags; odd: conflict-free column reads across rows
+
+template <int DB, int DC, bool NEAR_B, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_agg_kernel(const FastParams P, const FastGrads G, const float* __restrict__ x,
+                                                                      int64_t n, const int32_t* __restrict__ n_dev,
+                                                                      const float* __restrict__ g_feats, const float* __restrict__ g_coeff,
+                                                                      const float* __restrict__ coeff, const float* __restrict__ basis) {
+  constexpr int ROWS = 1 << (DC - 1), NCORN = 2 * ROWS;
+  __shared__ float rec_all[NT / 32][32 * AGG_STRIDE];
+  n = resolve_n(n, n_dev);
+  const float msize = fast_msize(P);
+  const int lane = threadIdx.x & 31, W = P.W;
+  float* rec = rec_all[threadIdx.x >> 5];
+  const int nops = (W + 3) >> 2;            // vector reductions per texel (16-byte ones + at most one 8-byte one)
+  const int64_t n_chunks = (n + 31) / 32;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp0; k < n_chunks; k += nwarps) {
+    const int64_t i = k * 32 + lane;
+    const bool active = i < n;
+    float xr[3] = {0.f, 0.f, 0.f};
+    const float* gf = nullptr;
+    const float* crow = nullptr;
+    TapSet<DC, false> tc;
+    float* my = rec + lane * AGG_STRIDE;
+    int key = -1 - lane;
+    if (active) {
+      for (int d = 0; d < P.xdim; ++d) xr[d] = x[i * P.xdim + d];
+      gf = g_feats ? g_feats + i * W : nullptr;
+      crow = coeff + i * W;
+    }
+    if (G.c) {
+      int flags = 0;
+      if (active) {
+        const float* gcf = g_coeff ? g_coeff + i * W : nullptr;
+        const float* brow = basis + i * W;
+        coeff_taps<DC, false>(P, xr, tc);
+#pragma unroll
+        for (int c = 0; c < AGG_G; c += 2) {
+          float2 v = make_float2(0.f, 0.f);
+          if (c < W) {
+            const float2 g = gf ? *reinterpret_cast<const float2*>(gf + c) : make_float2(0.f, 0.f);
+            const float2 b = *reinterpret_cast<const float2*>(brow + c);
+            v = make_float2(g.x * b.x, g.y * b.y);
+            if (gcf) {
+              const float2 g2 = *reinterpret_cast<const float2*>(gcf + c);
+              v.x += g2.x;
+              v.y += g2.y;
+            }
+          }
+          my[c] = v.x;
+          my[c + 1] = v.y;
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          my[AGG_G + 2 * r] = tc.wrow[r] * tc.wx0;
+          my[AGG_G + 2 * r + 1] = tc.wrow[r] * tc.wx1;
+          my[AGG_G + 8 + r] = __int_as_float(tc.base[r]);
+          flags |= (tc.row_ok[r] ? 1 : 0) << r;
+        }
+        flags |= (tc.x1_ok ? 1 : 0) << 4;
+        key = tc.base[0];
+      }
+      my[AGG_G + 12] = __int_as_float(flags);
+      const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const unsigned hm = __ballot_sync(0xffffffffu, lane == 0 || key != prev);     // run heads
+      const unsigned am = __ballot_sync(0xffffffffu, active);
+      __syncwarp();
+      const int total = __popc(hm) * NCORN * nops;
+      for (int t = lane; t < total; t += 32) {
+        const int v = t % nops, c = (t / nops) % NCORN, rho = t / (nops * NCORN);
+        const int s = (int)__fns(hm, 0, rho + 1);
+        if (!((am >> s) & 1u)) continue;
+        const unsigned rest = s < 31 ? (hm >> (s + 1)) : 0u;
+        const int e = rest ? s + __ffs(rest) : 32;                                    // one past the run's last lane
+        const float* L = rec + s * AGG_STRIDE;
+        const int fl = __float_as_int(L[AGG_G + 12]), r = c >> 1, xs = c & 1;
+        if (!((fl >> r) & 1) || (xs && !((fl >> 4) & 1))) continue;                   // corner outside the grid
+        const size_t e0 = (size_t)(__float_as_int(L[AGG_G + 8 + r]) + xs) * W;         // first float of the texel
+        int ch0, wd;
+        if ((e0 & 3) == 0) { ch0 = 4 * v; wd = (W - ch0) >= 4 ? 4 : 2; }              // 16-byte aligned texel: v4 ... [v2]
+        else { ch0 = v == 0 ? 0 : 4 * v - 2; wd = v == 0 ? 2 : 4; }                   // 8-byte aligned only: v2 v4 ...
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int m = s; m < e; ++m) {
+          const float* M = rec + m * AGG_STRIDE;
+          const float w = M[AGG_G + c];
+          a0 += w * M[ch0];
+          a1 += w * M[ch0 + 1];
+          if (wd == 4) {
+            a2 += w * M[ch0 + 2];
+            a3 += w * M[ch0 + 3];
+          }
+        }
+        if (wd == 4) red_add_v4(G.c + e0 + ch0, a0, a1, a2, a3);
+        else red_add_v2(G.c + e0 + ch0, a0, a1);
+      }
+      __syncwarp();
+    }
+    if (!active) continue;
+#pragma unroll 1
+    for (int l = 0; l < P.n_levels; ++l) {
+      const FastLevel L = P.lv[l];
+      if (!G.b[l]) continue;
+      TapSet<DB, NEAR_B> tb;
+      basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
+      for (int c0 = 0; c0 < L.C; c0 += 2) {
+        const int o = L.col + c0;
+        const float2 g = gf ? *reinterpret_cast<const float2*>(gf + o) : make_float2(0.f, 0.f);
+        const float2 ca = *reinterpret_cast<const float2*>(crow + o);
+        float gb[4];
+        gb[0] = g.x * ca.x;
+        gb[1] = g.y * ca.y;
+        if ((L.C & 3) == 0) {
+          if ((c0 & 2) == 0) {
+            const float2 g_n = gf ? *reinterpret_cast<const float2*>(gf + o + 2) : make_float2(0.f, 0.f);
+            const float2 ca_n = *reinterpret_cast<const float2*>(crow + o + 2);
+            gb[2] = g_n.x * ca_n.x;
+            gb[3] = g_n.y * ca_n.y;
+            scatter_vec<DB, NEAR_B, 4>(G.b[l], L.C, c0, tb, gb);
+          }
+        } else {
+          scatter_vec<DB, NEAR_B, 2>(G.b[l], L.C, c0, tb, gb);
+        }
+      }
+    }
+  }
+}
+
 static bool build_params(const ffb_field_desc& d, FastParams& P, int op_index[FAST_MAX_LEVELS + 1]) {
   if (d.coeff_width <= 0 || d.basis_width != d.coeff_width || d.basis_is_x || d.basis_perm) return false;
   if (d.n_cterms != 1 || d.cterms[0].n_ops != 1 || d.cterms[0].col != 0) return false;
@@ -489,7 +625,7 @@ using namespace ffb;
 // ---- launch configuration (tunable at run time for experiments; defaults are the measured best) -------------
 static int g_fwd_cfg = 1;   // 0: 128 threads, compiler-chosen registers   1: 128 x >=8 CTAs/SM   2: 128 x >=6   3: 256 x >=4
 static int g_fwd_stage = 0; // 1: narrow rows leave through shared memory as coalesced chunks
-static int g_bwd_cfg = 1;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)
+static int g_bwd_cfg = 2;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)   2: 1 + run-aggregated coefficient scatter
 static int g_lpar = 1;      // 1: batches of at most LPAR_MAX_ITEMS (query, level) pairs use the level-parallel kernels
 constexpr int64_t LPAR_MAX_ITEMS = 148 * 2048 * 3;   // ~3 full waves of resident threads; above that one thread per query wins
 
@@ -528,6 +664,10 @@ static void launch_bwd(const FastParams& P, const FastGrads& G, const float* x, 
   if (coeff && basis && g_bwd_cfg != 0 && n * P.n_levels <= LPAR_MAX_ITEMS && g_lpar) {
     fast_bwd_saved_kernel<DB, DC, NB, NC, 0, 128, 6, true><<<blocks_for(n * P.n_levels, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff,
                                                                                                             coeff, basis);
+    return;
+  }
+  if (coeff && basis && g_bwd_cfg == 2 && P.W <= AGG_G && !NC && (P.W & 1) == 0) {      // run-aggregated coefficient scatter
+    fast_bwd_saved_agg_kernel<DB, DC, NB, 128, 6><<<blocks_for(n, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis);
     return;
   }
   if (coeff && basis && g_bwd_cfg != 0) {
