@@ -45,6 +45,7 @@ struct TapSet {
   int base[NEAREST ? 1 : (1 << (D - 1))];
   float wrow[NEAREST ? 1 : (1 << (D - 1))];
   float wx0, wx1;
+  bool x0_ok;   // x-low corner inside the grid (its weight is also folded to 0 when not)
   bool x1_ok;   // x-high corner inside the grid
   bool row_ok[NEAREST ? 1 : (1 << (D - 1))];
 };
@@ -66,6 +67,7 @@ __device__ __forceinline__ void make_tapset(const float c[3], const int size[3],
     t.wrow[0] = 1.0f;
     t.wx0 = 1.0f;
     t.wx1 = 0.0f;
+    t.x0_ok = ok;
     t.x1_ok = false;
     return;
   }
@@ -96,6 +98,7 @@ __device__ __forceinline__ void make_tapset(const float c[3], const int size[3],
     t.wrow[r] = w;
   }
   // fold "x-low corner out of bounds" (zeros padding, only possible when the coordinate is outside [-1,1]) into the weight
+  t.x0_ok = x0_ok;
   if (!x0_ok) t.wx0 = 0.0f;
   if (!t.x1_ok) t.wx1 = 0.0f;
   // NB: weights are products (wx*wy)*wz in ATen; we apply wx * (wy*wz) — equal up to one rounding (inside 1e-4 bar).
@@ -454,7 +457,8 @@ template <int DB, int DC, bool NEAR_B, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_agg_kernel(const FastParams P, const FastGrads G, const float* __restrict__ x,
                                                                       int64_t n, const int32_t* __restrict__ n_dev,
                                                                       const float* __restrict__ g_feats, const float* __restrict__ g_coeff,
-                                                                      const float* __restrict__ coeff, const float* __restrict__ basis) {
+                                                                      const float* __restrict__ coeff, const float* __restrict__ basis,
+                                                                      int agg_levels) {
   constexpr int ROWS = 1 << (DC - 1), NCORN = 2 * ROWS;
   __shared__ float rec_all[NT / 32][32 * AGG_STRIDE];
   n = resolve_n(n, n_dev);
@@ -545,9 +549,64 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_agg_kernel(const Fast
       }
       __syncwarp();
     }
+    // ---- the coarsest basis levels (4-channel texels: one 16-byte reduction per corner) the same way
+    constexpr int BROWS = NEAR_B ? 1 : (1 << (DB - 1)), BCORN = NEAR_B ? 1 : 2 * BROWS;
+    int l_first = 0;
+    if (!NEAR_B) {
+#pragma unroll 1
+      for (; l_first < P.n_levels && l_first < agg_levels; ++l_first) {
+        const FastLevel L = P.lv[l_first];
+        if (L.C != 4) break;
+        if (!G.b[l_first]) continue;
+        int bkey = -1 - lane, flags = 0;
+        if (active) {
+          TapSet<DB, NEAR_B> tb;
+          basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
+          // rows are W floats apart (8-byte aligned only): float2 loads
+          const float2 ga = gf ? *reinterpret_cast<const float2*>(gf + L.col) : make_float2(0.f, 0.f);
+          const float2 gb2 = gf ? *reinterpret_cast<const float2*>(gf + L.col + 2) : make_float2(0.f, 0.f);
+          const float2 ca = *reinterpret_cast<const float2*>(crow + L.col), cb = *reinterpret_cast<const float2*>(crow + L.col + 2);
+          my[0] = ga.x * ca.x; my[1] = ga.y * ca.y; my[2] = gb2.x * cb.x; my[3] = gb2.y * cb.y;
+#pragma unroll
+          for (int r = 0; r < BROWS; ++r) {
+            my[AGG_G + 2 * r] = tb.wrow[r] * tb.wx0;
+            my[AGG_G + 2 * r + 1] = tb.wrow[r] * tb.wx1;
+            my[AGG_G + 8 + r] = __int_as_float(tb.base[r]);
+            flags |= (tb.row_ok[r] ? 1 : 0) << r;
+          }
+          flags |= (tb.x1_ok ? 1 : 0) << 4;
+          flags |= (tb.x0_ok ? 1 : 0) << 5;
+          bkey = tb.base[0];
+        }
+        my[AGG_G + 12] = __int_as_float(flags);
+        const int prev = __shfl_up_sync(0xffffffffu, bkey, 1);
+        const unsigned hm = __ballot_sync(0xffffffffu, lane == 0 || bkey != prev);
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        __syncwarp();
+        const int total = __popc(hm) * BCORN;
+        for (int t = lane; t < total; t += 32) {
+          const int c = t % BCORN, rho = t / BCORN;
+          const int s = (int)__fns(hm, 0, rho + 1);
+          if (!((am >> s) & 1u)) continue;
+          const unsigned rest = s < 31 ? (hm >> (s + 1)) : 0u;
+          const int e = rest ? s + __ffs(rest) : 32;
+          const float* Ld = rec + s * AGG_STRIDE;
+          const int fl = __float_as_int(Ld[AGG_G + 12]), r = c >> 1, xs = c & 1;
+          if (!((fl >> r) & 1) || !((fl >> (xs ? 4 : 5)) & 1)) continue;               // corner outside the grid (zeros padding)
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          for (int m = s; m < e; ++m) {
+            const float* M = rec + m * AGG_STRIDE;
+            const float w = M[AGG_G + c];
+            a0 += w * M[0]; a1 += w * M[1]; a2 += w * M[2]; a3 += w * M[3];
+          }
+          red_add_v4(G.b[l_first] + (size_t)(__float_as_int(Ld[AGG_G + 8 + r]) + xs) * 4, a0, a1, a2, a3);
+        }
+        __syncwarp();
+      }
+    }
     if (!active) continue;
 #pragma unroll 1
-    for (int l = 0; l < P.n_levels; ++l) {
+    for (int l = l_first; l < P.n_levels; ++l) {
       const FastLevel L = P.lv[l];
       if (!G.b[l]) continue;
       TapSet<DB, NEAR_B> tb;
@@ -626,6 +685,8 @@ using namespace ffb;
 static int g_fwd_cfg = 1;   // 0: 128 threads, compiler-chosen registers   1: 128 x >=8 CTAs/SM   2: 128 x >=6   3: 256 x >=4
 static int g_fwd_stage = 0; // 1: narrow rows leave through shared memory as coalesced chunks
 static int g_bwd_cfg = 2;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)   2: 1 + run-aggregated coefficient scatter
+static int g_agg_levels = 0;   // leading 4-channel basis levels whose scatter is run-aggregated too (knob "field_bwd_agg_levels"): measured
+                               // SLOWER at nerf.yaml (2 levels: 403 vs 342 us) — their runs are 2-5 samples, the extra staging pass costs more
 static int g_lpar = 1;      // 1: batches of at most LPAR_MAX_ITEMS (query, level) pairs use the level-parallel kernels
 constexpr int64_t LPAR_MAX_ITEMS = 148 * 2048 * 3;   // ~3 full waves of resident threads; above that one thread per query wins
 
@@ -667,7 +728,7 @@ static void launch_bwd(const FastParams& P, const FastGrads& G, const float* x, 
     return;
   }
   if (coeff && basis && g_bwd_cfg == 2 && P.W <= AGG_G && !NC && (P.W & 1) == 0) {      // run-aggregated coefficient scatter
-    fast_bwd_saved_agg_kernel<DB, DC, NB, 128, 6><<<blocks_for(n, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis);
+    fast_bwd_saved_agg_kernel<DB, DC, NB, 128, 6><<<blocks_for(n, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis, g_agg_levels);
     return;
   }
   if (coeff && basis && g_bwd_cfg != 0) {
@@ -709,6 +770,7 @@ int ffb_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "field_bwd_cfg")) g_bwd_cfg = value;
   else if (!strcmp(key, "field_fwd_stage")) g_fwd_stage = value;
   else if (!strcmp(key, "field_level_parallel")) g_lpar = value;
+  else if (!strcmp(key, "field_bwd_agg_levels")) g_agg_levels = value;
   else { set_error("ffb_set_tuning: unknown key %s", key); return FFB_EINVAL; }
   return FFB_OK;
 }
