@@ -404,19 +404,26 @@ __global__ void __launch_bounds__(256, 2) mlp2_bwd_kernel(const float* __restric
     phase ^= 1;
     tc_fence_after();
     if (gx) {
+      // g_x tile -> fp32 staging in the (now idle) A2 region -> coalesced 16-byte stores: the tile's rows are contiguous in
+      // global memory (128 x K0 floats), whereas one row per lane wrote 8-byte pieces 4 K0 bytes apart (7x sector amplification)
+      float* stg = reinterpret_cast<float*>(sA2);
       for (int c0 = half * 16; c0 < S.K0p; c0 += 32) {
         float v[16];
         tmem_ld16(d3 + lane_base + (uint32_t)c0, v);
-        if (row < n) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            if (c0 + i + 1 < S.K0 && (S.K0 & 1) == 0) *reinterpret_cast<float2*>(gx + row * S.K0 + c0 + i) = make_float2(v[i], v[i + 1]);
-            else {
-              if (c0 + i < S.K0) gx[row * S.K0 + c0 + i] = v[i];
-              if (c0 + i + 1 < S.K0) gx[row * S.K0 + c0 + i + 1] = v[i + 1];
-            }
-          }
-        }
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < S.K0) stg[rloc * S.K0 + c0 + i] = v[i];
+      }
+      __syncthreads();
+      const int64_t rows = (n - row0) < 128 ? (n - row0) : 128;
+      const int64_t total = rows * S.K0;                       // floats of this tile
+      float* dst = gx + row0 * S.K0;
+      if (((row0 * S.K0) & 3) == 0 && (reinterpret_cast<uintptr_t>(gx) & 15) == 0) {
+        const int64_t n4 = total >> 2;
+        for (int64_t t = tid; t < n4; t += blockDim.x) reinterpret_cast<float4*>(dst)[t] = reinterpret_cast<const float4*>(stg)[t];
+        for (int64_t t = (n4 << 2) + tid; t < total; t += blockDim.x) dst[t] = stg[t];
+      } else {
+        for (int64_t t = tid; t < total; t += blockDim.x) dst[t] = stg[t];
       }
     }
     tc_fence_before();

@@ -295,11 +295,11 @@ class TrainStep:
         self._check_params()
         if jitter is None:
             jitter = torch.rand(self.B, 1)[:, 0]
-        if self.graph is None:
-            self._capture()
         self.rays_s.copy_(rays[:, :6], non_blocking=True)
         self.target_s.copy_(target, non_blocking=True)
         self.jitter_s.copy_(jitter, non_blocking=True)
+        if self.graph is None:      # capture warms up on THIS batch (an all-zero ray buffer would aim every scatter at one texel)
+            self._capture()
         if not self.graph:
             self._body()
         elif len(self.graph) == 1:
@@ -388,10 +388,10 @@ class RegressStep(TrainStep):
         if x.shape[0] != self.B:
             raise RuntimeError(f'RegressStep was built for batches of {self.B} points, got {x.shape[0]}')
         self._check_params()
-        if self.graph is None:
-            self._capture()
         self.rays_s.copy_(x, non_blocking=True)
         self.target_s.copy_(target.reshape(self.B, -1), non_blocking=True)
+        if self.graph is None:
+            self._capture()
         if not self.graph:
             self._body()
         elif len(self.graph) == 1:
