@@ -51,7 +51,9 @@ __device__ __forceinline__ bool sample_valid(const ffb_sampler_desc& D, const Ra
   }
   bool ok = sample_pos(r.o, r.d, t, D.aabb_min, D.aabb_max, p);
   if (inner_out) *inner_out = ok;
-  if (ok && D.alpha_volume) ok = alpha_lookup(D.alpha_volume, D.alpha_size, D.alpha_aabb_min, D.alpha_inv_size, p) > D.alpha_thres;
+  // forward() looks the mask up for in-box samples only (:864-867); filtering_rays looks it up for EVERY sample (:832-833: a
+  // sample just outside the box still interpolates the boundary voxels under zeros padding)
+  if (D.alpha_volume && (ok || D.alpha_outside)) ok = alpha_lookup(D.alpha_volume, D.alpha_size, D.alpha_aabb_min, D.alpha_inv_size, p) > D.alpha_thres;
   return ok;
 }
 

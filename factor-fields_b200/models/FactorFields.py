@@ -510,10 +510,10 @@ class FactorFields(torch.nn.Module):
             return None
         return torch.rand(n_rays, 1)[:, 0].to(self.device)
 
-    def _sampler_desc(self, N_samples, with_alpha, alpha_thres=0.5, mode=ops.SAMPLE_BOUNDED, z_table=None):
+    def _sampler_desc(self, N_samples, with_alpha, alpha_thres=0.5, mode=ops.SAMPLE_BOUNDED, z_table=None, alpha_outside=False):
         return ops.make_sampler_desc(self.aabb[:, :self.in_dim], self.stepSize, N_samples,
                                      alpha=self.alphaMask if with_alpha else None, alpha_thres=alpha_thres,
-                                     mode=mode, z_table=z_table, bg_len=getattr(self, 'bg_len', 0.0))
+                                     mode=mode, z_table=z_table, bg_len=getattr(self, 'bg_len', 0.0), alpha_outside=alpha_outside)
 
     def sample_point(self, rays_o, rays_d, is_train=True, N_samples=-1):
         """FactorFields.py:586-602 -> (rays_pts [R,S,3], interpx [R,S], ~mask_outbbox [R,S])"""
@@ -749,7 +749,7 @@ class FactorFields(torch.nn.Module):
                 rate_b = (self.aabb[0] - rays_o) / vec
                 mask_inbbox = torch.maximum(rate_a, rate_b).amin(-1) > torch.minimum(rate_a, rate_b).amax(-1)
             else:
-                desc = self._sampler_desc(N_samples, True, alpha_thres=0.0)
+                desc = self._sampler_desc(N_samples, True, alpha_thres=0.0, alpha_outside=True)   # :832-833 tests every sample
                 counts = torch.empty(rays_chunk.shape[0], device=self.device, dtype=torch.int32)
                 nv.check(nv.lib().ffb_sample_count(C.byref(desc), nv.ptr(rays_chunk), None, C.c_int64(rays_chunk.shape[0]),
                                                    nv.i32p(counts), None, nv.stream()))

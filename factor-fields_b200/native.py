@@ -42,7 +42,7 @@ class FieldDesc(C.Structure):
 class SamplerDesc(C.Structure):
     _fields_ = [('aabb_min', f32 * 3), ('aabb_max', f32 * 3), ('step_size', f32), ('n_samples', i32), ('alpha_volume', C.c_void_p),
                 ('alpha_size', i32 * 3), ('alpha_aabb_min', f32 * 3), ('alpha_inv_size', f32 * 3), ('alpha_thres', f32),
-                ('mode', i32), ('bg_len', f32), ('z_table', C.c_void_p)]
+                ('mode', i32), ('bg_len', f32), ('z_table', C.c_void_p), ('alpha_outside', i32)]
 
 
 class CompositeDesc(C.Structure):

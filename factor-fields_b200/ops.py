@@ -383,11 +383,12 @@ SAMPLE_BOUNDED, SAMPLE_NDC, SAMPLE_UNBOUND = 0, 1, 2
 APPEARANCE_TERMS = 3
 
 
-def make_sampler_desc(aabb, step_size, n_samples, alpha=None, alpha_thres=0.5, mode=SAMPLE_BOUNDED, z_table=None, bg_len=0.0):
+def make_sampler_desc(aabb, step_size, n_samples, alpha=None, alpha_thres=0.5, mode=SAMPLE_BOUNDED, z_table=None, bg_len=0.0,
+                      alpha_outside=False):
     """mode / z_table: FFB_SAMPLE_* of include/ffb200.h; z_table is the device [n_samples] interpx row of
     sample_point_ndc / sample_point_unbound (the descriptor keeps a reference so the buffer outlives the launches)."""
     d = nv.SamplerDesc()
-    d.mode, d.bg_len = int(mode), float(bg_len)
+    d.mode, d.bg_len, d.alpha_outside = int(mode), float(bg_len), int(bool(alpha_outside))
     if mode != SAMPLE_BOUNDED:
         if z_table is None or not z_table.is_cuda or z_table.dtype != torch.float32 or z_table.numel() != int(n_samples):
             raise RuntimeError('NDC / unbounded sampling needs a CUDA float32 z_table with n_samples entries')

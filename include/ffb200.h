@@ -276,6 +276,7 @@ typedef struct ffb_sampler_desc {
   int32_t mode;                 /* FFB_SAMPLE_* */
   float bg_len;                 /* self.bg_len (:250), FFB_SAMPLE_UNBOUND only */
   const float* z_table;         /* device [n_samples]: the interpx row shared by all rays (:578-580, :611-623); NULL in mode 0 */
+  int32_t alpha_outside;        /* 1: look the alpha volume up for out-of-box samples too (filtering_rays :832-833) */
 } ffb_sampler_desc;
 
 /* Pass 1: counts[r] = number of valid samples of ray r; tmin[r] = entry distance.

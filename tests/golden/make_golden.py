@@ -225,6 +225,73 @@ def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, i
     print(name, 'valid', int(valid.sum()), 'of', valid.numel(), 'app', int(app.sum()), 'loss', float(loss), flush=True)
 
 
+def maintenance_case():
+    """Alpha-mask maintenance (FactorFields.py:693-841): compute_alpha, getDenseAlpha (times=1: no jitter), updateAlphaMask,
+    filtering_rays (alpha and bbox_only), shrink, upsample_volume_grid.  skimage is not installed here, so the reference's
+    `skimage.morphology.remove_small_objects` call (:774) is served by a scipy.ndimage restatement of that function (label
+    with face connectivity, drop components smaller than min_size) injected into the import stub."""
+    import sys as _sys
+    from scipy import ndimage
+
+    def remove_small_objects(ar, min_size=64, connectivity=1):
+        labels, n = ndimage.label(ar, structure=ndimage.generate_binary_structure(ar.ndim, connectivity))
+        sizes = np.bincount(labels.ravel())
+        small = sizes < min_size
+        small[0] = False
+        out = ar.copy()
+        out[small[labels]] = False
+        return out
+    _sys.modules['skimage.morphology'].remove_small_objects = remove_small_objects
+    _sys.modules['skimage'].morphology = _sys.modules['skimage.morphology']
+    seed = 41
+    cfg, m = build('nerf.yaml', BOX, {**SMALL, 'renderer.alphaMask_thres': 0.02}, seed)
+    with torch.no_grad():      # a density blob: coefficient channel 0 -> hidden unit 63 -> density feature
+        m.linear_mat.backbone[0].weight.mul_(10.0)
+        w0 = m.linear_mat.backbone[-1].weight[0]
+        w0.copy_(2.0 * torch.randn(w0.shape, generator=torch.Generator().manual_seed(seed + 8)))
+        m.linear_mat.backbone[0].weight[63].zero_()
+        m.linear_mat.backbone[0].bias[63] = 1.0
+        w0[63] = 3.5
+    out = dict(cfgname='nerf.yaml', overrides=json.dumps({**SMALL, 'renderer.alphaMask_thres': 0.02}), aabb_cfg=np.array(BOX, np.float64))
+    for n, p in m.named_parameters():
+        out['param.' + n] = p.detach().numpy().copy()
+    for k, v in facts(m).items():
+        out['fact.' + k] = v
+    g = torch.Generator().manual_seed(seed + 1)
+    lo, hi = m.aabb[0], m.aabb[1]
+    xyz = lo + (hi - lo) * torch.rand(500, 3, generator=g)
+    with torch.no_grad():
+        out['ca_xyz'], out['ca_alpha'] = xyz.numpy(), m.compute_alpha(xyz, length=0.2).numpy()
+        gs = [20, 18, 22]
+        alpha, dense_xyz = m.getDenseAlpha(gs, times=1)
+        out['dense_alpha'], out['dense_xyz_sum'] = alpha.numpy(), dense_xyz.double().sum((0, 1, 2)).numpy()
+        torch.manual_seed(777)       # updateAlphaMask jitters the lattice 16 times with torch.rand on the CPU generator (:748)
+        new_aabb = m.updateAlphaMask(tuple(gs), is_update_alphaMask=True)
+        out['new_aabb'] = new_aabb.numpy()
+        out['mask_volume'] = m.alphaMask.alpha_volume[0, 0].numpy()
+        out['mask_aabb'] = m.alphaMask.aabb.numpy()
+        out['ca_alpha_masked'] = m.compute_alpha(xyz, length=0.2).numpy()      # second call: through the alpha mask (:712-716)
+        rays = torch.from_numpy(blender_like_rays(600, seed + 2))
+        rgbs = torch.rand(600, 3, generator=g)
+        out['f_rays'], out['f_rgbs'] = rays.numpy().copy(), rgbs.numpy().copy()
+        r1, c1 = m.filtering_rays(rays.clone(), rgbs.clone(), N_samples=64, chunk=250)
+        out['f_kept_rays'], out['f_kept_rgbs'] = r1.numpy().copy(), c1.numpy().copy()
+        r2, c2 = m.filtering_rays(rays.clone(), rgbs.clone(), chunk=250, bbox_only=True)
+        out['f_kept_rays_bbox'] = r2.numpy().copy()
+        m.upsample_volume_grid([40, 36, 44])
+        out['up_stepSize'], out['up_nSamples'], out['up_gridSize'] = m.stepSize.numpy(), np.array(m.nSamples), m.gridSize.numpy()
+        m.shrink(new_aabb)
+        for k, v in facts(m).items():
+            out['shrunk.' + k] = v
+        out['shrunk.coeff_shape'] = np.array(m.coeffs[0].shape)
+        out['shrunk.coeff_const'] = np.array(float(m.coeffs[0].flatten()[0]))
+        out['shrunk.basis0'] = m.basises[0].detach().numpy()
+        out['shrunk.cfg_aabb'] = np.array(cfg.dataset.aabb)
+    np.savez_compressed(os.path.join(HERE, 'maintenance.npz'), **out)
+    print('maintenance: occupied', float(out['mask_volume'].mean()), 'kept', len(out['f_kept_rays']), 'of 600; bbox', len(out['f_kept_rays_bbox']),
+          'new aabb', out['new_aabb'].round(3).tolist(), flush=True)
+
+
 def sampler_case():
     """sample_point at the nerf.yaml scale (aabb +-1, 128^3 -> stepSize, 443 train samples): packed masks."""
     cfg, m = build('nerf.yaml', [[-1., -1., -1.], [1., 1., 1.]], {'model.total_params': 200000, 'model.coeff_reso': 8}, 3)
@@ -342,6 +409,8 @@ if __name__ == '__main__':
         unb = {**SMALL, 'dataset.is_unbound': True, 'renderer.fea2denseAct': 'relu'}   # configs/360_v2.yaml
         render_case('unbound_train', unb, CUBE, seed=29, mode='unbound', N_samples=90)
         render_case('unbound_eval_alpha', unb, CUBE, seed=31, mode='unbound', with_alpha=True, is_train=False, N_samples=90)
+    if not only or 'maintenance' in only:
+        maintenance_case()
     if not only or 'sampler' in only:
         sampler_case()
     if not only or 'mlp' in only:
