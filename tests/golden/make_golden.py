@@ -292,6 +292,50 @@ def maintenance_case():
           'new aabb', out['new_aabb'].round(3).tolist(), flush=True)
 
 
+def api_case():
+    """Free functions and small methods of the module surface: dct_dict, positional_encoding, raw2alpha,
+    basis2density, normalize_basis, get_optparam_groups, n_parameters, and the checkpoint layout written by save()."""
+    import tempfile
+    from models.FactorFields import dct_dict, positional_encoding, raw2alpha
+    out = {}
+    out['dct2'] = dct_dict(3, 12, n_selete=5, dim=2).numpy()
+    out['dct3'] = dct_dict(2, 7, n_selete=4, dim=3).numpy()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(20, 3, generator=g)
+    out['pe_x'], out['pe_y'] = x.numpy(), positional_encoding(x, 4).numpy()
+    sigma = torch.rand(7, 30, generator=g) * 3.0
+    dist = torch.rand(7, 30, generator=g) * 0.3
+    a, w, bg = raw2alpha(sigma, dist)
+    out['r2a_sigma'], out['r2a_dist'], out['r2a_alpha'], out['r2a_weight'], out['r2a_bg'] = sigma.numpy(), dist.numpy(), a.numpy(), w.numpy(), bg.numpy()
+    cfg, m = build('nerf.yaml', BOX, SMALL, 51)
+    f = torch.randn(50, generator=g) * 8 + 8
+    out['b2d_f'], out['b2d_softplus'] = f.numpy(), m.basis2density(f).numpy()
+    cfg.renderer.fea2denseAct = 'relu'
+    out['b2d_relu'] = m.basis2density(f).numpy()
+    cfg.renderer.fea2denseAct = 'softplus'
+    groups = m.get_optparam_groups(lr_small=0.001, lr_large=0.02)
+    out['groups'] = json.dumps([[gr['lr'], [list(p.shape) for p in gr['params']]] for gr in groups])
+    for n, p in m.named_parameters():
+        out['param.' + n] = p.detach().numpy().copy()
+    for k, v in facts(m).items():
+        out['fact.' + k] = v
+    out['cfgname'], out['overrides'], out['aabb_cfg'] = 'nerf.yaml', json.dumps(SMALL), np.array(BOX, np.float64)
+    vol = (torch.rand(14, 12, 16, generator=g) > 0.4).float()
+    m.alphaMask = AlphaGridMask('cpu', m.aabb, vol)
+    with tempfile.TemporaryDirectory() as td:
+        m.save(os.path.join(td, 'ck.th'))
+        ck = torch.load(os.path.join(td, 'ck.th'), weights_only=False)
+    out['ck_keys'] = json.dumps(sorted(ck.keys()))
+    out['ck_state_keys'] = json.dumps([[k, list(v.shape)] for k, v in ck['state_dict'].items()])
+    out['ck_mask'], out['ck_mask_shape'], out['ck_mask_aabb'] = ck['alphaMask.mask'], np.array(ck['alphaMask.shape']), ck['alphaMask.aabb'].numpy()
+    out['ck_volume'] = vol.numpy()
+    with torch.no_grad():
+        m.normalize_basis()
+    out['normalized_basis0'], out['normalized_basis5'] = m.basises[0].detach().numpy(), m.basises[5].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, 'api.npz'), **out)
+    print('api', out['ck_keys'], flush=True)
+
+
 def sampler_case():
     """sample_point at the nerf.yaml scale (aabb +-1, 128^3 -> stepSize, 443 train samples): packed masks."""
     cfg, m = build('nerf.yaml', [[-1., -1., -1.], [1., 1., 1.]], {'model.total_params': 200000, 'model.coeff_reso': 8}, 3)
@@ -411,6 +455,8 @@ if __name__ == '__main__':
         render_case('unbound_eval_alpha', unb, CUBE, seed=31, mode='unbound', with_alpha=True, is_train=False, N_samples=90)
     if not only or 'maintenance' in only:
         maintenance_case()
+    if not only or 'api' in only:
+        api_case()
     if not only or 'sampler' in only:
         sampler_case()
     if not only or 'mlp' in only:

@@ -142,3 +142,11 @@ extern "C" float mapc(float x, float lo, float scale, int mode) { return ffb::ma
         scale = np.float32(np.float32(2.5) / np.float32(3.1))
         got = np.array([lib.mapc(C.c_float(float(v)), C.c_float(-1.2), C.c_float(float(scale)), mode_id) for v in xs], np.float32)
         assert np.array_equal(got, ref), mode
+
+
+def test_dct_dict_matches_reference():
+    """Host-side DCT dictionary (FactorFields.py:36-71) that initialises every grid basis: equal to the reference's values."""
+    from ffb200.models.FactorFields import dct_dict
+    g = H.golden('api')
+    assert H.rel_err(dct_dict(3, 12, n_selete=5, dim=2).numpy(), g['dct2']) < 1e-6
+    assert H.rel_err(dct_dict(2, 7, n_selete=4, dim=3).numpy(), g['dct3']) < 1e-6
