@@ -330,10 +330,10 @@ def run_ours(args):
     # DRAM traffic of the same kernel per launch: from the committed `ncu --set full` capture (profiles/), never measured here
     traffic, traffic_src = None, None
     try:
-        cap = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_field_v2.json')))
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_field_v3.json')))
         for name, rec in cap.items():
             if ('bwd' in name) == (dom == 'field_bwd') and rec.get('traffic_bytes'):
-                traffic, traffic_src = int(rec['traffic_bytes']), 'profiles/r01_ncu_field_v2.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)'
+                traffic, traffic_src = int(rec['traffic_bytes']), 'profiles/r01_ncu_field_v3.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)'
     except Exception:
         pass
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 4),
