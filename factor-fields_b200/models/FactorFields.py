@@ -529,17 +529,18 @@ class FactorFields(torch.nn.Module):
         (:612); drawn from the CPU generator so that runs are reproducible against the reference's CPU path."""
         return torch.rand(1, n)[0] if is_train else None
 
-    def _z_table_ndc(self, N_samples, is_train):
-        """interpx of FactorFields.py:577-580: a handful of host-evaluated scalars shared by all rays."""
-        near, far = self.cfg.dataset.near_far
-        interpx = torch.linspace(near, far, N_samples).unsqueeze(0)
-        u = self._z_uniform(N_samples, is_train)
-        if u is not None:
-            interpx += u[None] * ((far - near) / N_samples)
-        return interpx[0].contiguous().to(self.device)
-
-    def _z_table_unbound(self, N_samples, is_train):
-        """interpx of FactorFields.py:607-623: 3/4 of the samples linear in [0,2], 1/4 in inverse depth out to 32."""
+    def _z_table_host(self, kind, N_samples, is_train):
+        """The interpx row shared by all rays, evaluated on the host like the reference's CPU tensors.
+        kind 'ndc' (FactorFields.py:577-580): linspace(near, far, N) + uniform * (far - near) / N when training.
+        kind 'unbound' (:607-623): 3/4 of the samples linear in [0,2], 1/4 in inverse depth out to 32; a uniform point
+        (training) or the midpoint (evaluation) of every bin."""
+        if kind == 'ndc':
+            near, far = self.cfg.dataset.near_far
+            interpx = torch.linspace(near, far, N_samples).unsqueeze(0)
+            u = self._z_uniform(N_samples, is_train)
+            if u is not None:
+                interpx += u[None] * ((far - near) / N_samples)
+            return interpx[0].contiguous()
         N_inner, N_outer = 3 * N_samples // 4, N_samples // 4
         b_inner = torch.linspace(0, 2, N_inner + 1)
         b_outer = 2 / torch.linspace(1, 1 / 16, N_outer + 1)
@@ -549,7 +550,21 @@ class FactorFields(torch.nn.Module):
                                  b_outer[1:] * rng[N_inner:] + b_outer[:-1] * (1 - rng[N_inner:])])
         else:
             interpx = torch.cat([(b_inner[1:] + b_inner[:-1]) * 0.5, (b_outer[1:] + b_outer[:-1]) * 0.5])
-        return interpx.contiguous().to(self.device)
+        return interpx.contiguous()
+
+    def _z_table(self, kind, N_samples, is_train):
+        """Device copy of the interpx row; a caller that replays a captured graph (train.TrainStep) parks a static buffer in
+        `_z_static` and refreshes it itself before every replay."""
+        static = getattr(self, '_z_static', None)
+        if static is not None:
+            return static
+        return self._z_table_host(kind, N_samples, is_train).to(self.device)
+
+    def _z_table_ndc(self, N_samples, is_train):
+        return self._z_table('ndc', N_samples, is_train)
+
+    def _z_table_unbound(self, N_samples, is_train):
+        return self._z_table('unbound', N_samples, is_train)
 
     def sample_point_ndc(self, rays_o, rays_d, is_train=True, N_samples=-1):
         """FactorFields.py:575-584 -> (rays_pts [R,S,3], interpx [1,S], ~mask_outbbox [R,S])"""

@@ -165,8 +165,11 @@ class TrainStep:
     CHUNK = 4096
 
     def __init__(self, model, param_groups, batch, n_samples, white_bg=True, betas=(0.9, 0.99), eps=1e-8, lr_decay=1.0,
-                 group=None, use_graph=True, warmup=2, nccl_in_graph=False):
+                 group=None, use_graph=True, warmup=2, nccl_in_graph=False, ndc_ray=False):
         self.model, self.B, self.S, self.white_bg = model, int(batch), int(n_samples), bool(white_bg)
+        # NDC (llff) / unbounded (360) scenes: the interpx row shared by all rays is a static device buffer refreshed per step
+        self.ndc_ray = bool(ndc_ray)
+        self.z_kind = 'unbound' if getattr(model, 'is_unbound', False) else ('ndc' if self.ndc_ray else None)
         self.betas, self.eps, self.lr_decay, self.group, self.use_graph = betas, eps, float(lr_decay), group, use_graph
         self.nccl_in_graph = nccl_in_graph
         self.groups = [{'params': [p for p in g['params']], 'lr': float(g['lr'])} for g in param_groups]
@@ -189,6 +192,9 @@ class TrainStep:
         self.rays_s = torch.zeros(self.B, 6, device=dev)
         self.target_s = torch.zeros(self.B, 3, device=dev)
         self.jitter_s = torch.zeros(self.B, device=dev)
+        self.z_s = None
+        if self.z_kind is not None:
+            self.z_s = model._z_table_host(self.z_kind, self.S, False).to(dev)
         self.loss_s = torch.zeros(1, device=dev)
         self.graph = None
         self._warmup = warmup
@@ -220,12 +226,14 @@ class TrainStep:
         _ops.set_grad_arena(self.arena)
         prev_jitter = m.__dict__.get('_jitter')
         m._jitter = lambda n, tr: self.jitter_s
+        m._z_static = self.z_s
         try:
-            rgb, depth, _ = m(self.rays_s, white_bg=self.white_bg, is_train=True, N_samples=self.S)
+            rgb, depth, _ = m(self.rays_s, white_bg=self.white_bg, is_train=True, ndc_ray=self.ndc_ray, N_samples=self.S)
             _, g_rgb = _ops.mse_fwd_bwd(rgb, self.target_s, loss=self.loss_s)
             grads = torch.autograd.grad([rgb], self.params, grad_outputs=[g_rgb], allow_unused=True)
         finally:
             _ops.set_grad_arena(None)
+            m._z_static = None
             if prev_jitter is None:
                 m.__dict__.pop('_jitter', None)
             else:
@@ -293,7 +301,10 @@ class TrainStep:
         if rays.shape[0] != self.B:
             raise RuntimeError(f'TrainStep was built for batches of {self.B} rays, got {rays.shape[0]}')
         self._check_params()
-        if jitter is None:
+        if self.z_kind is not None:      # per-SAMPLE uniforms (FactorFields.py:579,612) instead of the per-ray jitter
+            self.z_s.copy_(self.model._z_table_host(self.z_kind, self.S, True), non_blocking=True)
+            jitter = self.jitter_s
+        elif jitter is None:
             jitter = torch.rand(self.B, 1)[:, 0]
         self.rays_s.copy_(rays[:, :6], non_blocking=True)
         self.target_s.copy_(target, non_blocking=True)

@@ -151,3 +151,75 @@ def test_training_psnr_parity_with_reference_port():
     assert ref_test > 18.0, 'the scene was not learnt: the comparison would be vacuous'
     assert abs(ours_train - ref_train) < 0.1
     assert abs(res['psnr_test'] - ref_test) < 0.1
+
+
+@pytest.mark.parametrize('kind', ['ndc', 'unbound'])
+def test_train_step_ndc_and_unbounded_scenes(kind):
+    """The CUDA-graph step for llff-style NDC rays and 360-style unbounded scenes (FactorFields.py:847-857): the per-sample
+    interpx row lives in a static device buffer refreshed before each replay; same losses / parameters as the eager path."""
+    import ffb200
+    from ffb200.models.FactorFields import FactorFields
+    from ffb200.renderer import render_ray
+    from ffb200.train import TrainStep
+    from tests.golden.make_golden_rays import ndc_like_rays, inside_out_rays
+    torch.manual_seed(0)
+    ov = ['model.total_params=60000', 'model.coeff_reso=8']
+    if kind == 'ndc':
+        cfg = ffb200.load_cfg('nerf.yaml', ov + ['dataset.near_far=[0.0, 1.0]', 'dataset.ndc_ray=1'])
+        cfg.dataset.aabb = [[-1.5, -1.67, -1.0], [1.5, 1.67, 1.0]]
+    else:
+        cfg = ffb200.load_cfg('nerf.yaml', ov + ['dataset.is_unbound=true', 'renderer.fea2denseAct=relu'])
+        cfg.dataset.aabb = [[-1., -1., -1.], [1., 1., 1.]]
+    ma = FactorFields(cfg, 'cuda:0')
+    with torch.no_grad():
+        ma.linear_mat.backbone[0].weight.mul_(10.0)
+        ma.linear_mat.backbone[1].weight[0].normal_(0, 2.0)
+        ma.linear_mat.backbone[0].weight[63].zero_()
+        ma.linear_mat.backbone[0].bias[63] = 1.0
+        ma.linear_mat.backbone[1].weight[0, 63] = 12.0
+    mb = copy.deepcopy(ma)
+    mb._plans = {}
+    R, S, steps = 256, 64, 3
+    n_z = S if kind == 'ndc' else 3 * S // 4 + S // 4
+    rays = torch.from_numpy((ndc_like_rays if kind == 'ndc' else inside_out_rays)(R * steps, 3))
+    rng = np.random.RandomState(9)
+    target = torch.from_numpy(rng.rand(R * steps, 3).astype(np.float32))
+    uni = torch.from_numpy(rng.rand(steps, n_z).astype(np.float32))
+    opt = torch.optim.Adam(ma.get_optparam_groups(0.001, 0.02), betas=(0.9, 0.99))
+    losses_a = []
+    for i in range(steps):
+        sl = slice(i * R, (i + 1) * R)
+        ma._z_uniform = lambda n, tr, i=i: uni[i] if tr else None
+        rgb, depth, _ = render_ray(rays[sl], ma, chunk=R, N_samples=S, ndc_ray=(kind == 'ndc'), white_bg=True, is_train=True, device='cuda:0')
+        loss = torch.mean((rgb - target[sl].cuda()) ** 2)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses_a.append(float(loss.detach()))
+        if i == 0:
+            first_a = [p.detach().clone() for p in ma.parameters()]
+    ts = TrainStep(mb, mb.get_optparam_groups(0.001, 0.02), batch=R, n_samples=S, ndc_ray=(kind == 'ndc'))
+    losses_b = []
+    for i in range(steps):
+        sl = slice(i * R, (i + 1) * R)
+        mb._z_uniform = lambda n, tr, i=i: uni[i] if tr else None
+        losses_b.append(float(ts.step(rays[sl], target[sl]).item()))
+        if i == 0:
+            first_b = [p.detach().clone() for p in mb.parameters()]
+    assert int(mb.last_stats['n_app']) > 0, 'nothing shaded: the appearance MLP is not exercised'
+    assert abs(losses_b[0] - losses_a[0]) <= 2e-6 * losses_a[0]              # same weights, same rays, same interpx row
+    np.testing.assert_allclose(losses_b, losses_a, rtol=1e-4, atol=1e-7)     # later steps: Adam amplifies the atomics' summation order
+    # Grid texels that only far / contracted samples touch receive gradients within rounding noise of zero; Adam turns the SIGN of
+    # that noise into a +-lr step, so they differ between any two runs (atomics order).  Hence: MLP weights (dense gradients) must
+    # agree tightly; grid tensors must agree in the bulk and nowhere differ by more than the total lr spent.
+    # -> parameters are compared after the FIRST step (identical inputs on both sides); later steps through the losses only.
+    max_drift = 2 * 0.02
+    for (n, _), pa, pb in zip(ma.named_parameters(), first_a, first_b):
+        d = (pa - pb).abs().flatten()
+        tol = 2e-4 * max(1.0, float(pa.abs().max()))
+        if n.startswith(('coeffs', 'basises')):
+            # (measured: after one step 23 % of the coefficient texels of the unbounded scene sit +-lr apart between two runs of
+            # the SAME code path; from step 2 on that perturbs every gradient at the 1e-2 level — the losses still agree to 1e-4)
+            assert float(d.max()) <= max_drift, (n, float(d.max()))
+        else:
+            assert float((d > tol).float().mean()) < 5e-3, (n, float(d.max()))
