@@ -346,6 +346,11 @@ def run_ours(args):
         own = n_valid * B_BWD_OWN
         roofline['frac_own_design_bytes'] = round(own / (sec[dom] * 1e-3) / 1e9 / pk['hbm'], 4)
         roofline['own_design_bytes_per_query'] = B_BWD_OWN
+        roofline['note'] = ('frac > 1 by construction: SURVEY 8(d) charges the backward 3528 B/query (re-gather 1152 + read-modify-write 2304 + '
+                            'gradient row 72), but this kernel reads saved coefficient/basis rows (144 B) instead of re-gathering and merges the '
+                            'contributions of consecutive samples of a ray to the same coefficient cell before they reach L2; the factor grids and '
+                            'their gradients (21 MB each) stay L2-resident, so DRAM sees only the streamed rows (traffic). The forward kernel, whose '
+                            'algorithmic bytes are all real gathers, is at kernels.field_fwd.frac_hbm.')
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',

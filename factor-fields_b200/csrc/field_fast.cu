@@ -687,13 +687,14 @@ static int g_fwd_stage = 0; // 1: narrow rows leave through shared memory as coa
 static int g_bwd_cfg = 2;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)   2: 1 + run-aggregated coefficient scatter
 static int g_agg_levels = 0;   // leading 4-channel basis levels whose scatter is run-aggregated too (knob "field_bwd_agg_levels"): measured
                                // SLOWER at nerf.yaml (2 levels: 403 vs 342 us) — their runs are 2-5 samples, the extra staging pass costs more
+static int g_fwd_lpar_all = 0;  // experiment knob "field_fwd_lpar_all": level-parallel forward at every batch size
 static int g_lpar = 1;      // 1: batches of at most LPAR_MAX_ITEMS (query, level) pairs use the level-parallel kernels
 constexpr int64_t LPAR_MAX_ITEMS = 148 * 2048 * 3;   // ~3 full waves of resident threads; above that one thread per query wins
 
 template <int DB, int DC, bool NB, bool NC, int NT, int MINB>
 static void launch_fwd_cfg(const FastParams& P, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
                            cudaStream_t s) {
-  if (n * P.n_levels <= LPAR_MAX_ITEMS && g_lpar) {      // small batch: one thread per (query, level)
+  if (n * P.n_levels <= (g_fwd_lpar_all ? (int64_t)1 << 40 : LPAR_MAX_ITEMS) && g_lpar) {      // small batch: one thread per (query, level)
     fast_fwd_kernel<DB, DC, NB, NC, NT, MINB, false, true><<<blocks_for(n * P.n_levels, NT, (int64_t)sm_count() * 64), NT, 0, s>>>(
         P, x, n, n_dev, feats, coeff, basis);
     return;
@@ -771,6 +772,7 @@ int ffb_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "field_fwd_stage")) g_fwd_stage = value;
   else if (!strcmp(key, "field_level_parallel")) g_lpar = value;
   else if (!strcmp(key, "field_bwd_agg_levels")) g_agg_levels = value;
+  else if (!strcmp(key, "field_fwd_lpar_all")) g_fwd_lpar_all = value;
   else { set_error("ffb_set_tuning: unknown key %s", key); return FFB_EINVAL; }
   return FFB_OK;
 }
