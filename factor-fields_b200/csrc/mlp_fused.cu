@@ -191,7 +191,7 @@ struct RowLoader {
 // forward
 // ---------------------------------------------------------------------------------------------------------
 template <int TERMS, bool PREFETCH>
-__global__ void __launch_bounds__(256, 2) mlp2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ b1,
+__global__ void __launch_bounds__(256, 3) mlp2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ b1,
                                                           const float* __restrict__ W2, float* __restrict__ y, uint16_t* __restrict__ mask,
                                                           int64_t n, const int32_t* __restrict__ n_dev, const Mlp2Shape S, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -201,9 +201,10 @@ __global__ void __launch_bounds__(256, 2) mlp2_fwd_kernel(const float* __restric
   const uint32_t scW1 = (uint32_t)S.H * 16, scW2 = (uint32_t)S.Np * 16;
   uint8_t* sW1 = smem;
   uint8_t* sW2 = sW1 + TERMS * szW1;
+  // the hidden tile re-uses the x tile's bytes (x is dead once GEMM 1 has completed): 72 KB per CTA -> 3 CTAs per SM
   uint8_t* sX = sW2 + TERMS * szW2;
-  uint8_t* sH = sX + TERMS * szX;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sH + TERMS * szH);
+  uint8_t* sH = sX;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sX + TERMS * (szX > szH ? szX : szH));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
@@ -403,7 +404,23 @@ __global__ void __launch_bounds__(256, 2) mlp2_bwd_kernel(const float* __restric
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    if (gx) {
+    if (gx && (uint32_t)(128 * S.K0 * 4) > TERMS * szA2) {
+      // wide inputs (image presets): the staging below would not fit in the A2 region -> one row per lane, 8-byte stores
+      for (int c0 = half * 16; c0 < S.K0p; c0 += 32) {
+        float v[16];
+        tmem_ld16(d3 + lane_base + (uint32_t)c0, v);
+        if (row < n) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            if (c0 + i + 1 < S.K0 && (S.K0 & 1) == 0) *reinterpret_cast<float2*>(gx + row * S.K0 + c0 + i) = make_float2(v[i], v[i + 1]);
+            else {
+              if (c0 + i < S.K0) gx[row * S.K0 + c0 + i] = v[i];
+              if (c0 + i + 1 < S.K0) gx[row * S.K0 + c0 + i + 1] = v[i + 1];
+            }
+          }
+        }
+      }
+    } else if (gx) {
       // g_x tile -> fp32 staging in the (now idle) A2 region -> coalesced 16-byte stores: the tile's rows are contiguous in
       // global memory (128 x K0 floats), whereas one row per lane wrote 8-byte pieces 4 K0 bytes apart (7x sector amplification)
       float* stg = reinterpret_cast<float*>(sA2);
@@ -477,8 +494,12 @@ static bool mlp2_plan(int K0, int H, int N, Mlp2Shape* S, size_t* smem_fwd, size
   S->K0p = (K0 + 1 + 15) / 16 * 16;
   S->Np = (N + 15) / 16 * 16;
   if (S->K0p > 256 || S->Np > 256) return false;
+  // wide inputs (image presets, K0 = 144): the x tile alone is 3 x 40 KB -> one CTA per SM; measured slower than the
+  // per-layer tcgen05 kernels (image.yaml step 0.69 vs 0.63 ms), so those shapes stay on mlp_tc.cu
+  if (S->K0p > 64) return false;
   const size_t w = (size_t)H * S->K0p * 2 + (size_t)S->Np * H * 2;
-  *smem_fwd = 3 * (w + (size_t)128 * S->K0p * 2 + (size_t)128 * H * 2) + 64;
+  const size_t act = (size_t)128 * 2 * (S->K0p > H ? S->K0p : H);      // x tile and hidden tile share one region
+  *smem_fwd = 3 * (w + act) + 64;
   *smem_bwd = 2 * (w + (size_t)128 * S->K0p * 2 + (size_t)128 * S->Np * 2 + (size_t)2 * 128 * H * 2) + 64;
   if (S->Np + S->K0p > 256) return false;
   const int cf = H + S->Np, cb = 2 * H + 2 * S->K0p + S->Np;
