@@ -30,14 +30,14 @@ for c, st in ((0, 0), (1, 0), (1, 1), (2, 1), (3, 1)):
         f = lambda: nv.check(lib.ffb_field_query_fwd_train(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(feats), nv.ptr(coeff), nv.ptr(basis) if with_basis else None, nv.stream()))
         us = timeit(f)
         if ref is None: ref = feats.clone()
-        print(f'fwd cfg {c} stage {st} basis={with_basis}: {us:8.1f} us  frac {n*1236/us/1e3/6450.9:.3f}  maxdiff {float((feats-ref).abs().max()):.2e}', flush=True)
+        print(f'fwd cfg {c} stage {st} basis={with_basis}: {us:8.1f} us  frac {n*1236/us/1e3/6553.3:.3f}  maxdiff {float((feats-ref).abs().max()):.2e}', flush=True)
 lib.ffb_set_tuning(b'field_fwd_cfg', 1); lib.ffb_set_tuning(b'field_fwd_stage', 1)
 cb = (coeff.clone(), basis.clone())
 f(); torch.cuda.synchronize(); print('staged outputs equal direct:', bool((coeff == cb[0]).all() and (basis == cb[1]).all()), float((coeff-cb[0]).abs().max()))
 grads = [torch.zeros_like(t) for t in plan.tensors]
 arr = (C.c_void_p * nv.MAX_OPS)(*[gr.data_ptr() for gr in grads])
 gref = None
-for c, saved in ((0, False), (1, True)):
+for c, saved in ((0, False), (1, True), (2, True)):
     lib.ffb_set_tuning(b'field_bwd_cfg', c)
     f = lambda: nv.check(lib.ffb_field_query_bwd_saved(plan.handle, nv.ptr(x), C.c_int64(n), None, nv.ptr(g), None, nv.ptr(coeff) if saved else None, nv.ptr(basis) if saved else None, arr, nv.stream()))
     for gr in grads: gr.zero_()
@@ -46,4 +46,4 @@ for c, saved in ((0, False), (1, True)):
     if gref is None: gref = cur
     err = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(cur, gref))
     us = timeit(f)
-    print(f'bwd cfg {c}: {us:8.1f} us  frac {n*3528/us/1e3/6450.9:.3f}  rel err vs cfg0 {err:.2e}', flush=True)
+    print(f'bwd cfg {c}: {us:8.1f} us  frac {n*3528/us/1e3/6553.3:.3f}  rel err vs cfg0 {err:.2e}', flush=True)
