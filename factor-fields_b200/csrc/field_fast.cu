@@ -184,6 +184,12 @@ __device__ __forceinline__ void basis_taps(const FastParams& P, const FastLevel&
   make_tapset<DB, NEAR_B>(c, size, t);
 }
 
+// The saved basis row is private to the forward / backward kernel pair, so it is stored BLOCKED: element (query i, column c)
+// at (i / 32) * 32 W + c * 32 + i % 32.  A warp's 32 queries then write / read 128 contiguous bytes per column instead of 32
+// pieces 4 W bytes apart (one row per lane costs ~9x the LSU wavefronts; the row alone was 51 of the forward's 300 us).
+// Buffers hold ceil(n / 32) * 32 rows.
+__device__ __forceinline__ size_t blk_idx(int64_t i, int c, int W) { return (size_t)(i >> 5) * (size_t)(32 * W) + (size_t)c * 32 + (size_t)(i & 31); }
+
 __device__ __forceinline__ float fast_msize(const FastParams& P) {
   float m = FFB_SUB(P.hi[0], P.lo[0]);
   for (int k = 1; k < P.in_dim; ++k) m = fmaxf(m, FFB_SUB(P.hi[k], P.lo[k]));
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
       coeff_taps<DC, NEAR_C>(P, xr, tc);
       float* frow = feats ? feats + i * W : nullptr;
       float* crow = STAGE ? sC + lane * W : (coeff ? coeff + i * W : nullptr);
-      float* brow = STAGE ? sB + lane * W : (basis ? basis + i * W : nullptr);
+      float* brow = STAGE ? sB + lane * W : nullptr;      // STAGE: parked in shared memory; otherwise written blocked, below
       for (int l = l_begin; l < l_end; ++l) {
         const FastLevel L = P.lv[l];
         TapSet<DB, NEAR_B> tb;
@@ -251,6 +257,9 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
             if (brow) {
               *reinterpret_cast<float2*>(brow + o) = make_float2(b[0], b[1]);
               *reinterpret_cast<float2*>(brow + o + 2) = make_float2(b[2], b[3]);
+            } else if (basis) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) basis[blk_idx(i, o + j, W)] = b[j];
             }
           }
         } else {
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
             if (!STAGE && frow) *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
             if (crow) *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
             if (brow) *reinterpret_cast<float2*>(brow + o) = make_float2(b[0], b[1]);
+            else if (basis) { basis[blk_idx(i, o, W)] = b[0]; basis[blk_idx(i, o + 1, W)] = b[1]; }
           }
         }
       }
@@ -276,7 +286,11 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
       for (int t = lane; t < total; t += 32) {
         const float2 cv = c2[t], bv = b2[t];
         if (coeff) reinterpret_cast<float2*>(coeff)[base + t] = cv;
-        if (basis) reinterpret_cast<float2*>(basis)[base + t] = bv;
+        if (basis) {
+          const int rr = t / (W >> 1), cc = 2 * (t - rr * (W >> 1));
+          basis[blk_idx(k * 32 + rr, cc, W)] = bv.x;
+          basis[blk_idx(k * 32 + rr, cc + 1, W)] = bv.y;
+        }
         if (feats) reinterpret_cast<float2*>(feats)[base + t] = make_float2(bv.x * cv.x, bv.y * cv.y);
       }
       __syncwarp();
@@ -378,7 +392,6 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_kernel(const FastPara
     const float* gf = g_feats ? g_feats + i * P.W : nullptr;
     const float* gcf = g_coeff ? g_coeff + i * P.W : nullptr;
     const float* crow = coeff + i * P.W;
-    const float* brow = basis + i * P.W;
     TapSet<DC, NEAR_C> tc;
     if (G.c) coeff_taps<DC, NEAR_C>(P, xr, tc);
     if (AGGW > 0 && G.c) {
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_kernel(const FastPara
         gacc[c] = gacc[c + 1] = 0.0f;
         if (c < P.W) {
           const float2 g = gf ? *reinterpret_cast<const float2*>(gf + c) : make_float2(0.f, 0.f);
-          const float2 b = *reinterpret_cast<const float2*>(brow + c);
+          const float2 b = make_float2(basis[blk_idx(i, c, P.W)], basis[blk_idx(i, c + 1, P.W)]);
           gacc[c] = g.x * b.x;
           gacc[c + 1] = g.y * b.y;
           if (gcf) {
@@ -412,7 +425,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_kernel(const FastPara
         const float2 g = gf ? *reinterpret_cast<const float2*>(gf + o) : make_float2(0.f, 0.f);
         const float2 ca = *reinterpret_cast<const float2*>(crow + o);
         if (AGGW == 0 && G.c) {
-          const float2 b = *reinterpret_cast<const float2*>(brow + o);
+          const float2 b = make_float2(basis[blk_idx(i, o, P.W)], basis[blk_idx(i, o + 1, P.W)]);
           float gc[2] = {g.x * b.x, g.y * b.y};
           if (gcf) {
             const float2 g2 = *reinterpret_cast<const float2*>(gcf + o);
@@ -486,14 +499,13 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_agg_kernel(const Fast
       int flags = 0;
       if (active) {
         const float* gcf = g_coeff ? g_coeff + i * W : nullptr;
-        const float* brow = basis + i * W;
         coeff_taps<DC, false>(P, xr, tc);
 #pragma unroll
         for (int c = 0; c < AGG_G; c += 2) {
           float2 v = make_float2(0.f, 0.f);
           if (c < W) {
             const float2 g = gf ? *reinterpret_cast<const float2*>(gf + c) : make_float2(0.f, 0.f);
-            const float2 b = *reinterpret_cast<const float2*>(brow + c);
+            const float2 b = make_float2(basis[blk_idx(i, c, W)], basis[blk_idx(i, c + 1, W)]);
             v = make_float2(g.x * b.x, g.y * b.y);
             if (gcf) {
               const float2 g2 = *reinterpret_cast<const float2*>(gcf + c);

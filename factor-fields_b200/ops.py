@@ -163,7 +163,7 @@ class FieldQuery(torch.autograd.Function):
         coeff = _empty((n, plan.width), x)
         # training: also keep the basis row, so the backward pass scatters without re-gathering
         train = plan.fast and any(ctx.needs_input_grad[3:])
-        basis = _empty((n, plan.width), x) if train else None
+        basis = _empty(((n + 31) // 32 * 32, plan.width), x) if train else None     # private, blocked by 32 rows (field_fast.cu: blk_idx)
         if n > 0:
             with nv.section('field_fwd'):
                 if train:

@@ -106,7 +106,9 @@ int ffb_field_query_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t*
  * tensor), or NULL to use ops[i].grad of the descriptor.  g_coeff may be NULL. */
 int ffb_field_query_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
                         const float* g_feats, const float* g_coeff, float* const* h_grads, void* stream);
-/* Training pair: the forward also stores the concatenated basis row `basis` [n, W]; the backward then needs no
+/* Training pair: the forward also stores the concatenated basis row in `basis`, an OPAQUE buffer of
+ * ceil(n / 32) * 32 * W floats private to this pair (the specialised kernels block it by 32 queries so that a warp
+ * writes / reads 128 contiguous bytes per column); the backward then needs no
  * re-gather — it reads the saved `coeff` / `basis` rows, recomputes only the tap indices and weights, and issues the
  * scatter as 16-byte vector reductions.  Fields outside the specialised grid x grid kernels fall back to
  * ffb_field_query_bwd's behaviour (coeff / basis are then ignored). */

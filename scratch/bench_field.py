@@ -13,7 +13,8 @@ rays, target, jitter = W.make_rays(W.BATCH, seed=100)
 samp = ops.sample_compact(m._sampler_desc(W.N_SAMPLES, False), torch.from_numpy(rays).cuda(), torch.from_numpy(jitter).cuda())
 x = samp['xyz']; n = x.shape[0]
 plan = m._plan('coding'); lib = nv.lib()
-feats, coeff, basis = (torch.empty(n, 18, device='cuda') for _ in range(3))
+feats, coeff = (torch.empty(n, 18, device='cuda') for _ in range(2))
+basis = torch.empty((n + 31) // 32 * 32, 18, device='cuda')      # blocked by 32 rows
 g = torch.randn(n, 18, device='cuda')
 def timeit(fn, it=20):
     for _ in range(3): fn()
