@@ -173,6 +173,7 @@ class FieldQuery(torch.autograd.Function):
                     nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(n_dev), nv.ptr(feats), nv.ptr(coeff),
                                                           nv.stream()))
         ctx.plan, ctx.n_dev, ctx.train = plan, n_dev, train
+        ctx.set_materialize_grads(False)     # an unused output (the coefficient row in the render path) arrives as None, not as zeros
         if train:
             ctx.save_for_backward(x, coeff, basis)
         else:
@@ -185,6 +186,8 @@ class FieldQuery(torch.autograd.Function):
         x = ctx.saved_tensors[0]
         coeff, basis = (ctx.saved_tensors[1], ctx.saved_tensors[2]) if ctx.train else (None, None)
         n = x.shape[0]
+        if g_feats is None and g_coeff is None:
+            return (None, None, None, *[None] * len(plan.tensors))
         # one gradient tensor per distinct factor tensor (an op list may reference a tensor once only)
         grads = []
         arr = (C.c_void_p * nv.MAX_OPS)()
