@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(ffb_composite_desc D
       }
       const float after = suffix + (s - gww);   // sum over samples after i
       suffix += __shfl_sync(0xffffffffu, s, 0);
+      float g0 = 0.0f;
       if (act) {
         const float sg = sigma[i];
         const float delta = FFB_MUL(dist[i], D.distance_scale);
@@ -193,13 +194,20 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(ffb_composite_desc D
         const float fac = FFB_ADD(FFB_SUB(1.0f, FFB_SUB(1.0f, e)), 1e-10f);
         const float g_alpha = gw * trans[i] - after / fac;
         const float g_sigma = g_alpha * e * delta;
-        const float g0 = g_sigma * density_act_grad(D, feat0[i * ld_feat]);
-        if (zero_rest) {     // the whole gradient row: density column + zeros (the caller skips its memset of [Nv, ld_g])
-          float4* row = reinterpret_cast<float4*>(g_feat0 + i * ld_g);
-          row[0] = make_float4(g0, 0.f, 0.f, 0.f);
-          for (int q = 1; q < (ld_g >> 2); ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          g_feat0[i * ld_g] = g0;
+        g0 = g_sigma * density_act_grad(D, feat0[i * ld_feat]);
+        if (!zero_rest) g_feat0[i * ld_g] = g0;
+      }
+      if (zero_rest) {
+        // the whole gradient rows of this chunk: density column + zeros (the caller skips its memset of [Nv, ld_g]).  The chunk's
+        // rows are contiguous in memory, so the warp writes them as coalesced 16-byte pieces; piece t = row t / q4, quad t % q4.
+        const int q4 = ld_g >> 2;
+        const int64_t cbase = beg + ch * 32;
+        const int rows = (int)((end - cbase) < 32 ? (end - cbase) : 32);
+        float4* dst = reinterpret_cast<float4*>(g_feat0 + cbase * ld_g);
+        for (int t0 = 0; t0 < 32 * q4; t0 += 32) {
+          const int t = t0 + lane, r = t / q4, q = t - r * q4;
+          const float gr = __shfl_sync(0xffffffffu, g0, r & 31);
+          if (r < rows) dst[t] = make_float4(q == 0 ? gr : 0.f, 0.f, 0.f, 0.f);
         }
       }
     }
