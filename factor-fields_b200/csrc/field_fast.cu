@@ -199,10 +199,10 @@ __device__ __forceinline__ float fast_msize(const FastParams& P) {
 // NT threads per CTA, at least MINB CTAs resident per SM (caps the register count: the kernel is bound by the latency
 // of L2-resident gathers, so more resident warps = more loads in flight).  basis (optional): the concatenated basis
 // row, saved for the gather-free backward pass.
-// STAGE (experiment knob "field_fwd_stage", off by default — measured 6 % SLOWER on nerf.yaml: 315 vs 299 us): a warp
-// parks its 32 coefficient / basis rows in shared memory and streams the contiguous 32*W-float chunk out with
-// coalesced 8-byte stores, forming feats = coeff * basis on the way.  The warp-wide barrier costs more overlap than
-// the partially-written sectors of the direct per-lane row stores.
+// STAGE (knob "field_fwd_stage", on for W <= 32): a warp parks its 32 coefficient rows and its 32 feature rows in shared
+// memory and streams the two contiguous 32*W-float chunks out as coalesced 16-byte pieces (one row per lane writes 8-byte
+// pieces 4 W bytes apart: ~9x the LSU wavefronts).  A small win (278 -> 273 us) — an earlier version that streamed 8-byte
+// pieces and formed the product on the way out was 6 % slower than the direct stores.
 // LPAR (small batches: the regression drivers' 40-100 k points leave most of the 148 SMs without work at one thread per
 // query): one thread per (query, level) — consecutive lanes take the levels of one query, so a query's row segments are
 // still written by neighbouring lanes; the coefficient taps are recomputed per level (ALU only).
@@ -232,9 +232,10 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
       for (int d = 0; d < P.xdim; ++d) xr[d] = x[i * P.xdim + d];
       TapSet<DC, NEAR_C> tc;
       coeff_taps<DC, NEAR_C>(P, xr, tc);
-      float* frow = feats ? feats + i * W : nullptr;
+      // STAGE: the coefficient and feature rows are parked in shared memory (sC, sB) and leave as coalesced 16-byte pieces
+      float* frow = STAGE ? sB + lane * W : (feats ? feats + i * W : nullptr);
       float* crow = STAGE ? sC + lane * W : (coeff ? coeff + i * W : nullptr);
-      float* brow = STAGE ? sB + lane * W : nullptr;      // STAGE: parked in shared memory; otherwise written blocked, below
+      float* brow = nullptr;                              // the saved basis row is written blocked, below
       for (int l = l_begin; l < l_end; ++l) {
         const FastLevel L = P.lv[l];
         TapSet<DB, NEAR_B> tb;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
             gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
             gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0 + 2, tc, cb);
             const int o = L.col + c0;
-            if (!STAGE && frow) {
+            if (frow) {
               *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
               *reinterpret_cast<float2*>(frow + o + 2) = make_float2(b[2] * cb[0], b[3] * cb[1]);
             }
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
             gather_vec<DB, NEAR_B, 2>(L.data, L.C, c0, tb, b);
             gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
             const int o = L.col + c0;
-            if (!STAGE && frow) *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
+            if (frow) *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
             if (crow) *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
             if (brow) *reinterpret_cast<float2*>(brow + o) = make_float2(b[0], b[1]);
             else if (basis) { basis[blk_idx(i, o, W)] = b[0]; basis[blk_idx(i, o + 1, W)] = b[1]; }
@@ -279,19 +280,17 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
     if (STAGE) {
       __syncwarp();
       const int64_t rows = (n - k * 32) < 32 ? (n - k * 32) : 32;
-      const int total = (int)rows * (W >> 1);                 // float2 elements of the chunk
-      const int64_t base = k * 32 * (W >> 1);
-      const float2* c2 = reinterpret_cast<const float2*>(sC);
-      const float2* b2 = reinterpret_cast<const float2*>(sB);
+      const int total = (int)(rows * W) >> 2;                 // 16-byte pieces of the chunk (32 W floats: a multiple of 4)
+      const int64_t base = k * 8 * W;                         // = k * 32 * W / 4
+      const float4* c4 = reinterpret_cast<const float4*>(sC);
+      const float4* f4 = reinterpret_cast<const float4*>(sB);
       for (int t = lane; t < total; t += 32) {
-        const float2 cv = c2[t], bv = b2[t];
-        if (coeff) reinterpret_cast<float2*>(coeff)[base + t] = cv;
-        if (basis) {
-          const int rr = t / (W >> 1), cc = 2 * (t - rr * (W >> 1));
-          basis[blk_idx(k * 32 + rr, cc, W)] = bv.x;
-          basis[blk_idx(k * 32 + rr, cc + 1, W)] = bv.y;
-        }
-        if (feats) reinterpret_cast<float2*>(feats)[base + t] = make_float2(bv.x * cv.x, bv.y * cv.y);
+        if (coeff) reinterpret_cast<float4*>(coeff)[base + t] = c4[t];
+        if (feats) reinterpret_cast<float4*>(feats)[base + t] = f4[t];
+      }
+      for (int t = (total << 2) + lane; t < (int)(rows * W); t += 32) {     // tail of a partial last chunk
+        if (coeff) coeff[k * 32 * W + t] = sC[t];
+        if (feats) feats[k * 32 * W + t] = sB[t];
       }
       __syncwarp();
     }
@@ -695,7 +694,7 @@ using namespace ffb;
 
 // ---- launch configuration (tunable at run time for experiments; defaults are the measured best) -------------
 static int g_fwd_cfg = 1;   // 0: 128 threads, compiler-chosen registers   1: 128 x >=8 CTAs/SM   2: 128 x >=6   3: 256 x >=4
-static int g_fwd_stage = 0; // 1: narrow rows leave through shared memory as coalesced chunks
+static int g_fwd_stage = 1; // 1: narrow rows (W <= 32) leave through shared memory as coalesced 16-byte pieces (278 -> 273 us at nerf.yaml)
 static int g_bwd_cfg = 2;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)   2: 1 + run-aggregated coefficient scatter
 static int g_agg_levels = 0;   // leading 4-channel basis levels whose scatter is run-aggregated too (knob "field_bwd_agg_levels"): measured
                                // SLOWER at nerf.yaml (2 levels: 403 vs 342 us) — their runs are 2-5 samples, the extra staging pass costs more
