@@ -154,6 +154,13 @@ __device__ __forceinline__ void scatter_vec(float* __restrict__ grad, int C, int
     if (!t.row_ok[r]) continue;
     float* p = grad + (size_t)t.base[r] * C + c0;
     const float w0 = t.wrow[r] * t.wx0;
+    if (!NEAREST && NV == 2 && C == 2 && t.x0_ok && t.x1_ok && (t.base[r] & 1) == 0) {
+      // 2-channel texels: both x corners in one 16-byte reduction (-5 % on the scatter; the same merge on the forward's
+      // gathers made that kernel 15 % SLOWER — a divergent branch in its latency-bound inner loop — and is not used)
+      const float w1 = t.wrow[r] * t.wx1;
+      red_add_v4(p, g[0] * w0, g[1] * w0, g[0] * w1, g[1] * w1);
+      continue;
+    }
     if (NEAREST || t.wx0 != 0.0f) {
       if (NV == 4) red_add_v4(p, g[0] * w0, g[1] * w0, g[2] * w0, g[3] * w0);
       else red_add_v2(p, g[0] * w0, g[1] * w0);
