@@ -496,8 +496,15 @@ def reconstruction(cfg, model, allrays, allrgbs, white_bg=True, n_iters=None, te
     """Per-scene optimisation with the reference's schedule (train_per_scene.py:125-234).
 
     allrays [N,6] / allrgbs [N,3]: host tensors (the reference keeps them on the host, :146,151-152).  test: optional
-    (rays, rgbs) evaluated at the end.  Returns dict(psnr_train=[...per step], psnr_test=float|None, steps=int)."""
+    (rays, rgbs) evaluated at the end.  Returns dict(psnr_train=[...per step], psnr_test=float|None, steps=int).
+
+    Under torch.distributed (one process per GPU) the loop is data parallel with weak scaling: every rank holds the same
+    ray set and the same host random streams, each step draws ONE global batch of world * batch_size rays (+ their jitter)
+    and rank r trains on slice r of it; TrainStep all-reduces the gradient arena, the alpha-mask lattice is evaluated
+    sharded (getDenseAlpha), the final evaluation is sharded by ray.  The result equals a single process with batch size
+    world * batch_size."""
     from .utils import N_to_reso, SimpleSampler, cal_n_samples, mse2psnr
+    rank, world = _dist_world()
     t = cfg.training
     n_iters = int(n_iters if n_iters is not None else t.n_iters)
     decay_iters = t.lr_decay_iters if t.lr_decay_iters > 0 else t.n_iters
@@ -506,12 +513,15 @@ def reconstruction(cfg, model, allrays, allrgbs, white_bg=True, n_iters=None, te
     reso_list = torch.linspace(t.volume_resoInit, t.volume_resoFinal, len(upsamp_list)).ceil().long().tolist()
     reso_cur = N_to_reso(t.volume_resoInit ** model.in_dim, model.aabb)
     n_samples = min(cfg.renderer.max_samples, cal_n_samples(reso_cur, cfg.renderer.step_ratio))
-    sampler = SimpleSampler(allrays.shape[0], t.batch_size)
+    global_batch = t.batch_size * world
+    mine = shard_slice(global_batch, rank, world)
+    sampler = SimpleSampler(allrays.shape[0], global_batch)
     pinned = allrays.is_pinned()
+    ndc_ray = bool(getattr(cfg.dataset, 'ndc_ray', 0))
 
     def new_step(keep=None):
         ts = TrainStep(model, model.get_optparam_groups(t.lr_small, t.lr_large), batch=t.batch_size, n_samples=n_samples,
-                       white_bg=white_bg, betas=(0.9, 0.99), lr_decay=lr_factor, use_graph=use_graph)
+                       white_bg=white_bg, betas=(0.9, 0.99), lr_decay=lr_factor, use_graph=use_graph, ndc_ray=ndc_ray)
         if keep is not None:       # same parameters, new launch sequence (alpha mask changed): carry the optimiser over
             ts.m.copy_(keep.m); ts.v.copy_(keep.v); ts.lr_d.copy_(keep.lr_d); ts.step_d.copy_(keep.step_d)
         return ts
@@ -519,11 +529,17 @@ def reconstruction(cfg, model, allrays, allrgbs, white_bg=True, n_iters=None, te
     ts = new_step()
     psnrs, reso_mask = [], None
     for it in range(n_iters):
-        idx = sampler.nextids()
+        idx = sampler.nextids()[mine]
         rays_b, rgb_b = allrays[idx], allrgbs[idx]
         if pinned:
             rays_b, rgb_b = rays_b.pin_memory(), rgb_b.pin_memory()
-        loss = float(ts.step(rays_b, rgb_b).item())           # the reference reads the loss every step too (:164)
+        jitter = None if ts.z_kind is not None else torch.rand(global_batch, 1)[:, 0][mine]      # one uniform per ray (:593-595)
+        loss_d = ts.step(rays_b, rgb_b, jitter)
+        if world > 1:                                         # equal shards: the global MSE is the mean of the ranks' MSEs
+            loss_d = loss_d.clone()
+            torch.distributed.all_reduce(loss_d, op=torch.distributed.ReduceOp.SUM)
+            loss_d = loss_d / world
+        loss = float(loss_d.item())                           # the reference reads the loss every step too (:164)
         psnrs.append(mse2psnr(max(loss, 1e-12)))
         if log is not None and it % cfg.defaults.progress_refresh_rate == 0:
             log(f'Iteration {it:05d}: train_psnr = {psnrs[-1]:.2f} mse = {loss:.6f}')
@@ -538,7 +554,7 @@ def reconstruction(cfg, model, allrays, allrgbs, white_bg=True, n_iters=None, te
                 ts = new_step(keep=ts)
             if not cfg.dataset.ndc_ray and mask_list and it == mask_list[0] and not cfg.dataset.is_unbound:
                 allrays, allrgbs = model.filtering_rays(allrays, allrgbs)
-                sampler = SimpleSampler(allrgbs.shape[0], t.batch_size)
+                sampler = SimpleSampler(allrgbs.shape[0], global_batch)
         if it in upsamp_list:
             n_voxels = reso_list.pop(0)
             reso_cur = N_to_reso(n_voxels ** model.in_dim, model.aabb)
@@ -547,5 +563,13 @@ def reconstruction(cfg, model, allrays, allrgbs, white_bg=True, n_iters=None, te
             ts = new_step()
     out = dict(psnr_train=psnrs, psnr_test=None, steps=n_iters)
     if test is not None:
-        out['psnr_test'] = evaluate_psnr(model, test[0], test[1], white_bg=white_bg)
+        if world > 1:
+            lazy, model.lazy_counts = getattr(model, 'lazy_counts', False), False
+            try:
+                rgb_map, _ = render_sharded(test[0], model, chunk=8192, white_bg=white_bg, ndc_ray=ndc_ray)
+            finally:
+                model.lazy_counts = lazy
+            out['psnr_test'] = mse2psnr(max(float(torch.mean((rgb_map - test[1].to(rgb_map.device)) ** 2)), 1e-12))
+        else:
+            out['psnr_test'] = evaluate_psnr(model, test[0], test[1], white_bg=white_bg)
     return out
