@@ -43,7 +43,9 @@ __host__ __device__ inline bool rgb_shape(int Cf, int view_pe, int fea_pe, RgbSh
   S->K0 = 3 + Cf + 6 * view_pe + 2 * fea_pe * Cf;
   S->K0p = (S->K0 + 1 + 15) / 16 * 16;
   S->n1 = S->K0p / 16;
-  return S->K0p <= 208;      // activation tile: 3 parts x 128 x K0p x 2 B must leave room for the ring
+  // activation tile: 3 parts x 128 x K0p x 2 B must leave room for the ring (<= 208); the backward kernel produces g_x in a
+  // 128-column block plus a (K0p - 128)-column block, so narrower inputs stay on the per-layer kernels
+  return S->K0p > 128 && S->K0p <= 208;
 }
 __host__ __device__ inline size_t rgb_pack_fwd_bytes(const RgbShape& S) { return (size_t)(S.n1 + RGB_H / 16) * RGB_SLOT + 3 * RGB_W3_PART; }
 // backward operands (2 parts): W2^T slices [8][2][4096], W1^T rows 0..127 slices [8][2][4096], W1^T rows 128..K0p-1 slices [8][2][(K0p-128)*32]
