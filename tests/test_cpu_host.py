@@ -119,6 +119,11 @@ extern "C" void run(const float* rays, const float* jit, int R, int S, const flo
   }
 }
 extern "C" float mapc(float x, float lo, float scale, int mode) { return ffb::map_coord(x, lo, scale, mode, nullptr); }
+extern "C" void run_unbound(const float* rays, const float* zt, int R, int S, float bg, unsigned char* inner, float* pts) {
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s)
+      inner[r * S + s] = ffb::sample_pos_unbound(rays + r * 6, rays + r * 6 + 3, zt[s], bg, pts + (size_t)(r * S + s) * 3);
+}
 '''
     so = '/tmp/ffb_math_shim.so'
     subprocess.run(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-x', 'c++', '-', '-I', os.path.join(ROOT, 'factor-fields_b200', 'csrc'),
@@ -142,6 +147,17 @@ extern "C" float mapc(float x, float lo, float scale, int mode) { return ffb::ma
         scale = np.float32(np.float32(2.5) / np.float32(3.1))
         got = np.array([lib.mapc(C.c_float(float(v)), C.c_float(-1.2), C.c_float(float(scale)), mode_id) for v in xs], np.float32)
         assert np.array_equal(got, ref), mode
+    # unbounded scenes: inf-norm contraction (FactorFields.py:625-633) bit-exact vs the oracle, on the golden case's rays / interpx
+    gu = H.golden('render_unbound_train')
+    rays_u = np.ascontiguousarray(gu['rays'], np.float32)
+    zt = np.ascontiguousarray(gu['z'][0], np.float32)
+    Ru, Su = rays_u.shape[0], zt.shape[0]
+    inner_u = np.zeros((Ru, Su), np.uint8)
+    pts_u = np.zeros((Ru, Su, 3), np.float32)
+    lib.run_unbound(P(rays_u), P(zt), Ru, Su, C.c_float(float(gu['bg_len'])), P(inner_u), P(pts_u))
+    pts_ref, _, inner_ref = O.sample_point_unbound(float(gu['bg_len']), zt, rays_u[:, :3], rays_u[:, 3:])
+    assert np.array_equal(inner_u.astype(bool), inner_ref) and np.array_equal(pts_u, pts_ref)
+    assert np.array_equal(np.packbits(inner_ref), gu['inner_mask'])
 
 
 def test_dct_dict_matches_reference():
