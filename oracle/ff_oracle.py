@@ -706,6 +706,60 @@ class RenderOracle:
         return grads
 
 
+# --------------------------------------------------------------------------------------
+# Alpha-mask maintenance (:710-841)
+# --------------------------------------------------------------------------------------
+def compute_alpha(render, xyz, length=1.0):
+    """FactorFields.compute_alpha (:710-727) for a RenderOracle `render`: alpha = 1 - exp(-basis2density(linear_mat(feats)[..., 0])
+    * length) at the points that pass the alpha mask (`> 0`, :713), 0 elsewhere."""
+    xyz = _f(xyz)
+    keep = np.ones(xyz.shape[0], bool)
+    if render.alpha is not None:
+        keep = sample_alpha(render.alpha['volume'], render.alpha['aabb'], xyz) > f32(0)
+    sigma = np.zeros(xyz.shape[0], np.float32)
+    if keep.any():
+        feats, _ = render.field.get_coding(xyz[keep])
+        feat = mlp_forward(render.mlps['linear_mat'], feats)
+        sigma[keep] = render.basis2density(feat[:, 0])
+    return (f32(1) - np.exp(-(sigma * f32(length)).astype(np.float32))).astype(np.float32)
+
+
+def dense_lattice(aabb, gridSize):
+    """Voxel-centre lattice of getDenseAlpha (:733-745) -> dense_xyz [D,H,W,3] (already transposed like :746) and the step size."""
+    aabb = _f(aabb)
+    gs = np.asarray(gridSize, np.int64)
+    units = ((aabb[1] - aabb[0]) / (gs - 1).astype(np.float32)).astype(np.float32)
+    half = (f32(1.0) / (gs - 1).astype(np.float32) * f32(0.5)).astype(np.float32)
+    axes = [_linspace(half[k], f32(1) - half[k], int(gs[k])) for k in range(3)]
+    sx, sy, sz = np.meshgrid(*axes, indexing='ij')
+    samples = np.stack([sx, sy, sz], -1).astype(np.float32)
+    dense = (aabb[0] * (f32(1) - samples) + aabb[1] * samples).astype(np.float32)
+    return np.ascontiguousarray(dense.transpose(2, 1, 0, 3)), f32(np.mean(units, dtype=np.float32))
+
+
+def dense_alpha(render, aabb, gridSize):
+    """getDenseAlpha (:730-755) with times = 1 (no jitter): alpha [D,H,W] on the lattice, length = stepSize * distance_scale."""
+    dense, step = dense_lattice(aabb, gridSize)
+    length = f32(step * f32(render.r['distance_scale']))
+    out = np.stack([compute_alpha(render, dense[i].reshape(-1, 3), length).reshape(dense.shape[1], dense.shape[2]) for i in range(dense.shape[0])])
+    return out.astype(np.float32), dense
+
+
+def filter_rays_mask(render, rays, N_samples, bbox_only=False):
+    """filtering_rays (:811-841): which rays are kept.  bbox_only: slab test t_max > t_min; else: any of the N_samples
+    points (eval sampling, in-box or not) has alpha-mask value > 0 (:832-833)."""
+    rays = _f(rays)
+    o, d = rays[:, :3], rays[:, 3:6]
+    aabb = _f(render.r['aabb'])
+    if bbox_only:
+        vec = np.where(d == 0, f32(1e-6), d).astype(np.float32)
+        ra, rb = ((aabb[1] - o) / vec).astype(np.float32), ((aabb[0] - o) / vec).astype(np.float32)
+        return np.maximum(ra, rb).min(-1) > np.minimum(ra, rb).max(-1)
+    pts, _, _ = sample_point(aabb, render.r['stepSize'], o, d, N_samples, None)
+    a = sample_alpha(render.alpha['volume'], render.alpha['aabb'], pts.reshape(-1, 3)).reshape(pts.shape[:2])
+    return (a > f32(0)).any(-1)
+
+
 def mse_loss_and_grad(rgb_map, target):
     """train_per_scene.py:158: loss = mean((rgb_map - rgb_train)**2)"""
     d = (_f(rgb_map) - _f(target)).astype(np.float32)

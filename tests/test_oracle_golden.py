@@ -123,6 +123,40 @@ def test_render_forward_backward(name):
             assert H.rel_err(gb, g[f'grad.renderModule.mlp.{l}.bias']) < 2e-4
 
 
+def test_alpha_mask_maintenance():
+    """Oracle restatement of compute_alpha / getDenseAlpha (no jitter) / filtering_rays against the vectors recorded from the
+    reference (tests/golden/maintenance.npz)."""
+    g = H.golden('maintenance')
+    ro = _render_oracle(g)
+    assert H.rel_err(O.compute_alpha(ro, g['ca_xyz'], 0.2), g['ca_alpha']) < 2e-5
+    alpha, dense = O.dense_alpha(ro, g['fact.aabb'], [20, 18, 22])
+    assert np.allclose(dense.astype(np.float64).sum((0, 1, 2)), g['dense_xyz_sum'], rtol=1e-7)
+    assert H.rel_err(alpha, g['dense_alpha']) < 2e-5
+    ro.alpha = dict(volume=g['mask_volume'], aabb=g['mask_aabb'])
+    # alpha = 1 - exp(-x) carries the absolute rounding of exp() near 1 (an ulp of 1.0 = 6e-8), and every point the mask keeps
+    # here has a small alpha: absolute tolerance
+    assert np.abs(O.compute_alpha(ro, g['ca_xyz'], 0.2) - g['ca_alpha_masked']).max() < 3e-7
+    keep = O.filter_rays_mask(ro, g['f_rays'], 64)
+    assert np.array_equal(g['f_rays'][keep], g['f_kept_rays']) and np.array_equal(g['f_rgbs'][keep], g['f_kept_rgbs'])
+    keep_bbox = O.filter_rays_mask(ro, g['f_rays'], 64, bbox_only=True)
+    assert np.array_equal(g['f_rays'][keep_bbox], g['f_kept_rays_bbox'])
+    # update_renderParams after the upsample (:693-699)
+    step, n = O.update_render_params(g['fact.aabb'], g['up_gridSize'], 0.5)
+    assert step == np.float32(g['up_stepSize']) and n == int(g['up_nSamples'])
+
+
+def test_module_surface_functions():
+    """positional_encoding (:74-79), raw2alpha (:82-88) and basis2density (:639-643) of the oracle vs the reference's outputs."""
+    g = H.golden('api')
+    assert H.rel_err(O.positional_encoding(g['pe_x'], 4), g['pe_y']) < 1e-6
+    a, w, bg = O.raw2alpha(g['r2a_sigma'], g['r2a_dist'])
+    assert H.rel_err(a, g['r2a_alpha']) < 1e-6 and H.rel_err(w, g['r2a_weight']) < 1e-6 and H.rel_err(bg, g['r2a_bg']) < 1e-6
+    ro = O.RenderOracle(None, dict(density_shift=-10.0, fea2denseAct='softplus'), None)
+    assert H.rel_err(ro.basis2density(g['b2d_f']), g['b2d_softplus']) < 1e-6
+    ro.r['fea2denseAct'] = 'relu'
+    assert H.rel_err(ro.basis2density(g['b2d_f']), g['b2d_relu']) < 1e-6
+
+
 def test_torch_port():
     """oracle/torch_port.py (the CPU-baseline restatement with torch CPU operators) against the reference's golden
     render vectors: same masks, rgb, loss."""
