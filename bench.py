@@ -366,11 +366,38 @@ def run_ours(args):
             'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clk}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_leg()
+    if world == 1 and args.cuda_eager_baseline:
+        line['reference_cuda_eager'] = cuda_eager_leg()
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + '\n').encode())
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
+
+
+def cuda_eager_leg(steps=5):
+    """the reference's eager CUDA path on the same GPU is the kernel-level bar.  The pure-Python reference cannot
+    travel to the GPU box, so this runs oracle/torch_port.py — the reference's step restated with the same torch operators —
+    with device='cuda' on the full 4096-ray batch.  Opt-in (--cuda-eager-baseline); not yet measured (added after this round's
+    GPU budget was spent)."""
+    import torch
+    from oracle.torch_port import TorchPort
+    tp = TorchPort(W.make_state(0), W.AABB, W.FREQ_BANDS, W.step_size(), W.RCFG, device='cuda')
+    rays, target, jitter = W.make_rays(W.BATCH * (steps + 2), seed=1)
+    rays, target, jitter = (torch.from_numpy(a).cuda() for a in (rays, target, jitter))
+    sl = lambda i: slice(i * W.BATCH, (i + 1) * W.BATCH)
+    for i in range(2):
+        tp.train_step(rays[sl(i)], target[sl(i)], W.N_SAMPLES, jitter[sl(i)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(2, steps + 2):
+        tp.train_step(rays[sl(i)], target[sl(i)], W.N_SAMPLES, jitter[sl(i)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': W.BATCH / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'kind': 'port on CUDA (torch eager operators, fp32)',
+            'sample': f'{W.BATCH} rays x {steps} steps, device-resident inputs, loss read back every step like train_per_scene.py:164'}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -690,6 +717,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cuda-eager-baseline', action='store_true', help='also time the reference step restated with torch eager operators on the GPU')
     ap.add_argument('--eager', action='store_true', help='Python-driven launches instead of the CUDA-graph TrainStep')
     ap.add_argument('--exact-counts', action='store_true', help='read the sample counts back every step (the reference-like sync mode)')
     args = ap.parse_args()

@@ -20,7 +20,7 @@ def grid_mapping_sawtooth(x, freq_bands, aabb):                          # Facto
 
 
 def positional_encoding(p, freqs):                                         # :74-79
-    fb = (2 ** torch.arange(freqs).float())
+    fb = (2 ** torch.arange(freqs, device=p.device).float())
     pts = (p[..., None] * fb).reshape(p.shape[:-1] + (freqs * p.shape[-1],))
     return torch.cat([torch.sin(pts), torch.cos(pts)], dim=-1)
 
@@ -28,11 +28,14 @@ def positional_encoding(p, freqs):                                         # :74
 class TorchPort:
     """state: dict of numpy arrays with the reference's state_dict names (reference layout)."""
 
-    def __init__(self, state, aabb, freq_bands, step_size, rcfg, lr_small=0.001, lr_large=0.02):
-        self.p = {k: torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(v)).float()) for k, v in state.items()}
-        self.aabb = torch.tensor(aabb, dtype=torch.float32)
-        self.freq = torch.tensor(freq_bands, dtype=torch.float32)
-        self.step = torch.tensor(step_size, dtype=torch.float32)
+    def __init__(self, state, aabb, freq_bands, step_size, rcfg, lr_small=0.001, lr_large=0.02, device='cpu'):
+        """device='cuda' runs the same operators as the reference's eager CUDA path (bench.py --cuda-eager-baseline);
+        the pinned / default configuration is the CPU."""
+        self.dev = torch.device(device)
+        self.p = {k: torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(v)).float().to(self.dev)) for k, v in state.items()}
+        self.aabb = torch.tensor(aabb, dtype=torch.float32, device=self.dev)
+        self.freq = torch.tensor(freq_bands, dtype=torch.float32, device=self.dev)
+        self.step = torch.tensor(step_size, dtype=torch.float32, device=self.dev)
         self.r = rcfg
         self.n_basis = len([k for k in state if k.startswith('basises.')])
         small = [v for k, v in self.p.items() if k.startswith(('linear_mat', 'renderModule'))]
@@ -64,7 +67,7 @@ class TorchPort:
         o, d = rays[:, :3], rays[:, 3:6]
         vec = torch.where(d == 0, torch.full_like(d, 1e-6), d)
         t_min = torch.minimum((self.aabb[1] - o) / vec, (self.aabb[0] - o) / vec).amax(-1).clamp(min=0.05, max=1e3)
-        rng = torch.arange(n_samples)[None].float()
+        rng = torch.arange(n_samples, device=self.dev)[None].float()
         if jitter is not None:
             rng = rng.repeat(o.shape[0], 1) + jitter[:, None]
         z = t_min[..., None] + self.step * rng
@@ -72,8 +75,8 @@ class TorchPort:
         valid = ~((self.aabb[0] > pts) | (pts > self.aabb[1])).any(dim=-1)
         dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), dim=-1)
         viewdirs = d.view(-1, 1, 3).expand(pts.shape)
-        sigma = torch.zeros(pts.shape[:-1])
-        rgb = torch.zeros((*pts.shape[:2], 3))
+        sigma = torch.zeros(pts.shape[:-1], device=self.dev)
+        rgb = torch.zeros((*pts.shape[:2], 3), device=self.dev)
         if valid.any():
             feats, _ = self.get_coding(pts[valid])
             feat = self.linear_mat(feats)
@@ -99,7 +102,7 @@ class TorchPort:
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()
-        return float(loss)
+        return float(loss.detach())
 
 
 class RegressPort:
