@@ -80,63 +80,87 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
+def _ref_stepper(device):
+    """-> (step(rays_host, target_host, jitter_host), kind, stats()).  The UNMODIFIED reference (baseline/_ref/factor-fields, copied
+    from /root/reference by __graft_entry__.build(); it travels to the GPU box with the working tree) through its own
+    FactorFields + render_ray + torch.optim.Adam when the checkout is present, else the operator-level port
+    (oracle/torch_port.py, kind "port")."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_step
+    if ref_step.available():
+        rs = ref_step.RefStep(W.make_state(0), W.AABB, device, W.N_SAMPLES)
+        assert rs.model.nSamples == 440 and float(rs.model.stepSize) == float(W.step_size())
+
+        def step(rays, target, jitter):
+            # the reference draws its own per-ray jitter from the torch CPU generator (FactorFields.py:593-595)
+            return rs.train_step(rays, target.to(device))
+        return step, 'reference', lambda: rs.stats
+    from oracle.torch_port import TorchPort
+    tp = TorchPort(W.make_state(0), W.AABB, W.FREQ_BANDS, W.step_size(), W.RCFG, device=device)
+
+    def step(rays, target, jitter):
+        return tp.train_step(rays.to(device), target.to(device), W.N_SAMPLES, jitter.to(device))
+    return step, 'port', lambda: tp.stats
+
+
+REF_NOTE = ('ATen grid_sample parallelises over the batch axis, which the reference fixes at 1, so its dominant CPU op is effectively '
+            'single-threaded whatever the core count')
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path, restated with the same torch CPU operators
-    (oracle/torch_port.py; the pure-Python reference cannot travel to the GPU box).  Rank 0 only."""
+    """The reference's own CPU implementation of the path on the host cores: the unmodified checkout when it travelled
+    (kind "reference"), else the operator-level port.  Rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     import torch
-    from oracle.torch_port import TorchPort
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     torch.manual_seed(20211202)
-    tp = TorchPort(W.make_state(0), W.AABB, W.FREQ_BANDS, W.step_size(), W.RCFG)
+    step, kind, stats = _ref_stepper('cpu')
     rays, target, jitter = W.make_rays(W.BATCH * 2, seed=1)
     rays, target, jitter = torch.from_numpy(rays), torch.from_numpy(target), torch.from_numpy(jitter)
     # bounded sample: size the per-step ray count so the whole run stays within a few minutes
     t0 = time.perf_counter()
-    tp.train_step(rays[:128], target[:128], W.N_SAMPLES, jitter[:128])
+    step(rays[:128], target[:128], jitter[:128])
     probe = time.perf_counter() - t0
-    budget = 150.0
+    budget = 240.0
     n = int(min(W.BATCH, max(128, 128 * budget / max(probe, 1e-3) / max(args.steps + args.warmup, 1))))
     n = max(128, (n // 128) * 128)
     for i in range(args.warmup):
         s = (i * n) % (rays.shape[0] - n)
-        tp.train_step(rays[s:s + n], target[s:s + n], W.N_SAMPLES, jitter[s:s + n])
+        step(rays[s:s + n], target[s:s + n], jitter[s:s + n])
     t0 = time.perf_counter()
     for i in range(args.steps):
         s = ((i + args.warmup) * n) % (rays.shape[0] - n)
-        tp.train_step(rays[s:s + n], target[s:s + n], W.N_SAMPLES, jitter[s:s + n])
+        step(rays[s:s + n], target[s:s + n], jitter[s:s + n])
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     sample = f'{n} of {W.BATCH} rays per step x {args.steps} steps (rays/s is per-ray, so the sample size does not bias it)'
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'rays_per_step': n},
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
-                             'note': 'torch CPU operators as the reference calls them; ATen grid_sample parallelises over the batch '
-                                     'axis, which the reference fixes at 1, so its dominant op is effectively single-threaded',
-                             'stats': tp.stats},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample, 'note': REF_NOTE, 'stats': stats()},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_leg(n=256, steps=2):
     import torch
-    from oracle.torch_port import TorchPort
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    tp = TorchPort(W.make_state(0), W.AABB, W.FREQ_BANDS, W.step_size(), W.RCFG)
+    step, kind, _ = _ref_stepper('cpu')
     rays, target, jitter = W.make_rays(n * (steps + 1), seed=1)
     rays, target, jitter = torch.from_numpy(rays), torch.from_numpy(target), torch.from_numpy(jitter)
-    tp.train_step(rays[:n], target[:n], W.N_SAMPLES, jitter[:n])
+    step(rays[:n], target[:n], jitter[:n])
     t0 = time.perf_counter()
     for i in range(1, steps + 1):
-        tp.train_step(rays[i * n:(i + 1) * n], target[i * n:(i + 1) * n], W.N_SAMPLES, jitter[i * n:(i + 1) * n])
+        step(rays[i * n:(i + 1) * n], target[i * n:(i + 1) * n], jitter[i * n:(i + 1) * n])
     dt = time.perf_counter() - t0
-    return {'value': n * steps / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'{n} rays x {steps} steps of the same workload (oracle/torch_port.py, torch CPU, {cores} threads)'}
+    what = 'the unmodified reference checkout, FactorFields + render_ray + torch.optim.Adam' if kind == 'reference' else 'oracle/torch_port.py'
+    return {'value': n * steps / dt, 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': f'{n} rays x {steps} steps of the same workload ({what}, torch CPU, {cores} threads)', 'note': REF_NOTE}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -366,8 +390,9 @@ def run_ours(args):
             'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clk}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_leg()
-    if world == 1 and args.cuda_eager_baseline:
+    if world == 1 and not args.no_cuda_eager_baseline:
         line['reference_cuda_eager'] = cuda_eager_leg()
+        line['vs_reference_cuda_eager'] = round(e2e / line['reference_cuda_eager']['value'], 2)
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + '\n').encode())
     faulthandler.cancel_dump_traceback_later()
@@ -376,28 +401,28 @@ def run_ours(args):
 
 
 def cuda_eager_leg(steps=5):
-    """the reference's eager CUDA path on the same GPU is the kernel-level bar.  The pure-Python reference cannot
-    travel to the GPU box, so this runs oracle/torch_port.py — the reference's step restated with the same torch operators —
-    with device='cuda' on the full 4096-ray batch.  Opt-in (--cuda-eager-baseline); not yet measured (added after this round's
-    GPU budget was spent)."""
+    """the reference's eager CUDA path on the same GPU is the kernel-level bar.  Runs the unmodified reference
+    (else the operator-level port) with device='cuda' on the full 4096-ray batch: host rays in (render_ray copies them, as in
+    train_per_scene.py:151-156), loss read back every step (:164)."""
     import torch
-    from oracle.torch_port import TorchPort
-    tp = TorchPort(W.make_state(0), W.AABB, W.FREQ_BANDS, W.step_size(), W.RCFG, device='cuda')
+    step, kind, stats = _ref_stepper('cuda')
     rays, target, jitter = W.make_rays(W.BATCH * (steps + 2), seed=1)
-    rays, target, jitter = (torch.from_numpy(a).cuda() for a in (rays, target, jitter))
+    rays, target, jitter = (torch.from_numpy(a) for a in (rays, target, jitter))
     sl = lambda i: slice(i * W.BATCH, (i + 1) * W.BATCH)
     for i in range(2):
-        tp.train_step(rays[sl(i)], target[sl(i)], W.N_SAMPLES, jitter[sl(i)])
+        step(rays[sl(i)], target[sl(i)], jitter[sl(i)])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(2, steps + 2):
-        tp.train_step(rays[sl(i)], target[sl(i)], W.N_SAMPLES, jitter[sl(i)])
+        step(rays[sl(i)], target[sl(i)], jitter[sl(i)])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {'value': W.BATCH / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'kind': 'port on CUDA (torch eager operators, fp32)',
-            'sample': f'{W.BATCH} rays x {steps} steps, device-resident inputs, loss read back every step like train_per_scene.py:164'}
+    return {'value': W.BATCH / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+            'kind': kind + ' on CUDA (torch eager operators, fp32, TF32 off as in the reference)',
+            'sample': f'{W.BATCH} rays x {steps} steps, host rays in, loss read back every step like train_per_scene.py:164',
+            'stats': stats()}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -717,7 +742,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cuda-eager-baseline', action='store_true', help='also time the reference step restated with torch eager operators on the GPU')
+    ap.add_argument('--no-cuda-eager-baseline', action='store_true', help='skip timing the reference (eager torch CUDA operators) on the same GPU')
     ap.add_argument('--eager', action='store_true', help='Python-driven launches instead of the CUDA-graph TrainStep')
     ap.add_argument('--exact-counts', action='store_true', help='read the sample counts back every step (the reference-like sync mode)')
     args = ap.parse_args()

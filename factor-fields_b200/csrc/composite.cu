@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) composite_accum_kernel(ffb_composite_desc
       float c[3] = {c0s, c1s, c2s};
       for (int k = 0; k < 3; ++k) {
         float v = c[k];
-        if (D.white_bg) v = v + (1.0f - acc);
+        if (D.white_bg_dev ? (*D.white_bg_dev != 0) : (D.white_bg != 0)) v = v + (1.0f - acc);
         if (pre_clamp) pre_clamp[r * 3 + k] = v;
         rgb_map[r * 3 + k] = fminf(fmaxf(v, 0.0f), 1.0f);
       }
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(ffb_composite_desc D
       const float pc = pre_clamp[r * 3 + k];
       g[k] = (pc >= 0.0f && pc <= 1.0f) ? g_rgb_map[r * 3 + k] : 0.0f;   // clamp(0,1) backward
     }
-    const float gsum = D.white_bg ? (g[0] + g[1] + g[2]) : 0.0f;
+    const float gsum = (D.white_bg_dev ? (*D.white_bg_dev != 0) : (D.white_bg != 0)) ? (g[0] + g[1] + g[2]) : 0.0f;
     int64_t aend = app_offsets[r + 1];   // one past the last shaded sample of this ray
     float suffix = 0.0f;                 // sum_{k > chunk} g_w_k * w_k
     const int64_t nchunks = (end - beg + 31) / 32;

@@ -9,8 +9,22 @@
 namespace ffb {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
-int sm_count();
+int sm_count();             // of the current device (cached per device)
+int smem_optin_bytes();     // cudaDevAttrMaxSharedMemoryPerBlockOptin of the current device (cached per device)
+int current_device();
 void keep_pool_cached();
+
+// Function attributes (cudaFuncSetAttribute) are per device: `static PerDeviceOnce once; if (once.first()) { ... }`
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    const int d = current_device();
+    if (d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return FFB_OK;

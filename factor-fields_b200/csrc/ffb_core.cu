@@ -14,14 +14,29 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
+static int cached_attr(int (&cache)[64], cudaDeviceAttr attr, int fallback) {
+  const int dev = current_device();
+  if (dev < 0) return fallback;
+  if (dev < 64 && cache[dev]) return cache[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, attr, dev) != cudaSuccess || v <= 0) return fallback;
+  if (dev < 64) cache[dev] = v;
+  return v;
+}
+
 int sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
-  return n;
+  static int cache[64] = {};
+  return cached_attr(cache, cudaDevAttrMultiProcessorCount, 148);
+}
+
+int smem_optin_bytes() {
+  static int cache[64] = {};
+  return cached_attr(cache, cudaDevAttrMaxSharedMemoryPerBlockOptin, 48 * 1024);
 }
 // Stream-ordered allocations (generic field backward, grid_mapping) come from the device's default memory pool; keep
 // freed blocks cached across synchronisation points instead of returning them to the driver (default threshold 0),

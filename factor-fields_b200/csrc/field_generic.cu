@@ -283,7 +283,11 @@ __global__ void __launch_bounds__(128) field_generic_bwd(const ffb_field_desc* _
   }
 }
 
-__global__ void grid_mapping_kernel(const float* __restrict__ x, int64_t n, int in_dim, float3 lo, float msize, const float* __restrict__ freq,
+struct FreqTable {
+  float f[FFB_MAX_FREQ];     // by value in the kernel parameters: no allocation, no host->device copy, capturable in a CUDA graph
+};
+
+__global__ void grid_mapping_kernel(const float* __restrict__ x, int64_t n, int in_dim, float3 lo, float msize, const FreqTable freq,
                                     int F, int mapping, float* __restrict__ out) {
   const int per = in_dim * F;
   const float los[3] = {lo.x, lo.y, lo.z};
@@ -292,7 +296,7 @@ __global__ void grid_mapping_kernel(const float* __restrict__ x, int64_t n, int 
     int r = (int)(t % per);
     int d = r / F, f = r % F;
     float cs;
-    float v = map_coord(x[i * in_dim + d], los[d], FFB_DIV(msize, freq[f]), mapping, &cs);
+    float v = map_coord(x[i * in_dim + d], los[d], FFB_DIV(msize, freq.f[f]), mapping, &cs);
     if (mapping == FFB_MAP_TRIG) {
       out[(i * in_dim + d) * 2 * F + f] = v;
       out[(i * in_dim + d) * 2 * F + F + f] = cs;
@@ -413,15 +417,12 @@ int ffb_grid_mapping(const float* x, int64_t n, int32_t in_dim, const float* h_a
   cudaStream_t s = (cudaStream_t)stream;
   float msize = h_aabb_max[0] - h_aabb_min[0];
   for (int k = 1; k < in_dim; ++k) msize = fmaxf(msize, h_aabb_max[k] - h_aabb_min[k]);
-  float* dfreq = nullptr;
-  keep_pool_cached();
-  FFB_CUDA(cudaMallocAsync(&dfreq, sizeof(float) * n_freq, s));
-  FFB_CUDA(cudaMemcpyAsync(dfreq, h_freq, sizeof(float) * n_freq, cudaMemcpyHostToDevice, s));
+  FreqTable dfreq;
+  for (int i = 0; i < FFB_MAX_FREQ; ++i) dfreq.f[i] = i < n_freq ? h_freq[i] : 1.0f;
   float3 lo = make_float3(h_aabb_min[0], in_dim > 1 ? h_aabb_min[1] : 0.f, in_dim > 2 ? h_aabb_min[2] : 0.f);
   grid_mapping_kernel<<<blocks_for(n * in_dim * n_freq, 256, sm_count() * 16), 256, 0, s>>>(x, n, in_dim, lo, msize, dfreq, n_freq,
                                                                                          mapping, out);
   FFB_LAUNCHED();
-  FFB_CUDA(cudaFreeAsync(dfreq, s));
   return FFB_OK;
 }
 

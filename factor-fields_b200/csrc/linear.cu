@@ -440,10 +440,9 @@ int ffb_linear_fwd_ex(const float* x, const float* W, const float* b, float* y, 
   cudaStream_t s = (cudaStream_t)stream;
   if (skinny) {
     const size_t smem = (size_t)(8 * K + 256 * 33) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.first()) {
       FFB_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_done = true;
     }
     gemm_skinny_kernel<8><<<blocks_for(n, 256), 256, smem, s>>>(x, W, b, act, y, n, n_dev, K, M);
   } else {

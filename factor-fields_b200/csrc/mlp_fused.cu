@@ -474,15 +474,7 @@ __global__ void __launch_bounds__(256, 2) mlp2_bwd_kernel(const float* __restric
 
 static int fused_enabled = 1;
 
-static int smem_optin() {
-  static int v = 0;
-  if (!v) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  }
-  return v;
-}
+static int smem_optin() { return smem_optin_bytes(); }
 static int pow2_cols32(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -546,11 +538,10 @@ int ffb_mlp2_fwd(const float* x, const float* W1, const float* b1, const float* 
   int cf, cb;
   FFB_REQUIRE(mlp2_plan(K0, H, N, &S, &sf, &sb, &cf, &cb), "MLP shape not eligible for the fused tensor-core path");
   if (n <= 0) return FFB_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.first()) {
     FFB_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin()));
     FFB_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin()));
-    attr_done = true;
   }
   if (S.K0p <= 32)
     mlp2_fwd_kernel<3, true><<<persistent_grid(n, sf, cf), 256, sf, (cudaStream_t)stream>>>(x, W1, b1, W2, y, relu_mask, n, n_dev, S, cf);
@@ -568,10 +559,9 @@ int ffb_mlp2_bwd(const float* x, const float* gy, const float* W1, const float* 
   int cf, cb;
   FFB_REQUIRE(mlp2_plan(K0, H, N, &S, &sf, &sb, &cf, &cb), "MLP shape not eligible for the fused tensor-core path");
   if (n <= 0) return FFB_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.first()) {
     FFB_CUDA(cudaFuncSetAttribute(mlp2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin()));
-    attr_done = true;
   }
   mlp2_bwd_kernel<<<persistent_grid(n, sb, cb), 256, sb, (cudaStream_t)stream>>>(x, gy, W1, b1, W2, relu_mask, gx, gW1, gb1, gW2, n, n_dev, S, cb);
   FFB_LAUNCHED();

@@ -781,15 +781,7 @@ static size_t rgb_bwd_smem() {
   return (size_t)2 * RGB_G_PART + 2 * 4096 + 4096 + 3 * RGB_H * 4 + (size_t)RGB_B_NSLOT * RGB_B_SLOT + (2 * RGB_B_NSLOT + 2) * 8 + 16;
 }
 
-static int rgb_smem_optin() {
-  static int v = 0;
-  if (!v) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  }
-  return v;
-}
+static int rgb_smem_optin() { return smem_optin_bytes(); }
 static size_t rgb_fwd_smem(const RgbShape& S) {
   return (size_t)3 * 128 * S.K0p * 2 + (size_t)RGB_NSLOT * RGB_SLOT + 3 * RGB_W3_PART + (2 * RGB_NSLOT + 3) * 8 + 16;
 }
@@ -842,10 +834,9 @@ int ffb_rgbmlp_fwd(const float* feat, int32_t ld_feat, const float* rays, const 
   FFB_REQUIRE((!stream_x && !stream_h1 && !stream_h2) || (stream_x && stream_h1 && stream_h2), "pass all three activation streams or none");
   const size_t smem = rgb_fwd_smem(a.S);
   FFB_REQUIRE(smem <= (size_t)rgb_smem_optin(), "not enough shared memory for the fused appearance MLP");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.first()) {
     FFB_CUDA(cudaFuncSetAttribute(rgb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rgb_smem_optin()));
-    attr_done = true;
   }
   const int64_t tiles = (n + 127) / 128;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
@@ -876,10 +867,9 @@ int ffb_rgbmlp_bwd(const float* g_rgb, const float* rgb, const uint16_t* relu_bi
   a.wpack = (const uint8_t*)workspace + rgb_pack_fwd_bytes(a.S); a.W3 = W3; a.g_x = g_x; a.ld_gx = ld_gx;
   a.gW1 = gW1; a.gb1 = gb1; a.gW2 = gW2; a.gb2 = gb2; a.gW3 = gW3; a.n = n; a.n_dev = n_dev;
   const size_t smem = rgb_bwd_smem();
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.first()) {
     FFB_CUDA(cudaFuncSetAttribute(rgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rgb_smem_optin()));
-    attr_done = true;
   }
   const int64_t tiles = (n + 127) / 128;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());

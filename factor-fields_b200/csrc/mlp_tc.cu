@@ -375,15 +375,7 @@ static int pow2_cols(int n) {
   while (c < n) c <<= 1;
   return c;
 }
-static int max_smem_optin() {
-  static int v = 0;
-  if (!v) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  }
-  return v;
-}
+static int max_smem_optin() { return smem_optin_bytes(); }
 
 }  // namespace ffb
 
@@ -440,11 +432,10 @@ static int tc_gemm_launch(int terms, const float* A, const float* Y, int act_in,
   const int64_t tiles = (n + 127) / 128;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > tiles) grid = tiles;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.first()) {
     FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
     FFB_CUDA(cudaFuncSetAttribute(tc_gemm_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
-    attr_done = true;
   }
   if (terms == 3) {
     tc_gemm_rows_kernel<3><<<(unsigned)grid, NT, smem, s>>>(A, Y, act_in, Bp, sbj, sbk, bias, act_out, C, n, n_dev, K, N, Kp, Np, KC, CB, szU, cols);
@@ -496,10 +487,9 @@ int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const
   const int Np = (K + 1 + 15) / 16 * 16;
   const size_t smem = (size_t)2 * 128 * 256 + (size_t)2 * Np * 256 + 64;
   const int cols = pow2_cols(Np);
-  static bool wattr_done = false;
-  if (!wattr_done) {
+  static PerDeviceOnce wattr_done;
+  if (wattr_done.first()) {
     FFB_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
-    wattr_done = true;
   }
   int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
   if (per_sm > 512 / cols) per_sm = 512 / cols;

@@ -56,6 +56,7 @@ def dct_dict(n_atoms_fre, size, n_selete, dim=2):
     return torch.FloatTensor(atoms)
 
 
+@nv.on_device_of(0)
 def positional_encoding(positions, freqs):
     """FactorFields.py:74-79 (device kernel: ffb_pe_concat_fwd without the identity part)."""
     shp = positions.shape
@@ -68,6 +69,7 @@ def positional_encoding(positions, freqs):
 
 
 @torch.no_grad()
+@nv.on_device_of(0)
 def raw2alpha(sigma, dist):
     """FactorFields.py:82-88 on dense [rays, samples] inputs -> (alpha, weights, T[..., -1:]); no autograd (forward()
     differentiates through ops.RenderComposite instead).  Runs the composite kernel with every sample marked valid."""
@@ -102,6 +104,7 @@ class AlphaGridMask(torch.nn.Module):
         if not bool(((self.alpha_volume == 0) | (self.alpha_volume == 1)).all()):
             raise RuntimeError('AlphaGridMask expects a 0/1 volume')
 
+    @nv.on_device_of(1)
     def sample_alpha(self, xyz_sampled):
         xyz = xyz_sampled.reshape(-1, 3).contiguous().float()
         desc = ops.make_sampler_desc(self.aabb, 0.0, 1, alpha=self)
@@ -589,9 +592,9 @@ class FactorFields(torch.nn.Module):
         invaabbSize = 2.0 / (self.aabb[1] - self.aabb[0])
         return (xyz_sampled - self.aabb[0]) * invaabbSize - 1
 
-    def _cdesc(self, white_bg=True):
+    def _cdesc(self, white_bg=True, white_bg_dev=None):
         r = self.cfg.renderer
-        return ops.make_composite_desc(r.density_shift, r.fea2denseAct, r.distance_scale, r.rayMarch_weight_thres, white_bg)
+        return ops.make_composite_desc(r.density_shift, r.fea2denseAct, r.distance_scale, r.rayMarch_weight_thres, white_bg, white_bg_dev)
 
     def basis2density(self, density_features):
         """FactorFields.py:639-643"""
@@ -796,10 +799,11 @@ class FactorFields(torch.nn.Module):
             samp = ops.sample_compact(self._sampler_desc(N_samples, with_alpha), rays, jitter, lazy=lazy)
         self.last_stats = {'n_valid': samp['n_valid'], 'n_candidates': rays.shape[0] * N_samples}
 
-        if not (white_bg or (is_train and torch.rand((1,)) < 0.5)):
-            white_bg = False
-        else:
-            white_bg = True
+        # :890 `white_bg or (is_train and torch.rand((1,)) < 0.5)`.  A caller that replays a captured graph (train.TrainStep)
+        # parks a device flag in `_white_bg_static` and refreshes it per step, so the coin flip is not frozen at capture.
+        bg_dev = getattr(self, '_white_bg_static', None)
+        if bg_dev is None:
+            white_bg = bool(white_bg or (is_train and torch.rand((1,)) < 0.5))
         width = sum(self.cfg.model.basis_dims)
         if lazy or samp['n_valid'] > 0:
             feats, coeffs = self.get_coding(samp['xyz'], samp['n_dev'])
@@ -809,7 +813,7 @@ class FactorFields(torch.nn.Module):
             feat = torch.zeros((0, self.cfg.model.out_dim), device=rays.device)
         params, has_bias = self.renderModule._flat()
         rgb_map, depth_map, acc, weight, app_idx, n_app = ops.RenderComposite.apply(
-            feat, samp, self._cdesc(white_bg), self.renderModule.viewpe, self.renderModule.feape, has_bias, *params)
+            feat, samp, self._cdesc(white_bg, bg_dev), self.renderModule.viewpe, self.renderModule.feape, has_bias, *params)
         self.last_stats['n_app'] = n_app if lazy else int(n_app)
         self.last_aux = dict(samp=samp, weight=weight, app_idx=app_idx, acc=acc)
         return rgb_map, depth_map, coeffs

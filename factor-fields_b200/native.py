@@ -46,7 +46,7 @@ class SamplerDesc(C.Structure):
 
 
 class CompositeDesc(C.Structure):
-    _fields_ = [('density_shift', f32), ('softplus', i32), ('distance_scale', f32), ('weight_thres', f32), ('white_bg', i32)]
+    _fields_ = [('density_shift', f32), ('softplus', i32), ('distance_scale', f32), ('weight_thres', f32), ('white_bg', i32), ('white_bg_dev', C.c_void_p)]
 
 
 def sources():
@@ -118,6 +118,24 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def on_device_of(argpos):
+    """Decorator for the op entry points: run with the CUDA device of positional argument `argpos` (a tensor) current, so
+    that `FactorFields(cfg, 'cuda:1')` works without a global torch.cuda.set_device(1) — the library launches on the
+    current device and `stream()` is that device's current stream."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(*a, **k):
+            t = a[argpos]
+            if torch.is_tensor(t) and t.is_cuda and t.device.index != torch.cuda.current_device():
+                with torch.cuda.device(t.device):
+                    return fn(*a, **k)
+            return fn(*a, **k)
+        return wrapper
+    return deco
+
+
 def ptr(t, dtype=torch.float32, allow_none=False, contiguous=True):
     if t is None:
         if allow_none:
@@ -129,6 +147,9 @@ def ptr(t, dtype=torch.float32, allow_none=False, contiguous=True):
         raise RuntimeError(f'ffb200: expected dtype {dtype}, got {t.dtype}')
     if contiguous and not t.is_contiguous():
         raise RuntimeError('ffb200: tensor must be contiguous')
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f'ffb200: tensor lives on {t.device} but the current CUDA device is {torch.cuda.current_device()}: every '
+                           'tensor of a call must share one device (kernels launch on the current device and its current stream)')
     return C.c_void_p(t.data_ptr())
 
 

@@ -154,6 +154,7 @@ class FieldQuery(torch.autograd.Function):
     factor tensors (the reference never needs d/dx)."""
 
     @staticmethod
+    @nv.on_device_of(2)
     def forward(ctx, plan, x, n_dev, *tensors):
         """n_dev: None, or a 1-element int32 CUDA tensor holding the live row count (x is then a capacity-sized buffer)."""
         _dev_check(x)
@@ -209,6 +210,7 @@ class FieldQuery(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+@nv.on_device_of(0)
 def grid_mapping(positions, freq_bands, aabb, basis_mapping='sawtooth'):
     """FactorFields.py:11-33.  positions [..., d] -> [..., d, F] ([..., d, 2F] for 'trigonometric')."""
     _dev_check(positions)
@@ -292,6 +294,7 @@ class MLPFunction(torch.autograd.Function):
     """MLPMixer.forward (FactorFields.py:144-159): optional PE concat, Linear+ReLU ..., bias-free last layer."""
 
     @staticmethod
+    @nv.on_device_of(1)
     def forward(ctx, x, pe, has_bias, n_dev, *params):
         _dev_check(x)
         x = x.contiguous().float()
@@ -417,6 +420,7 @@ def make_sampler_desc(aabb, step_size, n_samples, alpha=None, alpha_thres=0.5, m
     return d
 
 
+@nv.on_device_of(0)
 def exclusive_scan(counts):
     R = counts.shape[0]
     out = _empty((R + 1,), counts, torch.int32)
@@ -425,6 +429,7 @@ def exclusive_scan(counts):
 
 
 @torch.no_grad()
+@nv.on_device_of(1)
 def sample_compact(desc, rays, jitter, lazy=False):
     """-> dict(xyz [Nv,3], ray_id, sample_id, z, dist, offsets [R+1], n_valid, n_dev).
     lazy=False: one host read of Nv, exact-size buffers (n_dev None).  lazy=True: no host round trip; buffers have the
@@ -459,6 +464,7 @@ def sample_compact(desc, rays, jitter, lazy=False):
 
 
 @torch.no_grad()
+@nv.on_device_of(1)
 def sample_dense(desc, rays, jitter, want_z=True, want_pts=False):
     _dev_check(rays)
     rays = rays.contiguous().float()
@@ -476,8 +482,12 @@ def sample_dense(desc, rays, jitter, want_z=True, want_pts=False):
 # --------------------------------------------------------------------------------------------------
 # Composite + appearance MLP
 # --------------------------------------------------------------------------------------------------
-def make_composite_desc(density_shift, fea2denseAct, distance_scale, weight_thres, white_bg):
+def make_composite_desc(density_shift, fea2denseAct, distance_scale, weight_thres, white_bg, white_bg_dev=None):
+    """white_bg_dev: optional 1-element int32 CUDA tensor that overrides `white_bg` on the device (the descriptor keeps a
+    reference so the buffer outlives the launches)."""
     d = nv.CompositeDesc()
+    d._keep = white_bg_dev
+    d.white_bg_dev = nv.i32p(white_bg_dev).value if white_bg_dev is not None else None
     d.density_shift = float(density_shift)
     d.softplus = 1 if fea2denseAct == 'softplus' else 0
     d.distance_scale = float(distance_scale)
@@ -491,6 +501,7 @@ class RenderComposite(torch.autograd.Function):
     activation, raw2alpha, weight-threshold compaction, MLPRender_Fea on the shaded samples, accumulation."""
 
     @staticmethod
+    @nv.on_device_of(1)
     def forward(ctx, feat, samp, cdesc, view_pe, fea_pe, has_bias, *params):
         lib = nv.lib()
         feat = feat.contiguous()
@@ -498,10 +509,13 @@ class RenderComposite(torch.autograd.Function):
         rays, offsets = samp['rays'], samp['offsets']
         R = rays.shape[0]
         if Nv == 0:   # every ray misses the box / the alpha mask: background only (FactorFields.py:887-893 with weight == 0)
-            bg = 1.0 if cdesc.white_bg else 0.0
+            if cdesc.white_bg_dev:
+                rgb0 = (cdesc._keep != 0).to(torch.float32).expand(R, 3).contiguous()
+            else:
+                rgb0 = torch.full((R, 3), 1.0 if cdesc.white_bg else 0.0, device=feat.device)
             ctx.Na, ctx.empty, ctx.has_bias = 0, True, has_bias
             ctx.save_for_backward(feat, *params)
-            outs = (torch.full((R, 3), bg, device=feat.device), torch.zeros(R, device=feat.device), torch.zeros(R, device=feat.device),
+            outs = (rgb0, torch.zeros(R, device=feat.device), torch.zeros(R, device=feat.device),
                     _empty((0,), feat), _empty((0,), feat, torch.int32), torch.tensor(0))
             ctx.mark_non_differentiable(*outs[1:])
             return outs
@@ -644,6 +658,7 @@ class RenderMLP(torch.autograd.Function):
     """MLPRender_Fea.forward (FactorFields.py:188-203) for callers that use the module directly."""
 
     @staticmethod
+    @nv.on_device_of(1)
     def forward(ctx, viewdirs, features, view_pe, fea_pe, has_bias, *params):
         _dev_check(features)
         lib = nv.lib()
@@ -694,6 +709,7 @@ class RenderMLP(torch.autograd.Function):
 
 
 @torch.no_grad()
+@nv.on_device_of(1)
 def density_alpha(cdesc, feat, length):
     n, ld = feat.shape
     out = _empty((n,), feat)
@@ -704,6 +720,7 @@ def density_alpha(cdesc, feat, length):
 
 
 @torch.no_grad()
+@nv.on_device_of(0)
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     """In-place fused Adam on the raw storage (any memory format, as long as p/g/m/v share it)."""
     n = p.numel()
@@ -713,6 +730,7 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
 
 
 @torch.no_grad()
+@nv.on_device_of(0)
 def adam_hyper_advance(lr_d, step_d, hyper_d, beta1, beta2, lr_decay):
     """lr_d [G] float64, step_d [1] int64, hyper_d [G,2] float32 — all on the device."""
     nv.check(nv.lib().ffb_adam_hyper_advance(nv.ptr(lr_d, torch.float64), nv.ptr(step_d, torch.int64), nv.ptr(hyper_d), lr_d.numel(),
@@ -720,6 +738,7 @@ def adam_hyper_advance(lr_d, step_d, hyper_d, beta1, beta2, lr_decay):
 
 
 @torch.no_grad()
+@nv.on_device_of(0)
 def adam_multi(table, chunk_tensor, chunk_start, chunk, hyper_d, beta1, beta2, eps, grad_scale=1.0):
     nv.check(nv.lib().ffb_adam_multi(nv.ptr(table, torch.int64), nv.ptr(chunk_tensor, torch.int32), nv.ptr(chunk_start, torch.int64),
                                      chunk_tensor.numel(), int(chunk), nv.ptr(hyper_d), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
@@ -727,12 +746,14 @@ def adam_multi(table, chunk_tensor, chunk_start, chunk, hyper_d, beta1, beta2, e
 
 
 @torch.no_grad()
+@nv.on_device_of(0)
 def scalar_decay(value_d, factor, out_f32=None):
     """value_d [1] float64 (device) *= factor; out_f32 [1] float32 receives the rounded copy."""
     nv.check(nv.lib().ffb_scalar_decay(nv.ptr(value_d, torch.float64), C.c_double(factor), nv.ptr(out_f32, allow_none=True), nv.stream()))
 
 
 @torch.no_grad()
+@nv.on_device_of(0)
 def mse_fwd_bwd(pred, target, g_scale=1.0, loss=None, g_scale_dev=None):
     """-> (loss [1] device tensor, g_pred); g_scale_dev: optional device float32 scalar multiplied into g_pred."""
     pred, target = pred.contiguous(), target.contiguous()

@@ -172,14 +172,14 @@ class TrainStep:
         self.z_kind = 'unbound' if getattr(model, 'is_unbound', False) else ('ndc' if self.ndc_ray else None)
         self.betas, self.eps, self.lr_decay, self.group, self.use_graph = betas, eps, float(lr_decay), group, use_graph
         self.nccl_in_graph = nccl_in_graph
-        self.groups = [{'params': [p for p in g['params']], 'lr': float(g['lr'])} for g in param_groups]
+        # frozen parameters (set_optimizable) stay out of the step, like torch.optim.Adam skips parameters without a gradient
+        self.groups = [{'params': [p for p in g['params'] if p.requires_grad], 'lr': float(g['lr'])} for g in param_groups]
         self.params = [p for g in self.groups for p in g['params']]
         dev = self.params[0].device
         self.dev = dev
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(group)
-        model.lazy_counts = True
         # gradient arena + optimiser state
         self.bucket = GradBucket(self.params)
         self.m = torch.zeros_like(self.bucket.flat)
@@ -196,6 +196,9 @@ class TrainStep:
         if self.z_kind is not None:
             self.z_s = model._z_table_host(self.z_kind, self.S, False).to(dev)
         self.loss_s = torch.zeros(1, device=dev)
+        # white-background decision as a device flag: for non-white-background scenes the reference flips a coin every step
+        # (FactorFields.py:890); a captured graph must read it at replay time, not freeze the value seen at capture
+        self.bg_s = torch.full((1,), int(self.white_bg), dtype=torch.int32, device=dev)
         self.graph = None
         self._warmup = warmup
 
@@ -227,6 +230,9 @@ class TrainStep:
         prev_jitter = m.__dict__.get('_jitter')
         m._jitter = lambda n, tr: self.jitter_s
         m._z_static = self.z_s
+        m._white_bg_static = self.bg_s
+        prev_lazy = m.__dict__.get('lazy_counts', False)
+        m.lazy_counts = True          # device-side sample counts, scoped to this step: direct model(rays) calls stay exact-sized
         try:
             rgb, depth, _ = m(self.rays_s, white_bg=self.white_bg, is_train=True, ndc_ray=self.ndc_ray, N_samples=self.S)
             _, g_rgb = _ops.mse_fwd_bwd(rgb, self.target_s, loss=self.loss_s)
@@ -234,6 +240,8 @@ class TrainStep:
         finally:
             _ops.set_grad_arena(None)
             m._z_static = None
+            m._white_bg_static = None
+            m.lazy_counts = prev_lazy
             if prev_jitter is None:
                 m.__dict__.pop('_jitter', None)
             else:
@@ -294,10 +302,11 @@ class TrainStep:
                 self._optimise()
             self.graph = (ga, gb)
 
-    def step(self, rays, target, jitter=None):
+    def step(self, rays, target, jitter=None, bg_coin=None):
         """rays [B,6], target [B,3]: host (ideally pinned) or device fp32 tensors; jitter [B] (default: torch.rand on the
         CPU generator, one draw per ray, as FactorFields.py:593-595).  Returns the loss as a 1-element DEVICE tensor
-        (valid until the next step); call .item() to read it back."""
+        (valid until the next step); call .item() to read it back.  bg_coin: for white_bg=False scenes, the step's
+        random-background decision (default: `torch.rand((1,)) < 0.5` on the CPU generator, FactorFields.py:890)."""
         if rays.shape[0] != self.B:
             raise RuntimeError(f'TrainStep was built for batches of {self.B} rays, got {rays.shape[0]}')
         self._check_params()
@@ -309,6 +318,8 @@ class TrainStep:
         self.rays_s.copy_(rays[:, :6], non_blocking=True)
         self.target_s.copy_(target, non_blocking=True)
         self.jitter_s.copy_(jitter, non_blocking=True)
+        if not self.white_bg:       # the per-step coin of FactorFields.py:890, drawn after the jitter like the reference does
+            self.bg_s.fill_(int(bool(torch.rand((1,)) < 0.5)) if bg_coin is None else int(bool(bg_coin)))
         if self.graph is None:      # capture warms up on THIS batch (an all-zero ray buffer would aim every scatter at one texel)
             self._capture()
         if not self.graph:
@@ -358,7 +369,6 @@ class RegressStep(TrainStep):
                          use_graph=use_graph, warmup=warmup)
         local = {p.data_ptr() for p in local_params}
         self._shared_ranges = arena_ranges(self.bucket, [p.data_ptr() not in local for p in self.params])
-        model.lazy_counts = False
         self.is_train, self.loss_scale_decay = bool(is_train), float(loss_scale_decay)
         self.rays_s = torch.zeros(self.B, int(x_dim), device=self.dev)         # coordinates
         self.target_s = torch.zeros(self.B, int(out_dim), device=self.dev)

@@ -136,6 +136,11 @@ int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int
                              const float* basis, float* const* h_grads, void* stream);
 /* Experiment knobs (launch configurations of the field kernels): "field_fwd_cfg", "field_bwd_cfg". */
 int ffb_set_tuning(const char* key, int value);
+/* Measurement probe (bench.py): issues blocks*256*iters `red.global.add.v4.f32` into buf[0..n_floats) — the instruction
+ * the scatter kernels are made of — so that the backward pass can be reported against a MEASURED L2-reduction
+ * throughput instead of the HBM roofline.  pattern 0: random 16-byte slots; 1: 512 contiguous bytes per warp. */
+int ffb_probe_red(float* buf, int64_t n_floats, int32_t blocks, int32_t iters, int32_t pattern,
+                  int64_t* n_ops_out, void* stream);
 /* The descriptor-driven generic kernels, callable directly (parity tests compare both paths).
  * basis_out: optional [n, W] copy of the (re-ordered) basis row. */
 int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,
@@ -308,7 +313,10 @@ typedef struct ffb_composite_desc {
   int32_t softplus;             /* 1: softplus, 0: relu (fea2denseAct) */
   float distance_scale;
   float weight_thres;           /* rayMarch_weight_thres */
-  int32_t white_bg;
+  int32_t white_bg;             /* 1: rgb_map += 1 - acc (FactorFields.py:890-891) */
+  const int32_t* white_bg_dev;  /* optional DEVICE flag that overrides white_bg when non-null: the per-step coin flip of
+                                   non-white-background scenes (:890 `is_train and torch.rand((1,)) < 0.5`) stays a
+                                   run-time value inside a captured CUDA graph */
 } ffb_composite_desc;
 
 /* Phase A, per ray: sigma, alpha, T, weight for each valid sample; app_counts[r] = #(weight>thres).

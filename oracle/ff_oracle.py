@@ -443,9 +443,9 @@ class FieldOracle:
         b = self.get_basis(x)
         return b, b
 
-    def get_coding_bwd(self, x, g_feats):
-        """Gradient of sum(feats * g_feats) w.r.t. the factor tensors (grid / vec / cp / vm types).
-        -> dict(coeffs=[...], basises=[...]) in the reference layout."""
+    def get_coding_bwd(self, x, g_feats, g_coeff=None):
+        """Gradient of sum(feats * g_feats) (+ sum(coeff * g_coeff): get_coding's second output, FactorFields.py:527) w.r.t.
+        the factor tensors (grid / vec / cp / vm types).  -> dict(coeffs=[...], basises=[...]) in the reference layout."""
         ct, bt = self.s['coeff_type'], self.s['basis_type']
         g_feats = _f(g_feats)
         grads = {'coeffs': [None] * len(self.p.get('coeffs', [])),
@@ -456,6 +456,8 @@ class FieldOracle:
         b = self.get_basis(x) if have_b else None
         gc = (g_feats * b).astype(np.float32) if (have_c and have_b) else g_feats
         gb = (g_feats * c).astype(np.float32) if (have_c and have_b) else g_feats
+        if g_coeff is not None and have_c and have_b:
+            gc = (gc + _f(g_coeff)).astype(np.float32)
         if have_c and 'mlp' in ct:
             i = self.s['scene_idx']
             _, cache = mlp_forward(self.p['coeffs'][i], self.normalize_coord(x), pe=4, want_cache=True)

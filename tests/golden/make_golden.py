@@ -125,7 +125,9 @@ def blender_like_rays(R, seed, radius=4.0 / 1.5):
 from make_golden_rays import ndc_like_rays, inside_out_rays  # noqa: E402
 
 
-def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, is_train=True, mode='bounded'):
+def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, is_train=True, mode='bounded', compact=False):
+    """compact=True (the nerf.yaml-scale case: > 151 552 valid samples, so forward() runs the large-batch kernel instantiations):
+    the dense [R,S] / [Nv,18] arrays are stored as packed bits, float64 sums and a strided row sample instead of in full."""
     cfg, m = build('nerf.yaml', aabb, ov, seed)
     with torch.no_grad():  # make the density field non-trivial at init (density_shift = -10)
         m.linear_mat.backbone[0].weight.mul_(10.0)
@@ -188,6 +190,16 @@ def render_case(name, ov, aabb, R=96, N_samples=80, seed=11, with_alpha=False, i
                app_mask=np.packbits(app.numpy()), z=z.numpy(), weight=weight.numpy(), sigma=sigma.numpy(),
                n_valid=np.array(int(valid.sum())), n_app=np.array(int(app.sum())), mode=mode,
                pts_sum=pts.double().sum((0, 1)).numpy())
+    if compact:
+        cf = out.pop('coeffs')
+        out['coeffs_rows'], out['coeffs_stride'], out['coeffs_colsum'] = cf[::61].copy(), np.array(61), cf.astype(np.float64).sum(0)
+        out['coeffs_shape'] = np.array(cf.shape)
+        zf = out.pop('z')
+        out['z_first'], out['z_last'], out['z_rowsum'] = zf[:, 0].copy(), zf[:, -1].copy(), zf.astype(np.float64).sum(1)
+        sg = out.pop('sigma')
+        out['sigma_valid_sum'] = np.array(sg.astype(np.float64).sum())
+        wv = out.pop('weight')
+        out['weight_valid'] = wv[valid.numpy()].astype(np.float32)       # compacted (ray, sample) order
     if mode == 'ndc':
         out['near_far'] = np.array(cfg.dataset.near_far, np.float64)
     if mode == 'unbound':
@@ -424,6 +436,9 @@ if __name__ == '__main__':
         render_case('train', SMALL, CUBE)
         render_case('train_alpha', SMALL, BOX, with_alpha=True, seed=13)
         render_case('eval_alpha', SMALL, BOX, with_alpha=True, seed=17, is_train=False)
+    if not only or 'render_big' in only:
+        # nerf.yaml sampling scale (128^3 render grid -> 443 samples per ray) on 1024 rays: ~250 k valid samples
+        render_case('train_big', {**SMALL, 'model.total_params': 120000}, CUBE, R=1024, N_samples=443, seed=37, compact=True)
     if not only or 'render_ndc' in only:
         NDC_BOX = [[-1.5, -1.67, -1.0], [1.5, 1.67, 1.0]]      # dataLoader/llff.py scene_bbox
         ndc = {**SMALL, 'dataset.near_far': [0.0, 1.0], 'dataset.ndc_ray': 1}

@@ -123,6 +123,32 @@ def test_render_forward_backward(name):
             assert H.rel_err(gb, g[f'grad.renderModule.mlp.{l}.bias']) < 2e-4
 
 
+def test_render_nerf_scale():
+    """The nerf.yaml-scale render case (1024 rays x 443 samples, 248 374 valid samples; recorded compactly): the oracle
+    reproduces the reference's masks bit-exactly and its weights / pixels / loss / factor gradients."""
+    g = H.golden('render_train_big')
+    ro = _render_oracle(g)
+    out = ro.forward(g['rays'], int(g['N_samples']), g['jitter'], white_bg=True, want_cache=True, mode='bounded')
+    assert np.array_equal(np.packbits(out['ray_valid']), g['ray_valid'])
+    assert int(out['ray_valid'].sum()) == int(g['n_valid']) > 151552
+    assert np.array_equal(out['z'][:, 0], g['z_first']) and np.array_equal(out['z'][:, -1], g['z_last'])
+    assert np.allclose(out['z'].astype(np.float64).sum(1), g['z_rowsum'], rtol=1e-12)
+    assert H.rel_err(out['weight'][out['ray_valid']], g['weight_valid']) < 2e-5
+    assert H.rel_err(out['rgb_map'], g['rgb_map']) < 1e-5
+    assert H.rel_err(out['depth_map'], g['depth_map']) < 1e-5
+    assert H.rel_err(out['coeffs'][::int(g['coeffs_stride'])], g['coeffs_rows']) < 1e-6
+    loss, g_rgb = O.mse_loss_and_grad(out['rgb_map'], g['target'])
+    assert abs(float(loss) - float(g['loss'])) < 1e-6
+    grads = ro.backward(out['cache'], g_rgb)
+    for kind in ('coeffs', 'basises'):
+        for i, gr in enumerate(grads[kind]):
+            assert H.rel_err(gr, g[f'grad.{kind}.{i}']) < 2e-4, (kind, i)
+    for l, (gW, gb) in enumerate(grads['linear_mat']):
+        assert H.rel_err(gW, g[f'grad.linear_mat.backbone.{l}.weight']) < 2e-4
+    for l, (gW, gb) in enumerate(grads['renderModule']):
+        assert H.rel_err(gW, g[f'grad.renderModule.mlp.{l}.weight']) < 2e-4
+
+
 def test_alpha_mask_maintenance():
     """Oracle restatement of compute_alpha / getDenseAlpha (no jitter) / filtering_rays against the vectors recorded from the
     reference (tests/golden/maintenance.npz)."""
