@@ -33,6 +33,18 @@ B_BWD_OWN = 12 + 72 + 144 + 2 * 1152      # x + upstream gradient row + saved co
 FLOP_LINEAR_MAT, FLOP_RGB = 6400, 83200
 
 
+def latest_field_capture():
+    """The newest committed `ncu --set full` summary of the field kernels (profiles/rNN_ncu_field*.json) -> (dict, path)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_field*.json')))
+    for f in reversed(files):
+        try:
+            return json.load(open(f)), os.path.relpath(f, ROOT)
+        except Exception:
+            pass
+    return {}, None
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -341,40 +353,50 @@ def run_ours(args):
     alg = {'field_fwd': n_valid * B_FWD, 'field_bwd': n_valid * B_BWD}
     for k, ms in sec.items():
         kern[k] = {'ms_per_step': round(ms, 4)}
-        if k in alg:
+        if k == 'field_fwd':
             kern[k]['achieved_GBps'] = round(alg[k] / (ms * 1e-3) / 1e9, 1)
             kern[k]['frac_hbm'] = round(alg[k] / (ms * 1e-3) / 1e9 / pk['hbm'], 4)
+        elif k == 'field_bwd':       # no HBM fraction: the kernel is L2-reduction bound (see roofline_bwd)
+            kern[k]['hbm_model_GBps'] = round(alg[k] / (ms * 1e-3) / 1e9, 1)
     flops = {'mlp_fwd': n_valid * FLOP_LINEAR_MAT, 'mlp_bwd': 2 * n_valid * FLOP_LINEAR_MAT, 'rgbmlp_fwd': n_app * FLOP_RGB,
              'rgbmlp_bwd': 2 * n_app * FLOP_RGB}
     for k, f in flops.items():
         if k in sec and sec[k] > 0:
             kern[k]['achieved_TFLOPs'] = round(f / (sec[k] * 1e-3) / 1e12, 3)
-    dom = max(('field_fwd', 'field_bwd'), key=lambda k: sec.get(k, 0.0))
+    # ---- roofline.  The HBM model applies to the GATHER kernel: every algorithmic byte of the forward query is a real
+    # load or store.  The scatter kernel is bound by L2 reductions (ncu: DRAM ~12 %, red sectors the busiest unit) and is reported
+    # against a live-measured L2-reduction throughput (roofline_bwd) instead of an HBM fraction it cannot be a fraction of.
+    cap, cap_src = latest_field_capture()
+    dom = 'field_fwd'
     ach = alg[dom] / (sec[dom] * 1e-3) / 1e9
-    # DRAM traffic of the same kernel per launch: from the committed `ncu --set full` capture (profiles/), never measured here
-    traffic, traffic_src = None, None
-    try:
-        cap = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_field_v3.json')))
-        for name, rec in cap.items():
-            if ('bwd' in name) == (dom == 'field_bwd') and rec.get('traffic_bytes'):
-                traffic, traffic_src = int(rec['traffic_bytes']), 'profiles/r01_ncu_field_v3.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)'
-    except Exception:
-        pass
+    fwd_cap = next((rec for name, rec in cap.items() if 'fwd' in name and rec.get('traffic_bytes')), None)
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 4),
-                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['src'],
+                'traffic': int(fwd_cap['traffic_bytes']) if fwd_cap else None,
+                'traffic_source': (cap_src + ' (dram__bytes_read.sum + dram__bytes_write.sum, one launch)') if fwd_cap else None,
+                'peak_source': pk['src'], 'algorithmic_bytes_per_query': B_FWD,
                 'algorithmic_bytes_per_launch': alg[dom], 'queries_per_launch': n_valid, 'launch_ms': round(sec[dom], 4),
                 'share_of_step': round(sec[dom] / (ms_total / args.steps), 4)}
-    if dom == 'field_bwd':
-        # SURVEY's 3 528 B/query counts a re-gather of the texels (1 152 B) that the saved-row design replaces by 144 B of
-        # streamed coefficient / basis rows: with the bytes this kernel is designed to move (12 + 72 + 144 + 2*1152) the fraction is
-        own = n_valid * B_BWD_OWN
-        roofline['frac_own_design_bytes'] = round(own / (sec[dom] * 1e-3) / 1e9 / pk['hbm'], 4)
-        roofline['own_design_bytes_per_query'] = B_BWD_OWN
-        roofline['note'] = ('frac > 1 by construction: SURVEY 8(d) charges the backward 3528 B/query (re-gather 1152 + read-modify-write 2304 + '
-                            'gradient row 72), but this kernel reads saved coefficient/basis rows (144 B) instead of re-gathering and merges the '
-                            'contributions of consecutive samples of a ray to the same coefficient cell before they reach L2; the factor grids and '
-                            'their gradients (21 MB each) stay L2-resident, so DRAM sees only the streamed rows (traffic). The forward kernel, whose '
-                            'algorithmic bytes are all real gathers, is at kernels.field_fwd.frac_hbm.')
+    roofline_bwd = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'scratch'))
+        import probe_red
+        probe = probe_red.measure()
+        bwd_cap = next((rec for name, rec in cap.items() if 'bwd' in name and rec.get('lts__t_sectors_srcunit_tex_op_red.sum')), None)
+        if bwd_cap and 'field_bwd' in sec:
+            red = float(bwd_cap['lts__t_sectors_srcunit_tex_op_red.sum']['value'])
+            q_cap = float(bwd_cap.get('queries_per_launch', 986959))
+            sectors = red / q_cap * n_valid                 # the capture's red sectors per query x this launch's queries
+            ach_b = sectors / (sec['field_bwd'] * 1e-3)
+            peak_b = max(v['sectors_per_s'] for v in probe.values())
+            roofline_bwd = {'kernel': 'field_bwd', 'bound': 'l2_red', 'unit': 'L2 reduction sectors/s', 'achieved': ach_b, 'peak': peak_b,
+                            'frac': round(ach_b / peak_b, 4), 'red_sectors_per_query': round(red / q_cap, 2), 'sectors_source': cap_src +
+                            ' (lts__t_sectors_srcunit_tex_op_red.sum, one launch)', 'peak_source': 'ffb_probe_red, measured in this run '
+                            '(red.global.add.v4.f32 into an L2-resident 21 MB buffer; best of the two address patterns)', 'probe': probe,
+                            'launch_ms': round(sec['field_bwd'], 4), 'share_of_step': round(sec['field_bwd'] / (ms_total / args.steps), 4),
+                            'hbm_model_note': f'SURVEY 8(d) charges this kernel {B_BWD} B/query; it reads saved rows instead of re-gathering and its '
+                                              'read-modify-write lands in L2, so an HBM fraction would be an accounting figure, not a bound'}
+    except Exception as e:      # the probe is informational; the headline roofline never depends on it
+        roofline_bwd = {'error': repr(e)}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
@@ -387,7 +409,7 @@ def run_ours(args):
             'field_queries_per_s': world * n_valid * args.steps / (ms_total * 1e-3),
             'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': B * (6 + 3 + 1) * 4,
                     'd2h_bytes_per_step': 4, 'api': api},
-            'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clk}
+            'gpu_launches': launches, 'roofline': roofline, 'roofline_bwd': roofline_bwd, 'kernels': kern, 'clocks': clk}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_leg()
     if world == 1 and not args.no_cuda_eager_baseline:
