@@ -210,6 +210,21 @@ int ffb_mlp2_bwd(const float* x, const float* gy, const float* W1, const float* 
                  const uint16_t* relu_mask, float* gx, float* gW1, float* gb1, float* gW2, int64_t n,
                  const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * get_coding + linear_mat as ONE kernel per direction (field_mlp.cu): FactorFields.py:425-533 followed by
+ * MLPMixer.forward :144-159 (2 layers, hidden 64, no PE / dropout), for grid x grid fields with linear taps.
+ * The feature row never reaches HBM: gather warps write it into shared-memory tensor-core operand tiles.
+ *   y [n,N]; relu_bits [n,4] uint16 (as ffb_mlp2_fwd); coeff_blk / basis_blk: the coefficient / basis rows BLOCKED by 32
+ *   queries (element (i,c) at (i/32)*32*W + c*32 + i%32; buffers of ceil(n/32)*32 rows) for ffb_field_mlp_bwd; optional
+ *   row-major copies feats [n,W] / coeff [n,W] (NULL: not written).
+ * ffb_field_mlp_bwd: g_y [n,N] -> factor gradients (h_grads as ffb_field_query_bwd) and gW1 / gb1 / gW2, all ACCUMULATED. */
+int ffb_set_field_mlp(int enabled);
+int ffb_field_mlp_eligible(ffb_field_t f, int32_t K0, int32_t H, int32_t N);
+int ffb_field_mlp_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* W1,
+                      const float* b1, const float* W2, float* y, uint16_t* relu_bits, float* coeff_blk,
+                      float* basis_blk, float* feats, float* coeff, int32_t K0, int32_t H, int32_t N,
+                      void* stream);
+
 /* positional_encoding (:74-79) appended to the input: out [n, D + 2*D*pe] = [x, sin, cos]. */
 int ffb_pe_concat_fwd(const float* x, float* out, int64_t n, const int32_t* n_dev, int32_t D,
                       int32_t pe, void* stream);
