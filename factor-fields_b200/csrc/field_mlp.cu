@@ -27,7 +27,6 @@ constexpr int FM_THREADS = 1024;
 constexpr int FM_NG = 27;             // gather warps 0..26
 constexpr int FM_MMA_WARP = 27;       // layer-1 issuer, owns the TMEM allocation
 constexpr int FM_EPI_WARP0 = 28;      // warps 28..31 -> TMEM lane quarters 0..3 (= warp % 4)
-constexpr int FM_NSLOT = 8;           // ring of x-tile slots: 27 chunks in flight span < 8 tiles, so a claim never waits
 constexpr int FM_TERMS = 3;
 constexpr uint32_t FM_SC = 2048;      // bytes between 8-column chunks of a 128-row activation tile
 constexpr uint32_t FM_XCHUNKS = 3;    // real chunks of an x tile (columns 0..23); chunk 3 (24..31) is the shared zero block
@@ -36,7 +35,8 @@ constexpr uint32_t FM_XSLOT = FM_TERMS * FM_XPART;         // 18 KB per slot
 constexpr uint32_t FM_HPART = 8 * FM_SC;                   // hidden tile: 64 columns
 constexpr int FM_H = 64, FM_K0P = 32, FM_NP = 32;
 
-struct FmSmem {
+template <int FM_NSLOT>      // ring of x-tile slots: 27 chunks in flight span < 8 tiles, so with 8 slots a claim never waits
+struct FmSmemT {
   // byte offsets into dynamic shared memory
   static constexpr uint32_t W1 = 0;                                   // 3 x 4 KB
   static constexpr uint32_t W2 = W1 + FM_TERMS * FM_H * FM_K0P * 2;    // 3 x 4 KB
@@ -70,10 +70,13 @@ struct FmFwdArgs {
   float* feats;         // optional row-major [n, W] copy of the feature row (tests / callers without the fused backward)
   float* coeff;         // optional row-major [n, W] coefficient row (get_coding's second output)
   Mlp2Shape S;
+  int n_gather;         // gather warps actually used (<= FM_NG and <= 4 * slots: a claim may run at most one use of a slot ahead)
+  int debug;            // experiment knob "fm_debug": bit 0 = gather warps skip the field arithmetic, bit 1 = epilogue warps skip their work
 };
 
-template <int DB, int DC>
+template <int DB, int DC, int FM_NSLOT>
 __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFwdArgs a) {
+  using FmSmem = FmSmemT<FM_NSLOT>;
   extern __shared__ __align__(128) uint8_t smem[];
   const FastParams& P = a.P;
   const int64_t n = resolve_n(a.n, a.n_dev);
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFw
   const int64_t n_tiles = (n + 127) >> 7;
   const int64_t Tc = n_tiles > (int64_t)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
 
-  if (warp < FM_NG) {
+  if (warp < a.n_gather) {
     // =================================== gather warps ===================================
     const float msize = fast_msize(P);
     const int n_chunks = (int)(4 * Tc);
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFw
       mbar_wait(slot_free + slot, (uint32_t)(((tseq / FM_NSLOT) & 1) ^ 1));     // layer 1 of the slot's previous tile has read it
       const int r = rg * 32 + lane;
       uint8_t* xrow = sX + (uint32_t)slot * FM_XSLOT + (uint32_t)(r >> 3) * TILE_SR + (uint32_t)(r & 7) * 16u;
-      if (active) {
+      if (active && !(a.debug & 1)) {
         float xr[3];
         for (int d = 0; d < P.xdim; ++d) xr[d] = a.x[i * P.xdim + d];
         TapSet<DC, false> tc;
@@ -198,6 +201,8 @@ __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFw
       __syncwarp();
       if (lane == 0) mbar_arrive(slot_full + slot);
     }
+  } else if (warp < FM_NG) {
+    // idle (experiment configurations with fewer gather warps)
   } else if (warp == FM_MMA_WARP) {
     // =================================== layer-1 issuer ===================================
     if (lane == 0) {
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFw
       const int64_t grow = (((int64_t)blockIdx.x + t * gridDim.x) << 7) + row;
 #pragma unroll
       for (int c0 = 0; c0 < FM_NP; c0 += 16) {
+        if (a.debug & 2) break;
         float v[16];
         tmem_ld16(d2 + lane_base + (uint32_t)c0, v);
         if (grow < n) {
@@ -271,6 +277,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFw
       const uint32_t d1 = tmem + (uint32_t)b * FM_H;
 #pragma unroll
       for (int c0 = 0; c0 < FM_H; c0 += 16) {
+        if (a.debug & 2) break;
         float v[16];
         tmem_ld16(d1 + lane_base + (uint32_t)c0, v);
         uint32_t bits = 0;
@@ -314,6 +321,8 @@ using namespace ffb;
 extern "C" {
 
 static int g_fm_enabled = 1;
+static int g_fm_debug = 0, g_fm_nslot = 8;
+int ffb_field_mlp_tuning(int debug, int nslot) { g_fm_debug = debug; g_fm_nslot = nslot; return FFB_OK; }
 
 int ffb_set_field_mlp(int enabled) {
   g_fm_enabled = enabled ? 1 : 0;
@@ -332,7 +341,7 @@ int ffb_field_mlp_eligible(ffb_field_t f, int32_t K0, int32_t H, int32_t N) {
   if (!((P.in_dim == 3 && P.xdim == 3) || (P.in_dim == 2 && P.xdim == 2))) return 0;
   Mlp2Shape S;
   if (!fm_shape_ok(P, K0, H, N, &S)) return 0;
-  return smem_optin_bytes() >= (int)FmSmem::TOTAL ? 1 : 0;
+  return smem_optin_bytes() >= (int)FmSmemT<8>::TOTAL ? 1 : 0;
 }
 
 int ffb_field_mlp_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* W1, const float* b1, const float* W2,
@@ -350,13 +359,21 @@ int ffb_field_mlp_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n
   const int64_t tiles = (n + 127) / 128;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
-  static PerDeviceOnce attr3, attr2;
+  a.debug = g_fm_debug;
+  a.n_gather = g_fm_nslot * 4 < FM_NG ? g_fm_nslot * 4 : FM_NG;
+#define FM_LAUNCH(DB_, DC_, NS_)                                                                                                    \
+  do {                                                                                                                              \
+    static PerDeviceOnce once;                                                                                                      \
+    if (once.first())                                                                                                               \
+      FFB_CUDA(cudaFuncSetAttribute(field_mlp_fwd_kernel<DB_, DC_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FmSmemT<NS_>::TOTAL)); \
+    field_mlp_fwd_kernel<DB_, DC_, NS_><<<grid, FM_THREADS, FmSmemT<NS_>::TOTAL, s>>>(a);                                           \
+  } while (0)
   if (a.P.in_dim == 3) {
-    if (attr3.first()) FFB_CUDA(cudaFuncSetAttribute(field_mlp_fwd_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FmSmem::TOTAL));
-    field_mlp_fwd_kernel<3, 3><<<grid, FM_THREADS, FmSmem::TOTAL, s>>>(a);
+    if (g_fm_nslot == 4) FM_LAUNCH(3, 3, 4);
+    else if (g_fm_nslot == 6) FM_LAUNCH(3, 3, 6);
+    else FM_LAUNCH(3, 3, 8);
   } else {
-    if (attr2.first()) FFB_CUDA(cudaFuncSetAttribute(field_mlp_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FmSmem::TOTAL));
-    field_mlp_fwd_kernel<2, 2><<<grid, FM_THREADS, FmSmem::TOTAL, s>>>(a);
+    FM_LAUNCH(2, 2, 8);
   }
   FFB_LAUNCHED();
   return FFB_OK;

@@ -34,3 +34,13 @@ def timeit(fn, reps=10):
 print('separate fwd (field + mlp2)  %.1f us' % timeit(lambda: _separate_fwd(m, x)))
 print('fused fwd (training outputs) %.1f us' % timeit(lambda: _fused_fwd(m, x, want_rows=False)))
 print('fused fwd (+ row-major rows) %.1f us' % timeit(lambda: _fused_fwd(m, x, want_rows=True)))
+
+lib = nv.lib()
+for nslot in (8, 6, 4):
+    for dbg in (0, 2, 1):
+        lib.ffb_field_mlp_tuning(dbg, nslot)
+        print('nslot %d (gather warps %d) debug %d (1: no gather math, 2: no epilogue work): %.1f us' % (nslot, min(27, 4 * nslot), dbg, timeit(lambda: _fused_fwd(m, x, want_rows=False))), flush=True)
+lib.ffb_field_mlp_tuning(0, 8)
+for cfgk in (1, 3, 0):
+    lib.ffb_set_tuning(b'field_fwd_cfg', cfgk)
+    print('old field fwd cfg %d + mlp2: %.1f us' % (cfgk, timeit(lambda: _separate_fwd(m, x))), flush=True)
