@@ -351,6 +351,13 @@ using namespace ffb;
 
 extern "C" {
 
+// the pipelined warp-specialised kernels (mlp_pipe.cu) take the shapes they cover; this file keeps the rest
+int ffb_mlp2_pipelined_eligible(int32_t K0, int32_t H, int32_t N);
+int ffb_mlp2p_fwd(const float* x, const float* W1, const float* b1, const float* W2, float* y, uint16_t* relu_mask, int64_t n,
+                  const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream);
+int ffb_mlp2p_bwd(const float* x, const float* gy, const float* W1, const float* b1, const float* W2, const uint16_t* relu_mask, float* gx,
+                  float* gW1, float* gb1, float* gW2, int64_t n, const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream);
+
 int ffb_set_fused_mlp(int enabled) {
   fused_enabled = enabled ? 1 : 0;
   return FFB_OK;
@@ -367,6 +374,7 @@ int ffb_mlp2_eligible(int32_t K0, int32_t H, int32_t N) {
 int ffb_mlp2_fwd(const float* x, const float* W1, const float* b1, const float* W2, float* y, uint16_t* relu_mask, int64_t n,
                  const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream) {
   FFB_REQUIRE(x && W1 && W2 && y, "null argument");
+  if (b1 && ffb_mlp2_pipelined_eligible(K0, H, N) == 1) return ffb_mlp2p_fwd(x, W1, b1, W2, y, relu_mask, n, n_dev, K0, H, N, stream);
   Mlp2Shape S;
   size_t sf, sb;
   int cf, cb;
@@ -388,6 +396,7 @@ int ffb_mlp2_fwd(const float* x, const float* W1, const float* b1, const float* 
 int ffb_mlp2_bwd(const float* x, const float* gy, const float* W1, const float* b1, const float* W2, const uint16_t* relu_mask, float* gx,
                  float* gW1, float* gb1, float* gW2, int64_t n, const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream) {
   FFB_REQUIRE(x && gy && W1 && W2, "null argument");
+  if (b1 && ffb_mlp2_pipelined_eligible(K0, H, N) == 1) return ffb_mlp2p_bwd(x, gy, W1, b1, W2, relu_mask, gx, gW1, gb1, gW2, n, n_dev, K0, H, N, stream);
   Mlp2Shape S;
   size_t sf, sb;
   int cf, cb;

@@ -1,0 +1,562 @@
+// mlp_pipe.cu — `linear_mat` (MLPMixer 2 layers, FactorFields.py:144-159) as PIPELINED warp-specialised tcgen05 kernels.
+//
+// mlp_fused.cu runs one 128-row tile per CTA as a serial chain (stage -> MMA -> wait -> epilogue -> MMA -> wait -> store) with
+// every thread of the CTA spinning on each MMA round trip: ncu shows 2 900 (forward) / 4 800 (backward) thread-instructions
+// per row, two thirds of them in the wait loops, tensor pipe 13 % busy.  Here one persistent CTA per SM splits the roles:
+//   * PRODUCER warps keep a ring of operand-tile slots full (rows prefetched into registers before the slot is free, bf16-split
+//     into the canonical no-swizzle UMMA layout);
+//   * ONE thread issues the first-stage MMAs of tile t+1, t+2 while earlier tiles are still in their epilogues (accumulators
+//     double-buffered in TMEM), tcgen05.commit frees the slot / publishes the accumulator through mbarriers;
+//   * EPILOGUE warps (one per TMEM lane quarter and column half) do the ReLU / masking / re-splitting and the output stores,
+//     and issue the second-stage MMAs themselves — the only threads that ever wait on an MMA.
+// Same arithmetic as mlp_fused.cu (3 bf16 parts forward, 2 parts for gradients, ReLU decisions taken once in the forward pass,
+// layer-1 bias as an all-ones input column, weight gradients accumulated in TMEM across all tiles of the CTA).
+#include "tc_tiles.cuh"
+#include "ffb_math.h"
+
+namespace ffb {
+
+constexpr int MP_H = 64, MP_K0P = 32, MP_NP = 32;
+constexpr uint32_t MP_SC = 2048;               // bytes between 8-column chunks of a 128-row tile
+
+template <int TERMS>
+__device__ __forceinline__ void mp_store2(uint8_t* row, uint32_t part_bytes, int c, float a, float b) {
+  uint32_t w[TERMS];
+  split2_packed<TERMS>(a, b, w);
+  uint8_t* p = row + (uint32_t)(c >> 3) * MP_SC + (uint32_t)(c & 7) * 2u;
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint32_t*>(p + (uint32_t)t * part_bytes) = w[t];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward:  y = relu([x | 1] [W1 | b1]^T) W2^T      warps: 0..7 epilogue (group = warp >> 2 takes tiles t = group mod 2),
+//                                                          8 layer-1 issuer, 9..20 producers
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MPF_THREADS = 21 * 32, MPF_NPROD = 12, MPF_NSLOT = 3, MPF_TERMS = 3;
+constexpr uint32_t MPF_XPART = 4 * MP_SC, MPF_XSLOT = MPF_TERMS * MPF_XPART;      // 8 KB / 24 KB
+constexpr uint32_t MPF_HPART = 8 * MP_SC, MPF_HBUF = MPF_TERMS * MPF_HPART;       // 16 KB / 48 KB
+struct MpfSmem {
+  static constexpr uint32_t W1 = 0;
+  static constexpr uint32_t W2 = W1 + MPF_TERMS * MP_H * MP_K0P * 2;
+  static constexpr uint32_t X = W2 + MPF_TERMS * MP_NP * MP_H * 2;
+  static constexpr uint32_t HID = X + MPF_NSLOT * MPF_XSLOT;
+  static constexpr uint32_t BAR = HID + 2 * MPF_HBUF;
+  static constexpr uint32_t N_BAR = 2 * MPF_NSLOT + 2 + 2 + 2;     // slot_full, slot_free, d1_full[2], d1_free[2], d2_full[2]
+  static constexpr uint32_t MISC = BAR + N_BAR * 8;
+  static constexpr uint32_t TOTAL = MISC + 16;
+};
+
+__global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1,
+                                                                   const float* __restrict__ b1, const float* __restrict__ W2,
+                                                                   float* __restrict__ y, uint16_t* __restrict__ mask, int64_t n_cap,
+                                                                   const int32_t* __restrict__ n_dev, const Mlp2Shape S) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int64_t n = resolve_n(n_cap, n_dev);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sW1 = smem + MpfSmem::W1;
+  uint8_t* sW2 = smem + MpfSmem::W2;
+  uint8_t* sX = smem + MpfSmem::X;
+  uint8_t* sH = smem + MpfSmem::HID;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MpfSmem::BAR);
+  uint64_t* slot_full = bars;
+  uint64_t* slot_free = bars + MPF_NSLOT;
+  uint64_t* d1_full = bars + 2 * MPF_NSLOT;
+  uint64_t* d1_free = d1_full + 2;
+  uint64_t* d2_full = d1_free + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MpfSmem::MISC);
+  int* next_chunk = reinterpret_cast<int*>(smem + MpfSmem::MISC + 4);
+  const int K0 = S.K0, N = S.N;
+
+  if (warp == 8) tmem_alloc(tmem_slot, 256u);
+  if (tid == 0) {
+    for (int s = 0; s < MPF_NSLOT; ++s) {
+      mbar_init(slot_full + s, 4);
+      mbar_init(slot_free + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(d1_full + b, 1);
+      mbar_init(d1_free + b, 128);
+      mbar_init(d2_full + b, 1);
+    }
+    *next_chunk = 0;
+  }
+  stage_weights<MPF_TERMS>(S, W1, b1, W2, sW1, sW2, tid, MPF_THREADS);
+  for (uint32_t o = tid * 16u; o < MPF_NSLOT * MPF_XSLOT; o += MPF_THREADS * 16u) *reinterpret_cast<uint4*>(sX + o) = make_uint4(0, 0, 0, 0);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t n_tiles = (n + 127) >> 7;
+  const int64_t Tc = n_tiles > (int64_t)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp >= 9) {
+    // ------------------------------ producers: one 32-row chunk at a time, rows prefetched before the slot wait
+    const int n_chunks = (int)(4 * Tc);
+    const bool vec2 = ((K0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+    for (;;) {
+      int j = 0;
+      if (lane == 0) j = atomicAdd(next_chunk, 1);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= n_chunks) break;
+      const int tseq = j >> 2, rg = j & 3, slot = tseq % MPF_NSLOT;
+      const int64_t i = (((int64_t)blockIdx.x + (int64_t)tseq * gridDim.x) << 7) + rg * 32 + lane;
+      float v[MP_K0P];
+#pragma unroll
+      for (int c = 0; c < MP_K0P; ++c) v[c] = 0.0f;
+      if (i < n) {
+        const float* xr = x + i * K0;
+        if (vec2) {
+#pragma unroll
+          for (int c = 0; c < MP_K0P; c += 2)
+            if (c < K0) {
+              const float2 t2 = *reinterpret_cast<const float2*>(xr + c);
+              v[c] = t2.x;
+              v[c + 1] = t2.y;
+            }
+        } else {
+#pragma unroll
+          for (int c = 0; c < MP_K0P; ++c)
+            if (c < K0) v[c] = xr[c];
+        }
+#pragma unroll
+        for (int c = 0; c < MP_K0P; ++c)
+          if (c == K0) v[c] = 1.0f;                 // bias column
+      }
+      mbar_wait(slot_free + slot, (uint32_t)(((tseq / MPF_NSLOT) & 1) ^ 1));
+      const int r = rg * 32 + lane;
+      uint8_t* xrow = sX + (uint32_t)slot * MPF_XSLOT + (uint32_t)(r >> 3) * TILE_SR + (uint32_t)(r & 7) * 16u;
+#pragma unroll
+      for (int c0 = 0; c0 < MP_K0P; c0 += 8) {
+        if (c0 <= K0) {                              // chunks beyond the bias column stay zero (cleared once at start)
+          uint4 parts[MPF_TERMS];
+          split8_packed<MPF_TERMS>(v + c0, parts);
+#pragma unroll
+          for (int t = 0; t < MPF_TERMS; ++t) *reinterpret_cast<uint4*>(xrow + (uint32_t)(c0 >> 3) * MP_SC + (uint32_t)t * MPF_XPART) = parts[t];
+        }
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(slot_full + slot);
+    }
+  } else if (warp == 8) {
+    // ------------------------------ layer-1 issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc(MP_H, 0, 0);
+      const uint32_t aW1 = smem_u32(sW1), szW1 = MP_H * MP_K0P * 2, scW1 = MP_H * 16;
+      for (int64_t t = 0; t < Tc; ++t) {
+        const int slot = (int)(t % MPF_NSLOT), b = (int)(t & 1);
+        mbar_wait(slot_full + slot, (uint32_t)((t / MPF_NSLOT) & 1));
+        mbar_wait(d1_free + b, (uint32_t)(((t >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t aX = smem_u32(sX) + (uint32_t)slot * MPF_XSLOT;
+        issue_gemm<MPF_TERMS>(tmem + (uint32_t)b * MP_H, idesc1, MP_K0P / 16, false,
+                              [&](int tt, int s) { return desc_k(aX + (uint32_t)tt * MPF_XPART, MP_SC, s); },
+                              [&](int tt, int s) { return desc_k(aW1 + (uint32_t)tt * szW1, scW1, s); });
+        umma_commit(slot_free + slot);
+        umma_commit(d1_full + b);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue: group g handles tiles g, g+2, ...
+    const int g = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t d1 = tmem + (uint32_t)g * MP_H, d2 = tmem + 2u * MP_H + (uint32_t)g * MP_NP;
+    const uint32_t idesc2 = make_idesc(MP_NP, 0, 0);
+    uint8_t* myH = sH + (uint32_t)g * MPF_HBUF;
+    const uint32_t aH = smem_u32(myH), aW2 = smem_u32(sW2), szW2 = MP_NP * MP_H * 2, scW2 = MP_NP * 16;
+    auto epi2 = [&](int64_t t, int64_t k) {
+      mbar_wait(d2_full + g, (uint32_t)(k & 1));
+      tc_fence_after();
+      const int64_t grow = (((int64_t)blockIdx.x + t * gridDim.x) << 7) + row;
+#pragma unroll
+      for (int c0 = 0; c0 < MP_NP; c0 += 16) {
+        float v[16];
+        tmem_ld16(d2 + lane_base + (uint32_t)c0, v);
+        if (grow < n) {
+          float* yr = y + grow * N + c0;
+          if ((N & 3) == 0 && c0 + 16 <= N) {
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2 += 4) *reinterpret_cast<float4*>(yr + k2) = make_float4(v[k2], v[k2 + 1], v[k2 + 2], v[k2 + 3]);
+          } else {
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2)
+              if (c0 + k2 < N) yr[k2] = v[k2];
+          }
+        }
+      }
+    };
+    int64_t k = 0;
+    for (int64_t t = g; t < Tc; t += 2, ++k) {
+      if (k > 0) epi2(t - 2, k - 1);          // also: layer 2 of this group's previous tile has finished reading the hidden tile
+      mbar_wait(d1_full + g, (uint32_t)(k & 1));
+      tc_fence_after();
+      const int64_t grow = (((int64_t)blockIdx.x + t * gridDim.x) << 7) + row;
+#pragma unroll
+      for (int c0 = 0; c0 < MP_H; c0 += 16) {
+        float v[16];
+        tmem_ld16(d1 + lane_base + (uint32_t)c0, v);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) {
+          bits |= (v[i2] > 0.0f ? 1u : 0u) << i2;
+          v[i2] = fmaxf(v[i2], 0.0f);
+        }
+        if (mask && grow < n) mask[grow * (MP_H >> 4) + (c0 >> 4)] = (uint16_t)bits;
+        store_row8<MPF_TERMS>(myH, MPF_HPART, MP_SC, row, c0, v);
+        store_row8<MPF_TERMS>(myH, MPF_HPART, MP_SC, row, c0 + 8, v + 8);
+      }
+      tc_fence_before();
+      mbar_arrive(d1_free + g);
+      proxy_fence();
+      named_sync(1 + g, 128);
+      if (q == 0 && lane == 0) {
+        tc_fence_after();
+        issue_gemm<MPF_TERMS>(d2, idesc2, MP_H / 16, false, [&](int tt, int s) { return desc_k(aH + (uint32_t)tt * MPF_HPART, MP_SC, s); },
+                              [&](int tt, int s) { return desc_k(aW2 + (uint32_t)tt * szW2, scW2, s); });
+        umma_commit(d2_full + g);
+      }
+    }
+    if (k > 0) epi2(g + 2 * (k - 1), k - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 256u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward.  Tiles (2 bf16 parts, 128 rows):  B2 = [ g_y | x 1 ]  (64 columns, ring of 3),  A2 = [ h | g_h ]  (128 columns).
+//   stage 1 (issuer warp, runs ahead):  D1 = X [W1|b1]^T   D2 = GY W2                       (double-buffered in TMEM)
+//   epilogue 1: ReLU decisions (forward's bits) -> A2
+//   stage 2 (issued by the epilogue):   D3 = GH W1 (g_x)   DW += A2^T B2  (gW2^T and [gW1|gb1], resident in TMEM)
+//   epilogue 2 (of the PREVIOUS tile, under stage 2 of this one): g_x tile -> fp32 staging -> coalesced stores
+// warps: 0..7 epilogue (q = warp & 3 lane quarter, half = warp >> 2 column half), 8 stage-1 issuer, 9..16 producers
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MPB_THREADS = 17 * 32, MPB_NPROD = 8, MPB_NSLOT = 3, MPB_TERMS = 2;
+constexpr uint32_t MPB_BPART = 8 * MP_SC, MPB_BSLOT = MPB_TERMS * MPB_BPART;      // 16 KB / 32 KB
+constexpr uint32_t MPB_APART = 16 * MP_SC, MPB_ABUF = MPB_TERMS * MPB_APART;      // 32 KB / 64 KB
+struct MpbSmem {
+  static constexpr uint32_t W1 = 0;
+  static constexpr uint32_t W2 = W1 + MPB_TERMS * MP_H * MP_K0P * 2;
+  static constexpr uint32_t B2 = W2 + MPB_TERMS * MP_NP * MP_H * 2;
+  static constexpr uint32_t A2 = B2 + MPB_NSLOT * MPB_BSLOT;
+  static constexpr uint32_t STG = A2 + MPB_ABUF;                    // g_x staging: 128 x 32 floats
+  static constexpr uint32_t BAR = STG + 128 * MP_K0P * 4;
+  static constexpr uint32_t N_BAR = 2 * MPB_NSLOT + 2 + 2 + 1;      // slot_full, slot_free, d12_full[2], d12_free[2], cd_full
+  static constexpr uint32_t MISC = BAR + N_BAR * 8;
+  static constexpr uint32_t TOTAL = MISC + 16;
+};
+
+__global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                   const float* __restrict__ W1, const float* __restrict__ b1,
+                                                                   const float* __restrict__ W2, const uint16_t* __restrict__ mask,
+                                                                   float* __restrict__ gx, float* __restrict__ gW1, float* __restrict__ gb1,
+                                                                   float* __restrict__ gW2, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                                                                   const Mlp2Shape S) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int64_t n = resolve_n(n_cap, n_dev);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sW1 = smem + MpbSmem::W1;
+  uint8_t* sW2 = smem + MpbSmem::W2;
+  uint8_t* sB2 = smem + MpbSmem::B2;
+  uint8_t* sA2 = smem + MpbSmem::A2;
+  float* stg = reinterpret_cast<float*>(smem + MpbSmem::STG);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MpbSmem::BAR);
+  uint64_t* slot_full = bars;
+  uint64_t* slot_free = bars + MPB_NSLOT;
+  uint64_t* d12_full = bars + 2 * MPB_NSLOT;
+  uint64_t* d12_free = d12_full + 2;
+  uint64_t* cd_full = d12_free + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MpbSmem::MISC);
+  int* next_chunk = reinterpret_cast<int*>(smem + MpbSmem::MISC + 4);
+  const int K0 = S.K0, N = S.N, H = MP_H;
+  constexpr uint32_t offX = (uint32_t)(MP_NP / 8) * MP_SC, offGH = (uint32_t)(MP_H / 8) * MP_SC;      // x inside B2, g_h inside A2
+  constexpr int NB2 = MP_NP + MP_K0P;
+
+  if (warp == 8) tmem_alloc(tmem_slot, 512u);
+  if (tid == 0) {
+    for (int s = 0; s < MPB_NSLOT; ++s) {
+      mbar_init(slot_full + s, 4);
+      mbar_init(slot_free + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(d12_full + b, 1);
+      mbar_init(d12_free + b, 256);
+    }
+    mbar_init(cd_full, 1);
+    *next_chunk = 0;
+  }
+  stage_weights<MPB_TERMS>(S, W1, b1, W2, sW1, sW2, tid, MPB_THREADS);
+  for (uint32_t o = tid * 16u; o < MPB_NSLOT * MPB_BSLOT; o += MPB_THREADS * 16u) *reinterpret_cast<uint4*>(sB2 + o) = make_uint4(0, 0, 0, 0);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: D1[2] 0..127, D2[2] 128..255, D3[2] 256..319, DW 320..383
+  const int64_t n_tiles = (n + 127) >> 7;
+  const int64_t Tc = n_tiles > (int64_t)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t szW1 = (uint32_t)H * MP_K0P * 2, szW2 = (uint32_t)MP_NP * H * 2, scW1 = (uint32_t)H * 16, scW2 = (uint32_t)MP_NP * 16;
+  const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aA2 = smem_u32(sA2);
+
+  if (warp >= 9) {
+    // ------------------------------ producers
+    const int n_chunks = (int)(4 * Tc);
+    const bool vecX = ((K0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+    const bool vecG = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
+    for (;;) {
+      int j = 0;
+      if (lane == 0) j = atomicAdd(next_chunk, 1);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= n_chunks) break;
+      const int tseq = j >> 2, rg = j & 3, slot = tseq % MPB_NSLOT;
+      const int64_t i = (((int64_t)blockIdx.x + (int64_t)tseq * gridDim.x) << 7) + rg * 32 + lane;
+      float v[MP_K0P], gv[MP_NP];
+#pragma unroll
+      for (int c = 0; c < MP_K0P; ++c) v[c] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < MP_NP; ++c) gv[c] = 0.0f;
+      if (i < n) {
+        const float* xr = x + i * K0;
+        const float* gr = gy + i * N;
+        if (vecG) {
+#pragma unroll
+          for (int c = 0; c < MP_NP; c += 4)
+            if (c < N) {
+              const float4 t4 = *reinterpret_cast<const float4*>(gr + c);
+              gv[c] = t4.x; gv[c + 1] = t4.y; gv[c + 2] = t4.z; gv[c + 3] = t4.w;
+            }
+        } else {
+#pragma unroll
+          for (int c = 0; c < MP_NP; ++c)
+            if (c < N) gv[c] = gr[c];
+        }
+        if (vecX) {
+#pragma unroll
+          for (int c = 0; c < MP_K0P; c += 2)
+            if (c < K0) {
+              const float2 t2 = *reinterpret_cast<const float2*>(xr + c);
+              v[c] = t2.x;
+              v[c + 1] = t2.y;
+            }
+        } else {
+#pragma unroll
+          for (int c = 0; c < MP_K0P; ++c)
+            if (c < K0) v[c] = xr[c];
+        }
+#pragma unroll
+        for (int c = 0; c < MP_K0P; ++c)
+          if (c == K0) v[c] = 1.0f;
+      }
+      mbar_wait(slot_free + slot, (uint32_t)(((tseq / MPB_NSLOT) & 1) ^ 1));
+      const int r = rg * 32 + lane;
+      uint8_t* brow = sB2 + (uint32_t)slot * MPB_BSLOT + (uint32_t)(r >> 3) * TILE_SR + (uint32_t)(r & 7) * 16u;
+#pragma unroll
+      for (int c0 = 0; c0 < MP_NP; c0 += 8) {
+        uint4 parts[MPB_TERMS];
+        split8_packed<MPB_TERMS>(gv + c0, parts);
+#pragma unroll
+        for (int t = 0; t < MPB_TERMS; ++t) *reinterpret_cast<uint4*>(brow + (uint32_t)(c0 >> 3) * MP_SC + (uint32_t)t * MPB_BPART) = parts[t];
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < MP_K0P; c0 += 8) {
+        uint4 parts[MPB_TERMS];
+        split8_packed<MPB_TERMS>(v + c0, parts);
+#pragma unroll
+        for (int t = 0; t < MPB_TERMS; ++t) *reinterpret_cast<uint4*>(brow + offX + (uint32_t)(c0 >> 3) * MP_SC + (uint32_t)t * MPB_BPART) = parts[t];
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(slot_full + slot);
+    }
+  } else if (warp == 8) {
+    // ------------------------------ stage-1 issuer: D1 = X [W1|b1]^T (hidden pre-activation), D2 = GY W2
+    if (lane == 0) {
+      const uint32_t id_h = make_idesc(H, 0, 0), id_gh = make_idesc(H, 0, 1);
+      for (int64_t t = 0; t < Tc; ++t) {
+        const int slot = (int)(t % MPB_NSLOT), b = (int)(t & 1);
+        mbar_wait(slot_full + slot, (uint32_t)((t / MPB_NSLOT) & 1));
+        mbar_wait(d12_free + b, (uint32_t)(((t >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t aB2 = smem_u32(sB2) + (uint32_t)slot * MPB_BSLOT;
+        issue_gemm<MPB_TERMS>(tmem + (uint32_t)b * H, id_h, MP_K0P / 16, false,
+                              [&](int tt, int s) { return desc_k(aB2 + offX + (uint32_t)tt * MPB_BPART, MP_SC, s); },
+                              [&](int tt, int s) { return desc_k(aW1 + (uint32_t)tt * szW1, scW1, s); });
+        issue_gemm<MPB_TERMS>(tmem + 128u + (uint32_t)b * H, id_gh, MP_NP / 16, false,
+                              [&](int tt, int s) { return desc_k(aB2 + (uint32_t)tt * MPB_BPART, MP_SC, s); },
+                              [&](int tt, int s) { return desc_mn(aW2 + (uint32_t)tt * szW2, scW2, s); });
+        umma_commit(d12_full + b);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue (256 threads): row = lane quarter * 32 + lane, columns of half = warp >> 2
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane, etid = tid;          // etid in [0, 256)
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t dW = tmem + 320u;
+    const uint32_t id_gx = make_idesc(MP_K0P, 0, 1), id_w = make_idesc(NB2, 1, 1, 128);
+    auto epi2 = [&](int64_t t) {       // g_x rows of tile t: D3[t & 1] -> staging -> coalesced 16-byte stores
+      const uint32_t d3 = tmem + 256u + (uint32_t)(t & 1) * MP_K0P;
+      const int64_t row0 = ((int64_t)blockIdx.x + t * gridDim.x) << 7;
+      if (gx) {
+        float v[16];
+        tmem_ld16(d3 + lane_base + (uint32_t)(half * 16), v);
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2)
+          if (half * 16 + i2 < K0) stg[row * K0 + half * 16 + i2] = v[i2];
+      }
+      tc_fence_before();
+      named_sync(2, 256);
+      if (gx) {
+        const int64_t rows = (n - row0) < 128 ? (n - row0) : 128;
+        const int64_t total = rows > 0 ? rows * K0 : 0;
+        float* dst = gx + row0 * K0;
+        if (((row0 * K0) & 3) == 0 && (reinterpret_cast<uintptr_t>(gx) & 15) == 0) {
+          const int64_t n4 = total >> 2;
+          for (int64_t e = etid; e < n4; e += 256) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(stg)[e];
+          for (int64_t e = (n4 << 2) + etid; e < total; e += 256) dst[e] = stg[e];
+        } else {
+          for (int64_t e = etid; e < total; e += 256) dst[e] = stg[e];
+        }
+      }
+      named_sync(2, 256);              // staging free again
+    };
+    for (int64_t t = 0; t < Tc; ++t) {
+      const int slot = (int)(t % MPB_NSLOT), b = (int)(t & 1);
+      if (t > 0) {                     // stage 2 of tile t-1 complete: A2 free, D3[(t-1)&1] ready, its B2 slot released
+        mbar_wait(cd_full, (uint32_t)((t - 1) & 1));
+        tc_fence_after();
+      }
+      mbar_wait(d12_full + b, (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const int64_t grow = (((int64_t)blockIdx.x + t * gridDim.x) << 7) + row;
+      const uint32_t d1 = tmem + (uint32_t)b * H, d2 = tmem + 128u + (uint32_t)b * H;
+#pragma unroll
+      for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 16) {
+        float h[16], g[16];
+        tmem_ld16(d1 + lane_base + (uint32_t)c0, h);
+        tmem_ld16(d2 + lane_base + (uint32_t)c0, g);
+        uint32_t bits;
+        if (mask) {
+          bits = grow < n ? (uint32_t)mask[grow * (H >> 4) + (c0 >> 4)] : 0u;
+        } else {
+          bits = 0;
+#pragma unroll
+          for (int i2 = 0; i2 < 16; ++i2) bits |= (h[i2] > 0.0f ? 1u : 0u) << i2;
+          if (grow >= n) bits = 0;
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) {
+          const bool on = (bits >> i2) & 1u;
+          g[i2] = on ? g[i2] : 0.0f;
+          h[i2] = on ? fmaxf(h[i2], 0.0f) : 0.0f;
+        }
+        store_row8<MPB_TERMS>(sA2, MPB_APART, MP_SC, row, c0, h);
+        store_row8<MPB_TERMS>(sA2, MPB_APART, MP_SC, row, c0 + 8, h + 8);
+        store_row8<MPB_TERMS>(sA2 + offGH, MPB_APART, MP_SC, row, c0, g);
+        store_row8<MPB_TERMS>(sA2 + offGH, MPB_APART, MP_SC, row, c0 + 8, g + 8);
+      }
+      tc_fence_before();
+      mbar_arrive(d12_free + b);
+      proxy_fence();
+      named_sync(1, 256);
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t aB2 = smem_u32(sB2) + (uint32_t)slot * MPB_BSLOT;
+        issue_gemm<MPB_TERMS>(tmem + 256u + (uint32_t)b * MP_K0P, id_gx, H / 16, false,
+                              [&](int tt, int s) { return desc_k(aA2 + offGH + (uint32_t)tt * MPB_APART, MP_SC, s); },
+                              [&](int tt, int s) { return desc_mn(aW1 + (uint32_t)tt * szW1, scW1, s); });
+        issue_gemm<MPB_TERMS>(dW, id_w, 8, t > 0, [&](int tt, int s) { return desc_mn(aA2 + (uint32_t)tt * MPB_APART, MP_SC, s); },
+                              [&](int tt, int s) { return desc_mn(aB2 + (uint32_t)tt * MPB_BPART, MP_SC, s); });
+        umma_commit(slot_free + slot);
+        umma_commit(cd_full);
+      }
+      if (t > 0) epi2(t - 1);          // under stage 2 of tile t
+    }
+    if (Tc > 0) {
+      mbar_wait(cd_full, (uint32_t)((Tc - 1) & 1));
+      tc_fence_after();
+      epi2(Tc - 1);
+      // ---- flush the weight gradients: accumulator row m (M = 128): m < 64 -> gW2^T row j = m; m >= 64 -> [gW1 | gb1] row j = m - 64
+      const int m = row;
+      for (int c0 = half * 16; c0 < NB2; c0 += 32) {
+        float v[16];
+        tmem_ld16(dW + lane_base + (uint32_t)c0, v);
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) {
+          const int c = c0 + i2;
+          if (v[i2] == 0.0f) continue;
+          if (m < H) {
+            if (c < N && gW2) atomicAdd(gW2 + (int64_t)c * H + m, v[i2]);
+          } else if (c >= MP_NP) {
+            const int kk = c - MP_NP, jj = m - H;
+            if (kk < K0) { if (gW1) atomicAdd(gW1 + (int64_t)jj * K0 + kk, v[i2]); }
+            else if (kk == K0 && gb1) atomicAdd(gb1 + jj, v[i2]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512u);
+}
+
+static int g_pipe_enabled = 1;
+
+static bool pipe_shape_ok(int K0, int H, int N, Mlp2Shape* S) {
+  if (H != MP_H || K0 < 1 || K0 + 1 > MP_K0P || N < 1 || N > MP_NP) return false;
+  S->K0 = K0; S->H = H; S->N = N; S->K0p = MP_K0P; S->Np = MP_NP;
+  return true;
+}
+
+}  // namespace ffb
+
+using namespace ffb;
+
+extern "C" {
+
+int ffb_set_mlp_pipelined(int enabled) {
+  g_pipe_enabled = enabled ? 1 : 0;
+  return FFB_OK;
+}
+
+/* 1 when the pipelined kernels take this shape: hidden width 64, K0 <= 31 inputs, N <= 32 outputs (linear_mat of nerf.yaml). */
+int ffb_mlp2_pipelined_eligible(int32_t K0, int32_t H, int32_t N) {
+  Mlp2Shape S;
+  if (!g_pipe_enabled || !ffb_tensor_cores_enabled() || !pipe_shape_ok(K0, H, N, &S)) return 0;
+  return smem_optin_bytes() >= (int)(MpfSmem::TOTAL > MpbSmem::TOTAL ? MpfSmem::TOTAL : MpbSmem::TOTAL) ? 1 : 0;
+}
+
+int ffb_mlp2p_fwd(const float* x, const float* W1, const float* b1, const float* W2, float* y, uint16_t* relu_mask, int64_t n,
+                  const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream) {
+  FFB_REQUIRE(x && W1 && b1 && W2 && y, "null argument");
+  Mlp2Shape S;
+  FFB_REQUIRE(pipe_shape_ok(K0, H, N, &S), "MLP shape not eligible for the pipelined tensor-core path");
+  if (n <= 0) return FFB_OK;
+  static PerDeviceOnce once;
+  if (once.first()) FFB_CUDA(cudaFuncSetAttribute(mlp2p_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MpfSmem::TOTAL));
+  const int64_t tiles = (n + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  mlp2p_fwd_kernel<<<grid, MPF_THREADS, MpfSmem::TOTAL, (cudaStream_t)stream>>>(x, W1, b1, W2, y, relu_mask, n, n_dev, S);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_mlp2p_bwd(const float* x, const float* gy, const float* W1, const float* b1, const float* W2, const uint16_t* relu_mask, float* gx,
+                  float* gW1, float* gb1, float* gW2, int64_t n, const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream) {
+  FFB_REQUIRE(x && gy && W1 && b1 && W2, "null argument");
+  Mlp2Shape S;
+  FFB_REQUIRE(pipe_shape_ok(K0, H, N, &S), "MLP shape not eligible for the pipelined tensor-core path");
+  if (n <= 0) return FFB_OK;
+  static PerDeviceOnce once;
+  if (once.first()) FFB_CUDA(cudaFuncSetAttribute(mlp2p_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MpbSmem::TOTAL));
+  const int64_t tiles = (n + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  mlp2p_bwd_kernel<<<grid, MPB_THREADS, MpbSmem::TOTAL, (cudaStream_t)stream>>>(x, gy, W1, b1, W2, relu_mask, gx, gW1, gb1, gW2, n, n_dev, S);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+}  // extern "C"

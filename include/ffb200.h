@@ -202,6 +202,10 @@ int ffb_linear_tc_bwd_weight(const float* gy, const float* y, int32_t act, const
  * through the per-layer entry points above.
  * ffb_mlp2_bwd: gx [n,K0] (may be NULL), gW1 [H,K0], gb1 [H], gW2 [N,H] are ACCUMULATED (+=), not zeroed. */
 int ffb_set_fused_mlp(int enabled);
+/* Shapes with K0 <= 31, H == 64, N <= 32 (linear_mat of nerf.yaml) run as pipelined warp-specialised kernels (mlp_pipe.cu:
+ * producer warps -> operand-tile ring -> MMA issuer -> epilogue warps); ffb_set_mlp_pipelined(0) keeps the one-tile-at-a-time kernels. */
+int ffb_set_mlp_pipelined(int enabled);
+int ffb_mlp2_pipelined_eligible(int32_t K0, int32_t H, int32_t N);
 int ffb_mlp2_eligible(int32_t K0, int32_t H, int32_t N);
 int ffb_mlp2_fwd(const float* x, const float* W1, const float* b1, const float* W2, float* y,
                  uint16_t* relu_mask, int64_t n, const int32_t* n_dev, int32_t K0, int32_t H, int32_t N,

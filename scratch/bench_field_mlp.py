@@ -36,11 +36,16 @@ print('fused fwd (training outputs) %.1f us' % timeit(lambda: _fused_fwd(m, x, w
 print('fused fwd (+ row-major rows) %.1f us' % timeit(lambda: _fused_fwd(m, x, want_rows=True)))
 
 lib = nv.lib()
-for nslot in (8, 6, 4):
-    for dbg in (0, 2, 1):
-        lib.ffb_field_mlp_tuning(dbg, nslot)
-        print('nslot %d (gather warps %d) debug %d (1: no gather math, 2: no epilogue work): %.1f us' % (nslot, min(27, 4 * nslot), dbg, timeit(lambda: _fused_fwd(m, x, want_rows=False))), flush=True)
-lib.ffb_field_mlp_tuning(0, 8)
-for cfgk in (1, 3, 0):
-    lib.ffb_set_tuning(b'field_fwd_cfg', cfgk)
-    print('old field fwd cfg %d + mlp2: %.1f us' % (cfgk, timeit(lambda: _separate_fwd(m, x))), flush=True)
+W1, b1, W2 = m.linear_mat.backbone[0].weight, m.linear_mat.backbone[0].bias, m.linear_mat.backbone[1].weight
+n = x.shape[0]
+feats = _separate_fwd(m, x)['feats']
+y = torch.empty(n, 32, device='cuda'); bits = torch.empty(n, 4, device='cuda', dtype=torch.int16)
+gy = torch.randn(n, 32, device='cuda'); gx = torch.empty(n, 18, device='cuda')
+gW1, gb1, gW2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2)
+P = lambda t: C.c_void_p(t.data_ptr())
+for pipelined in (0, 1):
+    lib.ffb_set_mlp_pipelined(pipelined)
+    tf = timeit(lambda: nv.check(lib.ffb_mlp2_fwd(P(feats), P(W1), P(b1), P(W2), P(y), P(bits), C.c_int64(n), None, 18, 64, 32, nv.stream())))
+    tb = timeit(lambda: nv.check(lib.ffb_mlp2_bwd(P(feats), P(gy), P(W1), P(b1), P(W2), P(bits), P(gx), P(gW1), P(gb1), P(gW2), C.c_int64(n), None, 18, 64, 32, nv.stream())))
+    print('linear_mat pipelined=%d: forward %.1f us, backward %.1f us' % (pipelined, tf, tb), flush=True)
+lib.ffb_set_mlp_pipelined(1)

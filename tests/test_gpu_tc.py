@@ -127,6 +127,71 @@ def test_fused_mlp2(K0, H, N, use_ndev):
     assert bool((gx[n:] == 7.0).all())
 
 
+@pytest.mark.parametrize('K0,N,cap,use_ndev,use_bits', [(18, 32, 300077, False, True), (18, 32, 300077, True, True), (18, 32, 130001, False, False),
+                                                        (20, 7, 70001, True, True), (31, 32, 1000, False, True), (5, 1, 129, False, True)])
+def test_pipelined_mlp2_many_tiles(K0, N, cap, use_ndev, use_bits):
+    """The pipelined warp-specialised linear_mat kernels (mlp_pipe.cu) with many tiles per CTA (ring wrap-around, both
+    accumulator buffers, weight gradients resident in TMEM across tiles) against float64; and against the one-tile-at-a-time
+    kernels of mlp_fused.cu on the same inputs."""
+    from ffb200 import native as nv
+    lib = nv.lib()
+    H = 64
+    assert lib.ffb_mlp2_pipelined_eligible(K0, H, N) == 1
+    torch.manual_seed(K0 * 7 + N)
+    n = cap - 1500 if use_ndev else cap
+    if n <= 0:
+        n = cap
+    x = torch.randn(cap, K0, device='cuda')
+    W1 = torch.randn(H, K0, device='cuda') / K0 ** 0.5
+    b1 = torch.randn(H, device='cuda') * 0.3
+    W2 = torch.randn(N, H, device='cuda') / H ** 0.5
+    gy = torch.randn(cap, N, device='cuda')
+    for _ in range(50):
+        near = ((x.double() @ W1.double().T + b1.double()).abs() < 1e-3).any(1)
+        if not bool(near.any()):
+            break
+        x[near] = torch.randn(int(near.sum()), K0, device='cuda')
+    n_dev = torch.tensor([n], device='cuda', dtype=torch.int32) if use_ndev and n != cap else None
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    s = nv.stream()
+    res = {}
+    for pipelined in (1, 0):
+        lib.ffb_set_mlp_pipelined(pipelined)
+        try:
+            if not pipelined and not lib.ffb_mlp2_eligible(K0, H, N):
+                continue
+            y = torch.full((cap, N), 7.0, device='cuda')
+            bits = torch.zeros(cap, H // 16, device='cuda', dtype=torch.int16)
+            nv.check(lib.ffb_mlp2_fwd(P(x), P(W1), P(b1), P(W2), P(y), P(bits), C.c_int64(cap), P(n_dev), K0, H, N, s))
+            gx = torch.full((cap, K0), 7.0, device='cuda')
+            gW1, gb1, gW2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2)
+            nv.check(lib.ffb_mlp2_bwd(P(x), P(gy), P(W1), P(b1), P(W2), P(bits) if use_bits else None, P(gx), P(gW1), P(gb1), P(gW2),
+                                      C.c_int64(cap), P(n_dev), K0, H, N, s))
+            torch.cuda.synchronize()
+            res[pipelined] = (y, bits, gx, gW1, gb1, gW2)
+        finally:
+            lib.ffb_set_mlp_pipelined(1)
+    y, bits, gx, gW1, gb1, gW2 = res[1]
+    xd, gd = x[:n].double(), gy[:n].double()
+    h = torch.relu(xd @ W1.double().T + b1.double())
+    ref = h @ W2.double().T
+    assert float((y[:n].double() - ref).abs().max() / ref.abs().max()) < 3e-6
+    assert bool((y[n:] == 7.0).all()), 'rows beyond the device-side count were written'
+    got_bits = ((bits[:n].int() & 0xffff)[:, :, None] >> torch.arange(16, device='cuda')) & 1
+    assert bool((got_bits.reshape(n, H).bool() == (h > 0)).all()), 'ReLU decision bits'
+    gh = (gd @ W2.double()) * (h > 0)
+    for name, got, want in (('gx', gx[:n], gh @ W1.double()), ('gW1', gW1, gh.T @ xd), ('gb1', gb1, gh.sum(0)), ('gW2', gW2, gd.T @ h)):
+        err = float((got.double() - want).abs().max() / want.abs().max())
+        assert err < 3e-5, (name, err)
+    assert bool((gx[n:] == 7.0).all())
+    if 0 in res:
+        for a, b in zip(res[1], res[0]):
+            if a.dtype == torch.int16:
+                assert torch.equal(a[:n], b[:n])
+            else:
+                assert float((a.double() - b.double())[:n if a.shape[0] == cap else None].abs().max() / b.double().abs().max()) < 3e-5
+
+
 def test_fused_mlp2_matches_per_layer_path():
     """MLPMixer module: fused kernels vs the per-layer tcgen05 kernels on the nerf.yaml linear_mat shape (autograd)."""
     from ffb200 import native as nv
