@@ -17,6 +17,21 @@
 namespace ffb {
 
 constexpr int MP_H = 64, MP_K0P = 32, MP_NP = 32;
+
+// Optional timeline trace (experiment knob ffb_mlp2p_trace): CTA 0 appends (event id, tile, globaltimer ns) triples.
+__device__ long long* g_mp_trace = nullptr;
+__device__ int g_mp_trace_n = 0;
+__device__ __forceinline__ void mp_trace(int ev, long long tile) {
+  long long* buf = g_mp_trace;
+  if (buf && blockIdx.x == 0) {
+    const int k = atomicAdd(&g_mp_trace_n, 1);
+    if (k < 20000) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      buf[3 * k] = ev; buf[3 * k + 1] = tile; buf[3 * k + 2] = (long long)t;
+    }
+  }
+}
 constexpr uint32_t MP_SC = 2048;               // bytes between 8-column chunks of a 128-row tile
 
 template <int TERMS>
@@ -29,10 +44,12 @@ __device__ __forceinline__ void mp_store2(uint8_t* row, uint32_t part_bytes, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// forward:  y = relu([x | 1] [W1 | b1]^T) W2^T      warps: 0..7 epilogue (group = warp >> 2 takes tiles t = group mod 2),
-//                                                          8 layer-1 issuer, 9..20 producers
+// forward:  y = relu([x | 1] [W1 | b1]^T) W2^T
+// warps: 0..6 producers, 7 layer-1 issuer, 8..23 epilogue — group = (warp - 8) >> 3 takes tiles t = group mod 2; inside a group
+// q = warp & 3 is the TMEM lane quarter and half = ((warp - 8) >> 2) & 1 the column half.  (The SM's warp arbiter favours
+// the highest warp ids: the latency-critical epilogue warps sit there, the producers — who mostly wait for a free slot — below.)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int MPF_THREADS = 21 * 32, MPF_NPROD = 12, MPF_NSLOT = 3, MPF_TERMS = 3;
+constexpr int MPF_THREADS = 24 * 32, MPF_NPROD = 7, MPF_ISSUER = 7, MPF_EPI0 = 8, MPF_NSLOT = 3, MPF_TERMS = 3;
 constexpr uint32_t MPF_XPART = 4 * MP_SC, MPF_XSLOT = MPF_TERMS * MPF_XPART;      // 8 KB / 24 KB
 constexpr uint32_t MPF_HPART = 8 * MP_SC, MPF_HBUF = MPF_TERMS * MPF_HPART;       // 16 KB / 48 KB
 struct MpfSmem {
@@ -67,7 +84,7 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
   int* next_chunk = reinterpret_cast<int*>(smem + MpfSmem::MISC + 4);
   const int K0 = S.K0, N = S.N;
 
-  if (warp == 8) tmem_alloc(tmem_slot, 256u);
+  if (warp == MPF_ISSUER) tmem_alloc(tmem_slot, 256u);
   if (tid == 0) {
     for (int s = 0; s < MPF_NSLOT; ++s) {
       mbar_init(slot_full + s, 4);
@@ -75,7 +92,7 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(d1_full + b, 1);
-      mbar_init(d1_free + b, 128);
+      mbar_init(d1_free + b, 256);
       mbar_init(d2_full + b, 1);
     }
     *next_chunk = 0;
@@ -90,7 +107,7 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
   const int64_t n_tiles = (n + 127) >> 7;
   const int64_t Tc = n_tiles > (int64_t)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp >= 9) {
+  if (warp < MPF_NPROD) {
     // ------------------------------ producers: one 32-row chunk at a time, rows prefetched before the slot wait
     const int n_chunks = (int)(4 * Tc);
     const bool vec2 = ((K0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
@@ -123,7 +140,9 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
         for (int c = 0; c < MP_K0P; ++c)
           if (c == K0) v[c] = 1.0f;                 // bias column
       }
+      if (lane == 0) mp_trace(10 + rg, tseq);      // rows loaded
       mbar_wait(slot_free + slot, (uint32_t)(((tseq / MPF_NSLOT) & 1) ^ 1));
+      if (lane == 0) mp_trace(20 + rg, tseq);      // slot free
       const int r = rg * 32 + lane;
       uint8_t* xrow = sX + (uint32_t)slot * MPF_XSLOT + (uint32_t)(r >> 3) * TILE_SR + (uint32_t)(r & 7) * 16u;
 #pragma unroll
@@ -138,63 +157,70 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
       proxy_fence();
       __syncwarp();
       if (lane == 0) mbar_arrive(slot_full + slot);
+      if (lane == 0) mp_trace(30 + rg, tseq);      // chunk delivered
     }
-  } else if (warp == 8) {
+  } else if (warp == MPF_ISSUER) {
     // ------------------------------ layer-1 issuer
     if (lane == 0) {
       const uint32_t idesc1 = make_idesc(MP_H, 0, 0);
-      const uint32_t aW1 = smem_u32(sW1), szW1 = MP_H * MP_K0P * 2, scW1 = MP_H * 16;
+      const DescBase dW1b = desc_base(smem_u32(sW1), MP_H * 16, TILE_SR);
       for (int64_t t = 0; t < Tc; ++t) {
         const int slot = (int)(t % MPF_NSLOT), b = (int)(t & 1);
         mbar_wait(slot_full + slot, (uint32_t)((t / MPF_NSLOT) & 1));
+        mp_trace(40, t);                              // slot full
         mbar_wait(d1_free + b, (uint32_t)(((t >> 1) & 1) ^ 1));
+        mp_trace(41, t);                              // accumulator free
         tc_fence_after();
         const uint32_t aX = smem_u32(sX) + (uint32_t)slot * MPF_XSLOT;
-        issue_gemm<MPF_TERMS>(tmem + (uint32_t)b * MP_H, idesc1, MP_K0P / 16, false,
-                              [&](int tt, int s) { return desc_k(aX + (uint32_t)tt * MPF_XPART, MP_SC, s); },
-                              [&](int tt, int s) { return desc_k(aW1 + (uint32_t)tt * szW1, scW1, s); });
+        // A = x tile (K-major: K slice = 2 chunks), B = [W1|b1] tile (K-major, chunk stride H*16)
+        issue_gemm_c<MPF_TERMS, MP_K0P / 16, MPF_XPART, 2 * MP_SC, MP_H * MP_K0P * 2, 2 * MP_H * 16, false>(
+            tmem + (uint32_t)b * MP_H, idesc1, desc_base(aX, MP_SC, TILE_SR), dW1b);
         umma_commit(slot_free + slot);
         umma_commit(d1_full + b);
+        mp_trace(42, t);                              // layer 1 issued
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue: group g handles tiles g, g+2, ...
-    const int g = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    // ------------------------------ epilogue: group g handles tiles g, g+2, ...; a thread owns one row and one column half
+    const int ew = warp - MPF_EPI0, g = ew >> 3, half = (ew >> 2) & 1, q = warp & 3, row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t d1 = tmem + (uint32_t)g * MP_H, d2 = tmem + 2u * MP_H + (uint32_t)g * MP_NP;
     const uint32_t idesc2 = make_idesc(MP_NP, 0, 0);
     uint8_t* myH = sH + (uint32_t)g * MPF_HBUF;
-    const uint32_t aH = smem_u32(myH), aW2 = smem_u32(sW2), szW2 = MP_NP * MP_H * 2, scW2 = MP_NP * 16;
+    const DescBase dHb = desc_base(smem_u32(myH), MP_SC, TILE_SR), dW2b = desc_base(smem_u32(sW2), MP_NP * 16, TILE_SR);
+    const bool tr = half == 0 && q == 0 && lane == 0;
     auto epi2 = [&](int64_t t, int64_t k) {
+      if (tr) mp_trace(50, t);
       mbar_wait(d2_full + g, (uint32_t)(k & 1));
+      if (tr) mp_trace(51, t);                        // layer 2 complete
       tc_fence_after();
       const int64_t grow = (((int64_t)blockIdx.x + t * gridDim.x) << 7) + row;
+      const int c0 = half * 16;
+      float v[16];
+      tmem_ld16(d2 + lane_base + (uint32_t)c0, v);
+      if (grow < n) {
+        float* yr = y + grow * N + c0;
+        if ((N & 3) == 0 && c0 + 16 <= N) {
 #pragma unroll
-      for (int c0 = 0; c0 < MP_NP; c0 += 16) {
-        float v[16];
-        tmem_ld16(d2 + lane_base + (uint32_t)c0, v);
-        if (grow < n) {
-          float* yr = y + grow * N + c0;
-          if ((N & 3) == 0 && c0 + 16 <= N) {
+          for (int k2 = 0; k2 < 16; k2 += 4) *reinterpret_cast<float4*>(yr + k2) = make_float4(v[k2], v[k2 + 1], v[k2 + 2], v[k2 + 3]);
+        } else {
 #pragma unroll
-            for (int k2 = 0; k2 < 16; k2 += 4) *reinterpret_cast<float4*>(yr + k2) = make_float4(v[k2], v[k2 + 1], v[k2 + 2], v[k2 + 3]);
-          } else {
-#pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2)
-              if (c0 + k2 < N) yr[k2] = v[k2];
-          }
+          for (int k2 = 0; k2 < 16; ++k2)
+            if (c0 + k2 < N) yr[k2] = v[k2];
         }
       }
     };
     int64_t k = 0;
     for (int64_t t = g; t < Tc; t += 2, ++k) {
       if (k > 0) epi2(t - 2, k - 1);          // also: layer 2 of this group's previous tile has finished reading the hidden tile
+      if (tr) mp_trace(52, t);                        // epilogue 2 done
       mbar_wait(d1_full + g, (uint32_t)(k & 1));
+      if (tr) mp_trace(53, t);                        // layer 1 complete
       tc_fence_after();
       const int64_t grow = (((int64_t)blockIdx.x + t * gridDim.x) << 7) + row;
 #pragma unroll
-      for (int c0 = 0; c0 < MP_H; c0 += 16) {
+      for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 16) {
         float v[16];
         tmem_ld16(d1 + lane_base + (uint32_t)c0, v);
         uint32_t bits = 0;
@@ -204,17 +230,18 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
           v[i2] = fmaxf(v[i2], 0.0f);
         }
         if (mask && grow < n) mask[grow * (MP_H >> 4) + (c0 >> 4)] = (uint16_t)bits;
-        store_row8<MPF_TERMS>(myH, MPF_HPART, MP_SC, row, c0, v);
-        store_row8<MPF_TERMS>(myH, MPF_HPART, MP_SC, row, c0 + 8, v + 8);
+        store_row8_trunc<MPF_TERMS>(myH, MPF_HPART, MP_SC, row, c0, v);
+        store_row8_trunc<MPF_TERMS>(myH, MPF_HPART, MP_SC, row, c0 + 8, v + 8);
       }
       tc_fence_before();
       mbar_arrive(d1_free + g);
       proxy_fence();
-      named_sync(1 + g, 128);
-      if (q == 0 && lane == 0) {
+      if (tr) mp_trace(54, t);                        // epilogue 1 done (this thread)
+      named_sync(1 + g, 256);
+      if (half == 0 && q == 0 && lane == 0) {
+        mp_trace(55, t);                              // group synchronised
         tc_fence_after();
-        issue_gemm<MPF_TERMS>(d2, idesc2, MP_H / 16, false, [&](int tt, int s) { return desc_k(aH + (uint32_t)tt * MPF_HPART, MP_SC, s); },
-                              [&](int tt, int s) { return desc_k(aW2 + (uint32_t)tt * szW2, scW2, s); });
+        issue_gemm_c<MPF_TERMS, MP_H / 16, MPF_HPART, 2 * MP_SC, MP_NP * MP_H * 2, 2 * MP_NP * 16, false>(d2, idesc2, dHb, dW2b);
         umma_commit(d2_full + g);
       }
     }
@@ -222,7 +249,7 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 256u);
+  if (warp == MPF_ISSUER) tmem_dealloc(tmem, 256u);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -231,9 +258,9 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
 //   epilogue 1: ReLU decisions (forward's bits) -> A2
 //   stage 2 (issued by the epilogue):   D3 = GH W1 (g_x)   DW += A2^T B2  (gW2^T and [gW1|gb1], resident in TMEM)
 //   epilogue 2 (of the PREVIOUS tile, under stage 2 of this one): g_x tile -> fp32 staging -> coalesced stores
-// warps: 0..7 epilogue (q = warp & 3 lane quarter, half = warp >> 2 column half), 8 stage-1 issuer, 9..16 producers
+// warps: 0..6 producers, 7 stage-1 issuer, 8..23 epilogue (q = warp & 3 lane quarter, cq = (warp - 8) >> 2 column quarter)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int MPB_THREADS = 17 * 32, MPB_NPROD = 8, MPB_NSLOT = 3, MPB_TERMS = 2;
+constexpr int MPB_THREADS = 24 * 32, MPB_NPROD = 7, MPB_ISSUER = 7, MPB_EPI0 = 8, MPB_NEPI = 512, MPB_NSLOT = 3, MPB_TERMS = 2;
 constexpr uint32_t MPB_BPART = 8 * MP_SC, MPB_BSLOT = MPB_TERMS * MPB_BPART;      // 16 KB / 32 KB
 constexpr uint32_t MPB_APART = 16 * MP_SC, MPB_ABUF = MPB_TERMS * MPB_APART;      // 32 KB / 64 KB
 struct MpbSmem {
@@ -274,7 +301,7 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
   constexpr uint32_t offX = (uint32_t)(MP_NP / 8) * MP_SC, offGH = (uint32_t)(MP_H / 8) * MP_SC;      // x inside B2, g_h inside A2
   constexpr int NB2 = MP_NP + MP_K0P;
 
-  if (warp == 8) tmem_alloc(tmem_slot, 512u);
+  if (warp == MPB_ISSUER) tmem_alloc(tmem_slot, 512u);
   if (tid == 0) {
     for (int s = 0; s < MPB_NSLOT; ++s) {
       mbar_init(slot_full + s, 4);
@@ -282,7 +309,7 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(d12_full + b, 1);
-      mbar_init(d12_free + b, 256);
+      mbar_init(d12_free + b, MPB_NEPI);
     }
     mbar_init(cd_full, 1);
     *next_chunk = 0;
@@ -300,7 +327,7 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
   const uint32_t szW1 = (uint32_t)H * MP_K0P * 2, szW2 = (uint32_t)MP_NP * H * 2, scW1 = (uint32_t)H * 16, scW2 = (uint32_t)MP_NP * 16;
   const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aA2 = smem_u32(sA2);
 
-  if (warp >= 9) {
+  if (warp < MPB_NPROD) {
     // ------------------------------ producers
     const int n_chunks = (int)(4 * Tc);
     const bool vecX = ((K0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
@@ -370,57 +397,57 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
       __syncwarp();
       if (lane == 0) mbar_arrive(slot_full + slot);
     }
-  } else if (warp == 8) {
+  } else if (warp == MPB_ISSUER) {
     // ------------------------------ stage-1 issuer: D1 = X [W1|b1]^T (hidden pre-activation), D2 = GY W2
     if (lane == 0) {
       const uint32_t id_h = make_idesc(H, 0, 0), id_gh = make_idesc(H, 0, 1);
+      const DescBase dW1k = desc_base(aW1, MP_H * 16, TILE_SR), dW2mn = desc_base(aW2, TILE_SR, MP_NP * 16);
       for (int64_t t = 0; t < Tc; ++t) {
         const int slot = (int)(t % MPB_NSLOT), b = (int)(t & 1);
         mbar_wait(slot_full + slot, (uint32_t)((t / MPB_NSLOT) & 1));
         mbar_wait(d12_free + b, (uint32_t)(((t >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t aB2 = smem_u32(sB2) + (uint32_t)slot * MPB_BSLOT;
-        issue_gemm<MPB_TERMS>(tmem + (uint32_t)b * H, id_h, MP_K0P / 16, false,
-                              [&](int tt, int s) { return desc_k(aB2 + offX + (uint32_t)tt * MPB_BPART, MP_SC, s); },
-                              [&](int tt, int s) { return desc_k(aW1 + (uint32_t)tt * szW1, scW1, s); });
-        issue_gemm<MPB_TERMS>(tmem + 128u + (uint32_t)b * H, id_gh, MP_NP / 16, false,
-                              [&](int tt, int s) { return desc_k(aB2 + (uint32_t)tt * MPB_BPART, MP_SC, s); },
-                              [&](int tt, int s) { return desc_mn(aW2 + (uint32_t)tt * szW2, scW2, s); });
+        issue_gemm_c<MPB_TERMS, MP_K0P / 16, MPB_BPART, 2 * MP_SC, MP_H * MP_K0P * 2, 2 * MP_H * 16, false>(
+            tmem + (uint32_t)b * H, id_h, desc_base(aB2 + offX, MP_SC, TILE_SR), dW1k);                       // D1 = X [W1|b1]^T
+        issue_gemm_c<MPB_TERMS, MP_NP / 16, MPB_BPART, 2 * MP_SC, MP_NP * MP_H * 2, 2 * TILE_SR, false>(
+            tmem + 128u + (uint32_t)b * H, id_gh, desc_base(aB2, MP_SC, TILE_SR), dW2mn);                     // D2 = GY W2 (W2 tile read MN-major)
         umma_commit(d12_full + b);
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue (256 threads): row = lane quarter * 32 + lane, columns of half = warp >> 2
-    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane, etid = tid;          // etid in [0, 256)
+    // ------------------------------ epilogue (512 threads): row = lane quarter * 32 + lane, 16 hidden columns of quarter cq
+    const int q = warp & 3, cq = (warp - MPB_EPI0) >> 2, row = q * 32 + lane, etid = tid - MPB_EPI0 * 32;          // etid in [0, 512)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t dW = tmem + 320u;
     const uint32_t id_gx = make_idesc(MP_K0P, 0, 1), id_w = make_idesc(NB2, 1, 1, 128);
+    const DescBase dGHk = desc_base(aA2 + offGH, MP_SC, TILE_SR), dW1mn = desc_base(aW1, TILE_SR, MP_H * 16), dA2mn = desc_base(aA2, TILE_SR, MP_SC);
     auto epi2 = [&](int64_t t) {       // g_x rows of tile t: D3[t & 1] -> staging -> coalesced 16-byte stores
       const uint32_t d3 = tmem + 256u + (uint32_t)(t & 1) * MP_K0P;
       const int64_t row0 = ((int64_t)blockIdx.x + t * gridDim.x) << 7;
-      if (gx) {
+      if (gx && cq < 2) {
         float v[16];
-        tmem_ld16(d3 + lane_base + (uint32_t)(half * 16), v);
+        tmem_ld16(d3 + lane_base + (uint32_t)(cq * 16), v);
 #pragma unroll
         for (int i2 = 0; i2 < 16; ++i2)
-          if (half * 16 + i2 < K0) stg[row * K0 + half * 16 + i2] = v[i2];
+          if (cq * 16 + i2 < K0) stg[row * K0 + cq * 16 + i2] = v[i2];
       }
       tc_fence_before();
-      named_sync(2, 256);
+      named_sync(2, MPB_NEPI);
       if (gx) {
         const int64_t rows = (n - row0) < 128 ? (n - row0) : 128;
         const int64_t total = rows > 0 ? rows * K0 : 0;
         float* dst = gx + row0 * K0;
         if (((row0 * K0) & 3) == 0 && (reinterpret_cast<uintptr_t>(gx) & 15) == 0) {
           const int64_t n4 = total >> 2;
-          for (int64_t e = etid; e < n4; e += 256) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(stg)[e];
-          for (int64_t e = (n4 << 2) + etid; e < total; e += 256) dst[e] = stg[e];
+          for (int64_t e = etid; e < n4; e += MPB_NEPI) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(stg)[e];
+          for (int64_t e = (n4 << 2) + etid; e < total; e += MPB_NEPI) dst[e] = stg[e];
         } else {
-          for (int64_t e = etid; e < total; e += 256) dst[e] = stg[e];
+          for (int64_t e = etid; e < total; e += MPB_NEPI) dst[e] = stg[e];
         }
       }
-      named_sync(2, 256);              // staging free again
+      named_sync(2, MPB_NEPI);         // staging free again
     };
     for (int64_t t = 0; t < Tc; ++t) {
       const int slot = (int)(t % MPB_NSLOT), b = (int)(t & 1);
@@ -432,8 +459,8 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
       tc_fence_after();
       const int64_t grow = (((int64_t)blockIdx.x + t * gridDim.x) << 7) + row;
       const uint32_t d1 = tmem + (uint32_t)b * H, d2 = tmem + 128u + (uint32_t)b * H;
-#pragma unroll
-      for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 16) {
+      {
+        const int c0 = cq * 16;
         float h[16], g[16];
         tmem_ld16(d1 + lane_base + (uint32_t)c0, h);
         tmem_ld16(d2 + lane_base + (uint32_t)c0, g);
@@ -460,15 +487,15 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
       tc_fence_before();
       mbar_arrive(d12_free + b);
       proxy_fence();
-      named_sync(1, 256);
-      if (tid == 0) {
+      named_sync(1, MPB_NEPI);
+      if (etid == 0) {
         tc_fence_after();
         const uint32_t aB2 = smem_u32(sB2) + (uint32_t)slot * MPB_BSLOT;
-        issue_gemm<MPB_TERMS>(tmem + 256u + (uint32_t)b * MP_K0P, id_gx, H / 16, false,
-                              [&](int tt, int s) { return desc_k(aA2 + offGH + (uint32_t)tt * MPB_APART, MP_SC, s); },
-                              [&](int tt, int s) { return desc_mn(aW1 + (uint32_t)tt * szW1, scW1, s); });
-        issue_gemm<MPB_TERMS>(dW, id_w, 8, t > 0, [&](int tt, int s) { return desc_mn(aA2 + (uint32_t)tt * MPB_APART, MP_SC, s); },
-                              [&](int tt, int s) { return desc_mn(aB2 + (uint32_t)tt * MPB_BPART, MP_SC, s); });
+        issue_gemm_c<MPB_TERMS, MP_H / 16, MPB_APART, 2 * MP_SC, MP_H * MP_K0P * 2, 2 * TILE_SR, false>(
+            tmem + 256u + (uint32_t)b * MP_K0P, id_gx, dGHk, dW1mn);                                          // D3 = GH W1 (W1 tile read MN-major)
+        const DescBase dB2mn = desc_base(aB2, TILE_SR, MP_SC);
+        if (t > 0) issue_gemm_c<MPB_TERMS, 8, MPB_APART, 2 * TILE_SR, MPB_BPART, 2 * TILE_SR, true>(dW, id_w, dA2mn, dB2mn);   // DW += A2^T B2
+        else issue_gemm_c<MPB_TERMS, 8, MPB_APART, 2 * TILE_SR, MPB_BPART, 2 * TILE_SR, false>(dW, id_w, dA2mn, dB2mn);
         umma_commit(slot_free + slot);
         umma_commit(cd_full);
       }
@@ -480,7 +507,8 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
       epi2(Tc - 1);
       // ---- flush the weight gradients: accumulator row m (M = 128): m < 64 -> gW2^T row j = m; m >= 64 -> [gW1 | gb1] row j = m - 64
       const int m = row;
-      for (int c0 = half * 16; c0 < NB2; c0 += 32) {
+      {
+        const int c0 = cq * 16;        // NB2 = 64 accumulator columns: one 16-column group per column quarter
         float v[16];
         tmem_ld16(dW + lane_base + (uint32_t)c0, v);
 #pragma unroll
@@ -500,7 +528,7 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512u);
+  if (warp == MPB_ISSUER) tmem_dealloc(tmem, 512u);
 }
 
 static int g_pipe_enabled = 1;
@@ -516,6 +544,14 @@ static bool pipe_shape_ok(int K0, int H, int N, Mlp2Shape* S) {
 using namespace ffb;
 
 extern "C" {
+
+/* experiment knob: device buffer of 60000 int64 for the timeline trace of CTA 0 (NULL switches it off) */
+int ffb_mlp2p_trace(long long* d_buf) {
+  int zero = 0;
+  FFB_CUDA(cudaMemcpyToSymbol(g_mp_trace, &d_buf, sizeof(d_buf)));
+  FFB_CUDA(cudaMemcpyToSymbol(g_mp_trace_n, &zero, sizeof(zero)));
+  return FFB_OK;
+}
 
 int ffb_set_mlp_pipelined(int enabled) {
   g_pipe_enabled = enabled ? 1 : 0;

@@ -65,6 +65,33 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Cheap MMA issue.  A timeline trace of the pipelined kernels (scratch/trace_mlp2p.py) showed the ISSUE of the MMAs — one thread
+// rebuilding two 64-bit descriptors per instruction — to be the pipeline's bottleneck (~170 cycles per tcgen05.mma, 36 per
+// tile).  A descriptor of a fixed layout differs between the MMAs of a tile only in its 14-bit start-address field, so the
+// base is built once and each MMA adds a compile-time constant to the low word.
+struct DescBase {
+  uint32_t lo, hi;
+};
+__device__ __forceinline__ DescBase desc_base(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  DescBase d;
+  d.lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+  d.hi = (sbo >> 4) | (1u << 14);       // bit 46 of the descriptor: version 1 (Blackwell)
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_at(const DescBase d, uint32_t byte_off) {
+  return ((uint64_t)d.hi << 32) | (uint64_t)(d.lo + (byte_off >> 4));
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{ .reg .pred p; setp.eq.u32 p, 1, 1; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc)
+                 : "memory");
+  else
+    asm volatile("{ .reg .pred p; setp.eq.u32 p, 1, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc)
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -123,6 +150,30 @@ __device__ __forceinline__ void split8_packed(const float x[8], uint4 out[TERMS]
   uint32_t w[4][TERMS];
 #pragma unroll
   for (int i = 0; i < 4; ++i) split2_packed<TERMS>(x[2 * i], x[2 * i + 1], w[i]);
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) out[t] = make_uint4(w[0][t], w[1][t], w[2][t], w[3][t]);
+}
+
+// Truncating variant: each part takes the top 16 bits of the running residual (PRMT, no F2FP conversion).  With three parts
+// the decomposition of a normal fp32 value is EXACT (8 + 8 + 8 significant bits); with fewer parts the residual is up to
+// twice that of the round-to-nearest split, so the gradient kernels (2 parts) keep split2_packed.
+template <int TERMS>
+__device__ __forceinline__ void split2_trunc(float a, float b, uint32_t out[TERMS]) {
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+    const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+    out[t] = __byte_perm(ua, ub, 0x7632);        // low half = high 16 bits of a, high half = high 16 bits of b
+    if (t + 1 < TERMS) {
+      a -= __uint_as_float(ua & 0xffff0000u);
+      b -= __uint_as_float(ub & 0xffff0000u);
+    }
+  }
+}
+template <int TERMS>
+__device__ __forceinline__ void split8_trunc(const float x[8], uint4 out[TERMS]) {
+  uint32_t w[4][TERMS];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split2_trunc<TERMS>(x[2 * i], x[2 * i + 1], w[i]);
 #pragma unroll
   for (int t = 0; t < TERMS; ++t) out[t] = make_uint4(w[0][t], w[1][t], w[2][t], w[3][t]);
 }

@@ -75,6 +75,16 @@ __device__ __forceinline__ void tile_store(float2 v[NB], uint8_t* dst, uint32_t 
   }
 }
 
+// thread-per-row store of 8 consecutive columns (c0 % 8 == 0) of an activation tile, truncating split (exact with 3 parts)
+template <int TERMS>
+__device__ __forceinline__ void store_row8_trunc(uint8_t* dst, uint32_t part_bytes, uint32_t sc, int r, int c0, const float v[8]) {
+  uint4 parts[TERMS];
+  split8_trunc<TERMS>(v, parts);
+  uint8_t* p = dst + (uint32_t)(c0 >> 3) * sc + (uint32_t)(r >> 3) * TILE_SR + (uint32_t)(r & 7) * 16u;
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint4*>(p + (uint32_t)t * part_bytes) = parts[t];
+}
+
 // thread-per-row store of 8 consecutive columns (c0 % 8 == 0) of an activation tile
 template <int TERMS>
 __device__ __forceinline__ void store_row8(uint8_t* dst, uint32_t part_bytes, uint32_t sc, int r, int c0, const float v[8]) {
@@ -97,6 +107,24 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t idesc, int 
         if (ta + tb >= TERMS) continue;
         umma_f16(tmem_d, da(ta, s), db(tb, s), idesc, acc);
         acc = 1u;
+      }
+  }
+}
+
+// The same with every address offset a compile-time constant: operand tiles whose parts are A_PART / B_PART bytes apart and
+// whose K = 16 slices are A_KSTEP / B_KSTEP bytes apart.  FIRST_ACC = false overwrites the accumulator with the first MMA.
+template <int TERMS, int KSLICES, uint32_t A_PART, uint32_t A_KSTEP, uint32_t B_PART, uint32_t B_KSTEP, bool FIRST_ACC>
+__device__ __forceinline__ void issue_gemm_c(uint32_t tmem_d, uint32_t idesc, const DescBase a, const DescBase b) {
+#pragma unroll
+  for (int s = 0; s < KSLICES; ++s) {
+#pragma unroll
+    for (int ta = 0; ta < TERMS; ++ta)
+#pragma unroll
+      for (int tb = 0; tb < TERMS; ++tb) {
+        if (ta + tb >= TERMS) continue;
+        const uint64_t da = desc_at(a, (uint32_t)ta * A_PART + (uint32_t)s * A_KSTEP), db = desc_at(b, (uint32_t)tb * B_PART + (uint32_t)s * B_KSTEP);
+        if (s == 0 && ta == 0 && tb == 0 && !FIRST_ACC) umma_f16_c<false>(tmem_d, da, db, idesc);
+        else umma_f16_c<true>(tmem_d, da, db, idesc);
       }
   }
 }
