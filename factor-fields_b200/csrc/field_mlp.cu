@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFw
     // idle (experiment configurations with fewer gather warps)
   } else if (warp == FM_MMA_WARP) {
     // =================================== layer-1 issuer ===================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc1 = make_idesc(FM_H, 0, 0);
       const uint32_t aW1 = smem_u32(sW1), aZero = smem_u32(smem + FmSmem::ZERO);
       const uint32_t szW1 = FM_H * FM_K0P * 2, scW1 = FM_H * 16;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) field_mlp_fwd_kernel(const FmFw
       mbar_arrive(d1_free + b);
       proxy_fence();
       named_sync(1, 128);
-      if (warp == FM_EPI_WARP0 && lane == 0) {
+      if (warp == FM_EPI_WARP0 && elect_one()) {
         tc_fence_after();
         issue_gemm<FM_TERMS>(d2, idesc2, FM_H / 16, false, [&](int tt, int s) { return desc_k(aH + (uint32_t)tt * FM_HPART, FM_SC, s); },
                              [&](int tt, int s) { return desc_k(aW2 + (uint32_t)tt * szW2, scW2, s); });

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, 3) mlp2_fwd_kernel(const float* __restric
     proxy_fence();
     __syncthreads();
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
         issue_gemm<TERMS>(d1, idesc1, S.K0p / 16, false, [&](int t, int s) { return desc_k(aX + t * szX, 2048u, s); },
                           [&](int t, int s) { return desc_k(aW1 + t * szW1, scW1, s); });
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256, 3) mlp2_fwd_kernel(const float* __restric
     proxy_fence();
     __syncthreads();
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
         issue_gemm<TERMS>(d2, idesc2, S.H / 16, false, [&](int t, int s) { return desc_k(aH + t * szH, 2048u, s); },
                           [&](int t, int s) { return desc_k(aW2 + t * szW2, scW2, s); });
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 2) mlp2_bwd_kernel(const float* __restric
     proxy_fence();
     __syncthreads();
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
         issue_gemm<TERMS>(d1, id_h, S.K0p / 16, false, [&](int t, int s) { return desc_k(aB2 + offX + t * szB2, 2048u, s); },
                           [&](int t, int s) { return desc_k(aW1 + t * szW1, scW1, s); });
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 2) mlp2_bwd_kernel(const float* __restric
     proxy_fence();
     __syncthreads();
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
         issue_gemm<TERMS>(d3, id_gx, H / 16, false, [&](int t, int s) { return desc_k(aA2 + offGH + t * szA2, 2048u, s); },
                           [&](int t, int s) { return desc_mn(aW1 + t * szW1, scW1, s); });

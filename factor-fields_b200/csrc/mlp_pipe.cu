@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
     }
   } else if (warp == MPF_ISSUER) {
     // ------------------------------ layer-1 issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc1 = make_idesc(MP_H, 0, 0);
       const DescBase dW1b = desc_base(smem_u32(sW1), MP_H * 16, TILE_SR);
       for (int64_t t = 0; t < Tc; ++t) {
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
       proxy_fence();
       if (tr) mp_trace(54, t);                        // epilogue 1 done (this thread)
       named_sync(1 + g, 256);
-      if (half == 0 && q == 0 && lane == 0) {
+      if (half == 0 && q == 0 && elect_one()) {
         mp_trace(55, t);                              // group synchronised
         tc_fence_after();
         issue_gemm_c<MPF_TERMS, MP_H / 16, MPF_HPART, 2 * MP_SC, MP_NP * MP_H * 2, 2 * MP_NP * 16, false>(d2, idesc2, dHb, dW2b);
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
     }
   } else if (warp == MPB_ISSUER) {
     // ------------------------------ stage-1 issuer: D1 = X [W1|b1]^T (hidden pre-activation), D2 = GY W2
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t id_h = make_idesc(H, 0, 0), id_gh = make_idesc(H, 0, 1);
       const DescBase dW1k = desc_base(aW1, MP_H * 16, TILE_SR), dW2mn = desc_base(aW2, TILE_SR, MP_NP * 16);
       for (int64_t t = 0; t < Tc; ++t) {
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
       mbar_arrive(d12_free + b);
       proxy_fence();
       named_sync(1, MPB_NEPI);
-      if (etid == 0) {
+      if (warp == MPB_EPI0 && elect_one()) {
         tc_fence_after();
         const uint32_t aB2 = smem_u32(sB2) + (uint32_t)slot * MPB_BSLOT;
         issue_gemm_c<MPB_TERMS, MP_H / 16, MPB_APART, 2 * MP_SC, MP_H * MP_K0P * 2, 2 * TILE_SR, false>(

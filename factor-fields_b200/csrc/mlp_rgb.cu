@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
 
   if (warp == RGB_WORKERS / 32 + 1) {
     // ---------------- producer: W3 once, then the same (W1, W2) slice sequence for every tile of this CTA
-    if (lane == 0 && (int64_t)blockIdx.x < n_tiles) {
+    if ((int64_t)blockIdx.x < n_tiles && elect_one()) {
       mbar_expect_tx(w3_full, 3 * RGB_W3_PART);
       bulk_g2s(sW3, a.wpack + (size_t)n_slices * RGB_SLOT, 3 * RGB_W3_PART, w3_full);   // == wpack + fwd bytes - W3 tile
       // Every CTA walks the K slices of a layer in its own rotation (the sum over slices is order-free): the 148 CTAs run
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(RGB_THREADS, 1) rgb_fwd_kernel(const RgbFwdArg
     }
   } else if (warp == RGB_WORKERS / 32) {
     // ---------------- MMA issuer
-    if (lane == 0 && (int64_t)blockIdx.x < n_tiles) {
+    if ((int64_t)blockIdx.x < n_tiles && elect_one()) {
       const uint32_t aA = smem_u32(sA), aRing = smem_u32(sRing), aW3 = smem_u32(sW3);
       const uint32_t idH = make_idesc(RGB_H, 0, 0), id3 = make_idesc(16, 0, 0);
       uint32_t seq = 0, ph_a = 0;
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(RGB_B_THREADS, 1) rgb_bwd_kernel(const RgbBwdA
 
   if (warp == RGB_B_WORKERS / 32 + 1) {
     // ---------------- producer: 48 ring items per tile, in the order the MMA warp consumes them
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t seq = 0;
       auto put = [&](const uint8_t* src, uint32_t bytes) {
         const uint32_t slot = seq % RGB_B_NSLOT, use = seq / RGB_B_NSLOT;
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(RGB_B_THREADS, 1) rgb_bwd_kernel(const RgbBwdA
     }
   } else if (warp == RGB_B_WORKERS / 32) {
     // ---------------- MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t aG = smem_u32(sG), aG3 = smem_u32(sG3), aOnes = smem_u32(sOnes), aRing = smem_u32(sRing);
       const uint32_t id_gh = make_idesc(RGB_H, 0, 0);          // scratch = G (K-major) x W^T slice (K-major)
       const uint32_t id_gxb = make_idesc(nb, 0, 0);

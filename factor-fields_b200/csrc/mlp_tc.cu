@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(512) tc_gemm_rows_kernel(const float* __restri
       __syncthreads();
       if (warp == 0) {        // whole warp enters; lane 0 issues, the others wait at __syncwarp (not inside try_wait, which
                               // would suspend the warp and delay the issuing lane)
-        if (lane == 0) {
+        if (elect_one()) {
         tc_fence_after();
         const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
         for (int ks = 0; ks < kc / 16; ++ks) {
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(512) tc_wgrad_kernel(const float* __restrict__
     proxy_fence();
     __syncthreads();
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
       tc_fence_after();
       const uint32_t gB = smem_u32(sG), xB = smem_u32(sX);
       for (int ks = 0; ks < 8; ++ks) {                        // 128 rows = 8 slices of K = 16

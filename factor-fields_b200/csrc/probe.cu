@@ -42,3 +42,57 @@ int ffb_probe_red(float* buf, int64_t n_floats, int32_t blocks, int32_t iters, i
 }
 
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05.mma issue / execution rate as a function of N (M = 128, K = 16, bf16, SWIZZLE_NONE operands in shared memory):
+// one elected thread per CTA issues `count` accumulating MMAs back to back, commits and waits; cycles by clock64.
+// The MLPs of this path are made of small-N MMAs (N = 32 / 64 / 128), so this — not the dense peak — is their roofline.
+// ---------------------------------------------------------------------------------------------------------
+#include "tc_common.cuh"
+namespace ffb {
+__global__ void __launch_bounds__(128) mma_probe_kernel(int n_cols, int count, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t o = threadIdx.x * 16u; o < 64u * 1024u; o += 128u * 16u) *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tmem_alloc(&tmem_slot, 256u);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(n_cols, 0, 0);
+      const DescBase a = desc_base(smem_u32(smem), 2048u, 128u), b = desc_base(smem_u32(smem) + 32768u, 4096u, 128u);
+      const long long t0 = clock64();
+      for (int i = 0; i < count; i += 4) {
+        umma_f16_c<true>(tmem, desc_at(a, 0), desc_at(b, 0), idesc);
+        umma_f16_c<true>(tmem, desc_at(a, 4096), desc_at(b, 8192), idesc);
+        umma_f16_c<true>(tmem, desc_at(a, 8192), desc_at(b, 0), idesc);
+        umma_f16_c<true>(tmem, desc_at(a, 12288), desc_at(b, 8192), idesc);
+      }
+      const long long t1 = clock64();
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256u);
+}
+}  // namespace ffb
+
+extern "C" int ffb_probe_mma(int32_t n_cols, int32_t count, long long* d_out, void* stream) {
+  FFB_REQUIRE(n_cols >= 16 && n_cols <= 256 && (n_cols % 16) == 0 && count > 0 && d_out, "bad argument");
+  static ffb::PerDeviceOnce once;
+  if (once.first()) FFB_CUDA(cudaFuncSetAttribute(ffb::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  ffb::mma_probe_kernel<<<ffb::sm_count(), 128, 64 * 1024, (cudaStream_t)stream>>>(n_cols, count, d_out);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}

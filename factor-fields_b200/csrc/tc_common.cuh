@@ -16,6 +16,16 @@
 
 namespace ffb {
 
+// One lane of a CONVERGED warp (elect.sync).  The tensor-core / TMA instructions are warp-uniform in SASS (UTCHMMA, UBLKCP, UTCBAR):
+// inside an `if (lane == 0)` branch nvcc cannot prove that and wraps EVERY such instruction in an ELECT / BRA.U.ANY waterfall
+// loop (~150 cycles per MMA, measured: the issue rate, not the tensor pipe, bounded every MLP kernel); behind elect.sync it
+// emits them back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

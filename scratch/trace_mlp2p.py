@@ -21,7 +21,7 @@ t0 = ev[:, 2].min()
 names = {40: 'I slot_full', 41: 'I acc_free', 42: 'I issued', 50: 'E epi2 start', 51: 'E L2 complete', 52: 'E epi2 done', 53: 'E L1 complete', 54: 'E epi1 done', 55: 'E synced'}
 rows = sorted((int(e[2] - t0), int(e[1]), int(e[0])) for e in ev)
 for t, tile, e in rows:
-    if 8 <= tile <= 13:
+    if 20 <= tile <= 23 and e >= 40:
         nm = names.get(e, ('P%d loaded' % (e - 10)) if e < 20 else ('P%d slot_free' % (e - 20)) if e < 30 else ('P%d delivered' % (e - 30)))
         print(f'{t:8d} ns  tile {tile:3d}  {nm}')
 print('events', len(rows), 'span us', (ev[:, 2].max() - t0) / 1e3)
