@@ -57,6 +57,30 @@ def _grad_like(t):
     return torch.zeros_like(t)   # preserve_format keeps the channels-last strides
 
 
+# Two-phase field backward (train.TrainStep under data parallelism): while `_field_bwd_split` is a dict, FieldQuery.backward
+# scatters only into the tensors whose data_ptr is NOT in split['late'] and stashes the launch arguments; the caller runs
+# `field_bwd_deferred()` later (a second CUDA graph) for the rest.  The early gradients — the fine basis levels, 15 of the
+# 21 MB at nerf.yaml — can then be all-reduced while the late scatter (coefficients + coarse levels) is still running.
+_field_bwd_split = None
+
+
+def set_field_bwd_split(split):
+    global _field_bwd_split
+    _field_bwd_split = split
+
+
+def field_bwd_deferred():
+    """Launch the stashed second phase of the field backward (no-op when nothing was deferred)."""
+    sp = _field_bwd_split
+    if not sp or not sp.get('stash'):
+        return
+    for plan, x, n, n_dev, gf, gc, coeff, basis, arr in sp['stash']:
+        with nv.section('field_bwd'):
+            nv.check(nv.lib().ffb_field_query_bwd_saved(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(n_dev), nv.ptr(gf, allow_none=True),
+                                                        nv.ptr(gc, allow_none=True), nv.ptr(coeff, allow_none=True),
+                                                        nv.ptr(basis, allow_none=True), arr, nv.stream()))
+
+
 def _empty(shape, like, dtype=torch.float32):
     return torch.empty(shape, device=like.device, dtype=dtype)
 
@@ -203,6 +227,16 @@ class FieldQuery(torch.autograd.Function):
         if n > 0 and any(g is not None for g in grads):
             gf = g_feats.contiguous() if g_feats is not None else None
             gc = g_coeff.contiguous() if g_coeff is not None else None
+            sp = _field_bwd_split
+            if sp is not None and plan.fast and ctx.train:
+                late = (C.c_void_p * nv.MAX_OPS)()
+                n_late = 0
+                for i, t in enumerate(plan.tensors):
+                    if arr[i] and t.data_ptr() in sp['late']:
+                        late[i], arr[i] = arr[i], 0
+                        n_late += 1
+                if n_late:
+                    sp.setdefault('stash', []).append((plan, x, n, ctx.n_dev, gf, gc, coeff, basis, late))
             with nv.section('field_bwd'):
                 nv.check(nv.lib().ffb_field_query_bwd_saved(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(ctx.n_dev),
                                                             nv.ptr(gf, allow_none=True), nv.ptr(gc, allow_none=True),

@@ -165,7 +165,13 @@ class TrainStep:
     CHUNK = 4096
 
     def __init__(self, model, param_groups, batch, n_samples, white_bg=True, betas=(0.9, 0.99), eps=1e-8, lr_decay=1.0,
-                 group=None, use_graph=True, warmup=2, nccl_in_graph=False, ndc_ray=False):
+                 group=None, use_graph=True, warmup=2, nccl_in_graph=False, ndc_ray=False, overlap_comm=None):
+        """overlap_comm (default: on when world_size > 1): split the field backward in two phases and all-reduce the gradients
+        of the first phase (fine basis levels + both MLPs) while the second (coefficients + coarse levels) is still scattering."""
+        if overlap_comm is None:
+            overlap_comm = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size(group) > 1
+        overlap_comm = bool(overlap_comm) and self._can_split(model)
         self.model, self.B, self.S, self.white_bg = model, int(batch), int(n_samples), bool(white_bg)
         # NDC (llff) / unbounded (360) scenes: the interpx row shared by all rays is a static device buffer refreshed per step
         self.ndc_ray = bool(ndc_ray)
@@ -175,13 +181,21 @@ class TrainStep:
         # frozen parameters (set_optimizable) stay out of the step, like torch.optim.Adam skips parameters without a gradient
         self.groups = [{'params': [p for p in g['params'] if p.requires_grad], 'lr': float(g['lr'])} for g in param_groups]
         self.params = [p for g in self.groups for p in g['params']]
+        # Arena order (data parallel): the gradients that are complete LAST — the coefficient grid and the coarse basis levels,
+        # scattered by the deferred second phase of the field backward — first, everything else behind them, so that both
+        # all-reduce ranges are contiguous.  `late` = the tensors of that second phase.
+        late_ids = {id(p) for p in (self._late_params(model) if overlap_comm else [])}
+        self.late = [p for p in self.params if id(p) in late_ids]
+        self.arena_order = [p for p in self.params if id(p) in late_ids] + [p for p in self.params if id(p) not in late_ids]
         dev = self.params[0].device
         self.dev = dev
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(group)
         # gradient arena + optimiser state
-        self.bucket = GradBucket(self.params)
+        self.bucket = GradBucket(self.arena_order)
+        self._arena_index = {id(p): k for k, p in enumerate(self.arena_order)}
+        self.late_end = self.bucket.offsets[len(self.late)]          # arena[:late_end] = late gradients
         self.m = torch.zeros_like(self.bucket.flat)
         self.v = torch.zeros_like(self.bucket.flat)
         self.lr_d = torch.tensor([g['lr'] for g in self.groups], dtype=torch.float64, device=dev)
@@ -202,12 +216,34 @@ class TrainStep:
         self.graph = None
         self._warmup = warmup
 
+    @staticmethod
+    def _can_split(model):
+        try:
+            return bool(model._plan('coding').fast) and len(getattr(model, 'basises', [])) >= 2 and not isinstance(model.basises, torch.nn.ModuleList)
+        except Exception:
+            return False
+
+    @staticmethod
+    def _late_params(model):
+        """Second phase of the field backward: the coefficient tensor(s) and the coarser half of the basis levels (by bytes
+        the smaller part: 6 of 21 MB at nerf.yaml), so the bulk of the arena is on the wire while they scatter."""
+        bas = list(model.basises)
+        order = sorted(range(len(bas)), key=lambda i: bas[i].numel())
+        total, acc, coarse = sum(b.numel() for b in bas), 0, []
+        for i in order:
+            if acc + bas[i].numel() > 0.35 * total:
+                break
+            coarse.append(bas[i])
+            acc += bas[i].numel()
+        return [p for p in list(model.coeffs) + coarse if p.requires_grad]
+
     def _build_tables(self):
         rows, ct, cs = [], [], []
         i = 0
         for gi, g in enumerate(self.groups):
             for p in g['params']:
-                off, n = self.bucket.offsets[i], p.numel()
+                k = self._arena_index[id(p)]
+                off, n = self.bucket.offsets[k], p.numel()
                 base = off * 4
                 rows.append([p.data_ptr(), self.bucket.flat.data_ptr() + base, self.m.data_ptr() + base, self.v.data_ptr() + base, n, gi])
                 for s in range(0, n, self.CHUNK):
@@ -217,7 +253,7 @@ class TrainStep:
         self.table = torch.tensor(rows, dtype=torch.int64, device=self.dev)
         self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=self.dev)
         self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=self.dev)
-        self.arena = {p.data_ptr(): self.bucket.view(k) for k, p in enumerate(self.params)}
+        self.arena = {p.data_ptr(): self.bucket.view(k) for k, p in enumerate(self.arena_order)}
         self._param_ptrs = [p.data_ptr() for p in self.params]
 
     # -- the step body: only stream-ordered device work (capturable) ------------------------------------------
@@ -233,12 +269,15 @@ class TrainStep:
         m._white_bg_static = self.bg_s
         prev_lazy = m.__dict__.get('lazy_counts', False)
         m.lazy_counts = True          # device-side sample counts, scoped to this step: direct model(rays) calls stay exact-sized
+        self._split = {'late': {p.data_ptr() for p in self.late}} if self.late else None
+        _ops.set_field_bwd_split(self._split)
         try:
             rgb, depth, _ = m(self.rays_s, white_bg=self.white_bg, is_train=True, ndc_ray=self.ndc_ray, N_samples=self.S)
             _, g_rgb = _ops.mse_fwd_bwd(rgb, self.target_s, loss=self.loss_s)
             grads = torch.autograd.grad([rgb], self.params, grad_outputs=[g_rgb], allow_unused=True)
         finally:
             _ops.set_grad_arena(None)
+            _ops.set_field_bwd_split(None)
             m._z_static = None
             m._white_bg_static = None
             m.lazy_counts = prev_lazy
@@ -248,13 +287,33 @@ class TrainStep:
                 m._jitter = prev_jitter
         for k, g in enumerate(grads):       # gradients produced outside the arena (factor types without arena support)
             if g is not None:
-                v = self.bucket.view(k)
+                v = self.bucket.view(self._arena_index[id(self.params[k])])
                 if g.data_ptr() != v.data_ptr():
                     v.copy_(g)
+
+    def _late_backward(self):
+        """Second phase of the field backward (deferred by _render_backward when `self.late` is non-empty)."""
+        from . import ops as _ops
+        if self._split:
+            _ops.set_field_bwd_split(self._split)
+            try:
+                _ops.field_bwd_deferred()
+            finally:
+                _ops.set_field_bwd_split(None)
 
     def _all_reduce(self):
         if self.world > 1:
             torch.distributed.all_reduce(self.bucket.flat, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def _all_reduce_early(self):
+        """Asynchronous all-reduce of arena[late_end:] (complete after the first backward phase); -> work handle | None"""
+        if self.world > 1 and self.late_end < self.bucket.flat.numel():
+            return torch.distributed.all_reduce(self.bucket.flat[self.late_end:], op=torch.distributed.ReduceOp.SUM, group=self.group, async_op=True)
+        return None
+
+    def _all_reduce_late(self):
+        if self.world > 1 and self.late_end > 0:
+            torch.distributed.all_reduce(self.bucket.flat[:self.late_end], op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     def _optimise(self):
         from . import ops as _ops
@@ -264,7 +323,14 @@ class TrainStep:
 
     def _body(self):
         self._render_backward()
-        self._all_reduce()
+        if self.late:
+            work = self._all_reduce_early()
+            self._late_backward()
+            self._all_reduce_late()
+            if work is not None:
+                work.wait()
+        else:
+            self._all_reduce()
         self._optimise()
 
     def _check_params(self):
@@ -298,9 +364,19 @@ class TrainStep:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
                 self._render_backward()
-            with torch.cuda.graph(gb, pool=ga.pool()):
-                self._optimise()
-            self.graph = (ga, gb)
+            if self.late:
+                # [render + backward, phase 1] -> async all-reduce of the early range || [backward phase 2] -> all-reduce of the
+                # late range -> [Adam].  The stash of phase 2 keeps graph 1's buffers alive, so the shared pool cannot recycle them.
+                gl = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gl, pool=ga.pool()):
+                    self._late_backward()
+                with torch.cuda.graph(gb, pool=ga.pool()):
+                    self._optimise()
+                self.graph = (ga, gl, gb)
+            else:
+                with torch.cuda.graph(gb, pool=ga.pool()):
+                    self._optimise()
+                self.graph = (ga, gb)
 
     def step(self, rays, target, jitter=None, bg_coin=None):
         """rays [B,6], target [B,3]: host (ideally pinned) or device fp32 tensors; jitter [B] (default: torch.rand on the
@@ -326,6 +402,14 @@ class TrainStep:
             self._body()
         elif len(self.graph) == 1:
             self.graph[0].replay()
+        elif len(self.graph) == 3:
+            self.graph[0].replay()
+            work = self._all_reduce_early()
+            self.graph[1].replay()
+            self._all_reduce_late()
+            if work is not None:
+                work.wait()
+            self.graph[2].replay()
         else:
             self.graph[0].replay()
             self._all_reduce()
@@ -366,9 +450,9 @@ class RegressStep(TrainStep):
         """local_params: parameters that are NOT replicated across ranks (the image-set coefficient slabs each rank owns,
         `image_set_shard`): their gradients stay out of the all-reduce."""
         super().__init__(model, param_groups, batch, n_samples=1, betas=betas, eps=eps, lr_decay=1.0, group=group,
-                         use_graph=use_graph, warmup=warmup)
+                         use_graph=use_graph, warmup=warmup, overlap_comm=False)
         local = {p.data_ptr() for p in local_params}
-        self._shared_ranges = arena_ranges(self.bucket, [p.data_ptr() not in local for p in self.params])
+        self._shared_ranges = arena_ranges(self.bucket, [p.data_ptr() not in local for p in self.arena_order])
         self.is_train, self.loss_scale_decay = bool(is_train), float(loss_scale_decay)
         self.rays_s = torch.zeros(self.B, int(x_dim), device=self.dev)         # coordinates
         self.target_s = torch.zeros(self.B, int(out_dim), device=self.dev)
@@ -390,7 +474,7 @@ class RegressStep(TrainStep):
             _ops.set_grad_arena(None)
         for k, g in enumerate(grads):
             if g is not None:
-                v = self.bucket.view(k)
+                v = self.bucket.view(self._arena_index[id(self.params[k])])
                 if g.data_ptr() != v.data_ptr():
                     v.copy_(g)
 

@@ -223,3 +223,72 @@ def test_train_step_ndc_and_unbounded_scenes(kind):
             assert float(d.max()) <= max_drift, (n, float(d.max()))
         else:
             assert float((d > tol).float().mean()) < 5e-3, (n, float(d.max()))
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_two_phase_backward_equals_single_phase(use_graph):
+    """TrainStep(overlap_comm=True) — field backward split in two launches (fine basis levels first, coefficients + coarse
+    levels deferred), gradient arena re-ordered so each phase is one contiguous all-reduce range — takes the same optimisation
+    steps as the single-phase path (one GPU: the all-reduces are no-ops, everything else is the data-parallel code path)."""
+    from ffb200.train import TrainStep
+    cfg, ma = _small_model(3)
+    mb = copy.deepcopy(ma)
+    mb._plans = {}
+    R, S, steps = 256, 96, 3
+    rays = torch.from_numpy(blender_like_rays(R * steps, 9))
+    rng = np.random.RandomState(11)
+    target = torch.from_numpy(rng.rand(R * steps, 3).astype(np.float32))
+    jitter = torch.from_numpy(rng.rand(R * steps).astype(np.float32))
+    out = []
+    for m, overlap in ((ma, False), (mb, True)):
+        ts = TrainStep(m, m.get_optparam_groups(0.001, 0.02), batch=R, n_samples=S, lr_decay=0.98, use_graph=use_graph, overlap_comm=overlap)
+        assert bool(ts.late) == overlap
+        if overlap:       # coefficients + the coarse levels come first in the arena, and are a minority of it
+            assert 0 < ts.late_end < 0.5 * ts.bucket.flat.numel()
+        out.append([float(ts.step(rays[i * R:(i + 1) * R], target[i * R:(i + 1) * R], jitter[i * R:(i + 1) * R]).item()) for i in range(steps)])
+    np.testing.assert_allclose(out[1], out[0], rtol=2e-5, atol=1e-7)
+    for (n, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+        d = (pa - pb).abs().flatten()
+        tol = 2e-4 * max(1.0, float(pa.abs().max()))
+        assert float((d > tol).float().mean()) < 2e-3, n
+
+
+def test_random_background_coin_is_not_frozen_in_the_graph():
+    """white_bg=False scenes (llff / 360): the reference flips a coin per step for a white background (FactorFields.py:890).
+    The captured step must see the per-step value: steps with coin = 1 / 0 reproduce the eager white_bg=True / False losses."""
+    from ffb200.renderer import render_ray
+    from ffb200.train import TrainStep
+    cfg, m = _small_model(4)
+    R, S = 256, 96
+    rays = torch.from_numpy(blender_like_rays(R, 2))
+    rng = np.random.RandomState(3)
+    target = torch.from_numpy(rng.rand(R, 3).astype(np.float32))
+    jitter = torch.from_numpy(rng.rand(R).astype(np.float32))
+    seeds = {}
+    for sd in range(64):                  # CPU-generator seeds whose first uniform is below / above 0.5
+        torch.manual_seed(sd)
+        seeds.setdefault(bool(torch.rand((1,)) < 0.5), sd)
+    eager = {}
+    for coin in (True, False):            # eager forward(): jitter injected, so the coin is the first draw after the seed
+        m._jitter = lambda n, tr: jitter.cuda()
+        m.lazy_counts = False
+        torch.manual_seed(seeds[coin])
+        with torch.no_grad():
+            rgb, _, _ = m(rays.cuda(), white_bg=False, is_train=True, N_samples=S)
+        eager[coin] = float(torch.mean((rgb - target.cuda()) ** 2))
+    m.__dict__.pop('_jitter', None)
+    assert abs(eager[True] - eager[False]) > 1e-4        # the background matters on this scene
+    ts = TrainStep(m, m.get_optparam_groups(0.0, 0.0), batch=R, n_samples=S, white_bg=False, use_graph=True)
+    for coin in (1, 0, 0, 1):
+        loss = float(ts.step(rays, target, jitter, bg_coin=coin).item())
+        assert int(ts.bg_s.item()) == coin
+        assert abs(loss - eager[bool(coin)]) < 2e-5 * max(1.0, abs(loss)), (coin, loss, eager)
+    # default: the coin is drawn from the CPU generator, one draw per step
+    torch.manual_seed(5)
+    want = [int(bool(torch.rand((1,)) < 0.5)) for _ in range(6)]
+    torch.manual_seed(5)
+    got = []
+    for _ in range(6):
+        ts.step(rays, target, jitter)
+        got.append(int(ts.bg_s.item()))
+    assert got == want and 0 in got and 1 in got
