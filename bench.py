@@ -269,8 +269,9 @@ def run_ours(args):
         api = 'ffb200.renderer.render_ray(host rays) -> loss.item()'
     else:
         # the product path: the whole step (render, MSE, backward, all-reduce, Adam, lr decay) is one CUDA graph
+        ov = os.environ.get('FFB_OVERLAP_COMM')
         ts = TrainStep(model, groups, batch=B, n_samples=S, white_bg=True, betas=(0.9, 0.99), lr_decay=lr_factor,
-                       nccl_in_graph=bool(int(os.environ.get('FFB_NCCL_IN_GRAPH', '0'))))
+                       nccl_in_graph=bool(int(os.environ.get('FFB_NCCL_IN_GRAPH', '0'))), overlap_comm=None if ov is None else bool(int(ov)))
 
         def step_resident():
             """inputs already in HBM (device -> static-buffer copies only)"""

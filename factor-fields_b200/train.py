@@ -1,5 +1,8 @@
 """Train-step glue (train_per_scene.py:124-171): fused Adam over the model's parameter groups with the reference's
 per-step multiplicative lr decay, and the flat gradient bucket used for the data-parallel all-reduce."""
+import os
+import sys
+
 import torch
 
 from . import ops
@@ -72,18 +75,57 @@ def image_set_shard(n_img, rank, world):
     return sl.start, sl.stop - sl.start
 
 
+class SymmArena:
+    """The gradient arena in symmetric memory (torch.distributed._symmetric_memory: every rank maps every peer's buffer and,
+    where the NVSwitch fabric offers it, one multicast address), reduced by OUR kernel (csrc/allreduce.cu: multimem.ld_reduce /
+    multimem.st through the switch, or peer loads / stores over NVLink) instead of an NCCL call — a plain stream-ordered
+    launch, so the data-parallel step is again ONE CUDA graph.  Raises if symmetric memory cannot be set up on this system
+    (TrainStep then falls back to NCCL and says so)."""
+
+    BLOCKS = 32
+
+    def __init__(self, n_floats, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        dist = torch.distributed
+        group = group if group is not None else dist.group.WORLD
+        n_floats = (int(n_floats) + 3) // 4 * 4
+        self.flat = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.hdl = symm_mem.rendezvous(self.flat, group)
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        if self.BLOCKS * self.world * 4 > int(self.hdl.signal_pad_size):
+            raise RuntimeError('signal pad too small for the all-reduce barrier slots')
+        off = int(getattr(self.hdl, 'offset', 0))
+        ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
+        if ptrs[self.rank] != self.flat.data_ptr():
+            raise RuntimeError('symmetric buffer address does not match the arena tensor')
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.pads = torch.tensor([int(p) for p in self.hdl.signal_pad_ptrs], dtype=torch.int64, device=device)
+        mc = int(self.hdl.multicast_ptr) if bool(self.hdl.has_multicast_support(torch.device(device).type, torch.device(device).index or 0)) else 0
+        self.multicast = (mc + off) if (mc and os.environ.get('FFB_ALLREDUCE_NVLS', '1') != '0') else 0
+        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)
+        dist.barrier(group)
+
+    def all_reduce(self):
+        from . import native as nv
+        import ctypes as C
+        nv.check(nv.lib().ffb_allreduce_symm(C.c_void_p(self.flat.data_ptr()), C.c_void_p(self.peers.data_ptr()), C.c_uint64(self.multicast),
+                                             C.c_void_p(self.pads.data_ptr()), C.c_void_p(self.epoch.data_ptr()), self.rank, self.world,
+                                             C.c_int64(self.flat.numel()), self.BLOCKS, nv.stream()))
+
+
 class GradBucket:
     """Flat fp32 buffer holding every gradient back to back (parameter storage order), so that one all-reduce per
     step covers grids + MLPs.  Device-agnostic torch code (tested with gloo on CPU)."""
 
-    def __init__(self, params):
+    def __init__(self, params, flat_alloc=None):
         self.params = [p for p in params]
         self.sizes = [p.numel() for p in self.params]
         self.offsets = [0]
         for n in self.sizes:      # every slice starts on a 256-byte boundary (the scatter kernels use 16-byte vector reductions)
             self.offsets.append((self.offsets[-1] + n + 63) // 64 * 64)
         dev = self.params[0].device
-        self.flat = torch.zeros(self.offsets[-1], device=dev, dtype=torch.float32)
+        self.flat = flat_alloc(self.offsets[-1]) if flat_alloc is not None else torch.zeros(self.offsets[-1], device=dev, dtype=torch.float32)
 
     def view(self, i):
         """Gradient slice of parameter i in the parameter's own memory order (as_strided over the flat storage)."""
@@ -165,13 +207,15 @@ class TrainStep:
     CHUNK = 4096
 
     def __init__(self, model, param_groups, batch, n_samples, white_bg=True, betas=(0.9, 0.99), eps=1e-8, lr_decay=1.0,
-                 group=None, use_graph=True, warmup=2, nccl_in_graph=False, ndc_ray=False, overlap_comm=None):
+                 group=None, use_graph=True, warmup=2, nccl_in_graph=False, ndc_ray=False, overlap_comm=None, comm=None):
         """overlap_comm (default: on when world_size > 1): split the field backward in two phases and all-reduce the gradients
         of the first phase (fine basis levels + both MLPs) while the second (coefficients + coarse levels) is still scattering."""
-        if overlap_comm is None:
-            overlap_comm = torch.distributed.is_available() and torch.distributed.is_initialized() and \
-                torch.distributed.get_world_size(group) > 1
+        comm: 'symm' (default when world_size > 1: the arena lives in symmetric memory and is reduced by csrc/allreduce.cu inside
+        the step's single CUDA graph) or 'nccl' (torch.distributed.all_reduce between two graphs; also the fallback when symmetric
+        memory cannot be set up — the reason is printed)."""
+        # measured on 2 and 8 B200s: the split costs more (+52 us of scatter, +3 launches) than the overlap hides -> opt-in only
         overlap_comm = bool(overlap_comm) and self._can_split(model)
+        self.comm = (comm or os.environ.get('FFB_COMM', 'symm')).lower()
         self.model, self.B, self.S, self.white_bg = model, int(batch), int(n_samples), bool(white_bg)
         # NDC (llff) / unbounded (360) scenes: the interpx row shared by all rays is a static device buffer refreshed per step
         self.ndc_ray = bool(ndc_ray)
@@ -193,7 +237,21 @@ class TrainStep:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(group)
         # gradient arena + optimiser state
-        self.bucket = GradBucket(self.arena_order)
+        self.symm = None
+        if self.world > 1 and self.comm == 'symm' and not self.late:
+            try:
+                box = {}
+
+                def alloc(n):
+                    box['a'] = SymmArena(n, dev, group)
+                    return box['a'].flat
+                self.bucket = GradBucket(self.arena_order, flat_alloc=alloc)
+                self.symm = box['a']
+            except Exception as e:      # loud, not fatal: NCCL is an equally correct transport
+                print(f'[ffb200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL', file=sys.stderr, flush=True)
+                self.symm = None
+        if self.symm is None:
+            self.bucket = GradBucket(self.arena_order)
         self._arena_index = {id(p): k for k, p in enumerate(self.arena_order)}
         self.late_end = self.bucket.offsets[len(self.late)]          # arena[:late_end] = late gradients
         self.m = torch.zeros_like(self.bucket.flat)
@@ -303,7 +361,10 @@ class TrainStep:
 
     def _all_reduce(self):
         if self.world > 1:
-            torch.distributed.all_reduce(self.bucket.flat, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            if self.symm is not None:
+                self.symm.all_reduce()
+            else:
+                torch.distributed.all_reduce(self.bucket.flat, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     def _all_reduce_early(self):
         """Asynchronous all-reduce of arena[late_end:] (complete after the first backward phase); -> work handle | None"""
@@ -353,7 +414,7 @@ class TrainStep:
             self.m.copy_(st[0]); self.v.copy_(st[1]); self.lr_d.copy_(st[2]); self.step_d.copy_(st[3])
         if not self.use_graph:
             self.graph = False
-        elif self.world == 1 or self.nccl_in_graph:
+        elif self.world == 1 or self.nccl_in_graph or self.symm is not None:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._body()
@@ -450,7 +511,7 @@ class RegressStep(TrainStep):
         """local_params: parameters that are NOT replicated across ranks (the image-set coefficient slabs each rank owns,
         `image_set_shard`): their gradients stay out of the all-reduce."""
         super().__init__(model, param_groups, batch, n_samples=1, betas=betas, eps=eps, lr_decay=1.0, group=group,
-                         use_graph=use_graph, warmup=warmup, overlap_comm=False)
+                         use_graph=use_graph, warmup=warmup, overlap_comm=False, comm='nccl')
         local = {p.data_ptr() for p in local_params}
         self._shared_ranges = arena_ranges(self.bucket, [p.data_ptr() not in local for p in self.arena_order])
         self.is_train, self.loss_scale_decay = bool(is_train), float(loss_scale_decay)

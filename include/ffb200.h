@@ -136,6 +136,18 @@ int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int
                              const float* basis, float* const* h_grads, void* stream);
 /* Experiment knobs (launch configurations of the field kernels): "field_fwd_cfg", "field_bwd_cfg". */
 int ffb_set_tuning(const char* key, int value);
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange: in-place sum all-reduce of the flat fp32 gradient arena as ONE kernel over
+ * NVLink / NVSwitch peer memory (allreduce.cu).  The arena is symmetric memory: d_peer_ptrs[p] = rank p's arena as mapped
+ * into this process (device array of `world` 64-bit addresses), multicast_ptr = one address backed by all of them (0 when
+ * the fabric has no multicast: the kernel then sums peer loads instead of using multimem.ld_reduce / multimem.st).
+ * d_signal_pads[p]: rank p's signal pad (>= blocks*world*4 bytes, zeroed once); d_epoch: 2 zeroed uint32 on this device.
+ * Stream-ordered and capturable in a CUDA graph; every rank launches it with the same arguments in the same order.
+ * ------------------------------------------------------------------------------------------- */
+int ffb_allreduce_symm(float* local, const uint64_t* d_peer_ptrs, uint64_t multicast_ptr,
+                       const uint64_t* d_signal_pads, uint32_t* d_epoch, int32_t rank, int32_t world,
+                       int64_t n_floats, int32_t blocks, void* stream);
+
 /* Measurement probe (bench.py): issues blocks*256*iters `red.global.add.v4.f32` into buf[0..n_floats) — the instruction
  * the scatter kernels are made of — so that the backward pass can be reported against a MEASURED L2-reduction
  * throughput instead of the HBM roofline.  pattern 0: random 16-byte slots; 1: 512 contiguous bytes per warp. */

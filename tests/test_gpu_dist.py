@@ -40,3 +40,11 @@ def test_data_parallel_training_equals_single_process_global_batch():
 def test_image_set_sharded_by_image_equals_union_batch():
     out = _torchrun('dist_check_imageset.py')
     assert 'OK' in out or 'True' in out
+
+
+@needs2
+def test_symmetric_memory_allreduce_kernel_equals_nccl():
+    """csrc/allreduce.cu (multimem through NVSwitch, and the peer load/store path) against ncclAllReduce on the 21 MB arena:
+    same sums to fp32 rounding, bit-identical on every rank."""
+    out = _torchrun('dist_check_allreduce.py')
+    assert out.count(': OK') == 2, out[-2000:]
