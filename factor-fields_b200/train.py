@@ -208,8 +208,8 @@ class TrainStep:
 
     def __init__(self, model, param_groups, batch, n_samples, white_bg=True, betas=(0.9, 0.99), eps=1e-8, lr_decay=1.0,
                  group=None, use_graph=True, warmup=2, nccl_in_graph=False, ndc_ray=False, overlap_comm=None, comm=None):
-        """overlap_comm (default: on when world_size > 1): split the field backward in two phases and all-reduce the gradients
-        of the first phase (fine basis levels + both MLPs) while the second (coefficients + coarse levels) is still scattering."""
+        """overlap_comm (opt-in): split the field backward in two phases and all-reduce the gradients of the first phase (fine
+        basis levels + both MLPs) over NCCL while the second (coefficients + coarse levels) is still scattering.
         comm: 'symm' (default when world_size > 1: the arena lives in symmetric memory and is reduced by csrc/allreduce.cu inside
         the step's single CUDA graph) or 'nccl' (torch.distributed.all_reduce between two graphs; also the fallback when symmetric
         memory cannot be set up — the reason is printed)."""
