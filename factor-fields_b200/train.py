@@ -82,7 +82,7 @@ class SymmArena:
     launch, so the data-parallel step is again ONE CUDA graph.  Raises if symmetric memory cannot be set up on this system
     (TrainStep then falls back to NCCL and says so)."""
 
-    BLOCKS = 32
+    BLOCKS = int(os.environ.get('FFB_ALLREDUCE_BLOCKS', '96'))
 
     def __init__(self, n_floats, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -93,7 +93,7 @@ class SymmArena:
         self.flat.zero_()
         self.hdl = symm_mem.rendezvous(self.flat, group)
         self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
-        if self.BLOCKS * self.world * 4 > int(self.hdl.signal_pad_size):
+        if self.world * 4 > int(self.hdl.signal_pad_size):
             raise RuntimeError('signal pad too small for the all-reduce barrier slots')
         off = int(getattr(self.hdl, 'offset', 0))
         ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
@@ -101,9 +101,9 @@ class SymmArena:
             raise RuntimeError('symmetric buffer address does not match the arena tensor')
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
         self.pads = torch.tensor([int(p) for p in self.hdl.signal_pad_ptrs], dtype=torch.int64, device=device)
-        mc = int(self.hdl.multicast_ptr) if bool(self.hdl.has_multicast_support(torch.device(device).type, torch.device(device).index or 0)) else 0
+        mc = int(self.hdl.multicast_ptr or 0)         # 0 when the fabric / driver offers no multicast object for this buffer
         self.multicast = (mc + off) if (mc and os.environ.get('FFB_ALLREDUCE_NVLS', '1') != '0') else 0
-        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)
+        self.epoch = torch.zeros(4, dtype=torch.int32, device=device)
         dist.barrier(group)
 
     def all_reduce(self):

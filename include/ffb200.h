@@ -141,7 +141,7 @@ int ffb_set_tuning(const char* key, int value);
  * NVLink / NVSwitch peer memory (allreduce.cu).  The arena is symmetric memory: d_peer_ptrs[p] = rank p's arena as mapped
  * into this process (device array of `world` 64-bit addresses), multicast_ptr = one address backed by all of them (0 when
  * the fabric has no multicast: the kernel then sums peer loads instead of using multimem.ld_reduce / multimem.st).
- * d_signal_pads[p]: rank p's signal pad (>= blocks*world*4 bytes, zeroed once); d_epoch: 2 zeroed uint32 on this device.
+ * d_signal_pads[p]: rank p's signal pad (>= world*4 bytes, zeroed once); d_epoch: 4 zeroed uint32 on this device; blocks <= SM count.
  * Stream-ordered and capturable in a CUDA graph; every rank launches it with the same arguments in the same order.
  * ------------------------------------------------------------------------------------------- */
 int ffb_allreduce_symm(float* local, const uint64_t* d_peer_ptrs, uint64_t multicast_ptr,

@@ -49,6 +49,11 @@ for nvls in ('1', '0'):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
     t_ours = timeit(ar.all_reduce)
+    for nb in (32, 64, 148):
+        ar.BLOCKS = nb
+        tt = timeit(ar.all_reduce)
+        if rank == 0:
+            print(f'   blocks {nb}: {tt:.1f} us', flush=True)
     buf = torch.randn(n, device=dev)
     t_nccl = timeit(lambda: dist.all_reduce(buf))
     if rank == 0:
