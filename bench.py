@@ -33,6 +33,42 @@ B_BWD_OWN = 12 + 72 + 144 + 2 * 1152      # x + upstream gradient row + saved co
 FLOP_LINEAR_MAT, FLOP_RGB = 6400, 83200
 
 
+class Variant:
+    """What distinguishes the NeRF train-step workloads: nerf (the headline: nerf.yaml, grid x grid) and BASELINE config 4, the
+    -vm / -CP presets on Tanks&Temples-shaped rays (non-cubic box, 1920x1080 rays, 498 samples per ray)."""
+
+    def __init__(self, name):
+        self.name = name
+        if name == 'nerf':
+            self.metric, self.workload, self.overrides = METRIC, WORKLOAD, {}
+            self.aabb, self.n_samples, self.b_fwd, self.b_bwd, self.flop_lm = W.AABB, W.N_SAMPLES, B_FWD, B_BWD, FLOP_LINEAR_MAT
+            self.rays = W.make_rays
+        else:
+            ov, fdim, bf, bb, fl = W.PRESETS[name]
+            self.metric = name + '_train_rays_per_s'
+            self.overrides, self.aabb, self.n_samples, self.b_fwd, self.b_bwd, self.flop_lm = ov, W.TNT_AABB, W.TNT_N_SAMPLES, bf, bb, fl
+            self.rays = W.tnt_rays
+            self.workload = (f'nerf.yaml + preset {name[5:]} ({", ".join(f"model.{k}={v}" for k, v in ov.items())}) train step (fwd+bwd+Adam): 4096 Tanks&Temples-shaped '
+                             f'rays (1920x1080) x {W.TNT_N_SAMPLES} samples/ray, aabb {np.round(np.array(W.TNT_AABB), 2).tolist()}, Fdim {fdim}, seeded init + density offset '
+                             '(bench_workload.density_offset_)')
+
+    def cfg_overrides(self):
+        return [f'model.{k}={json.dumps(v)}' for k, v in self.overrides.items()]
+
+    def prepare(self, model):
+        """Load / shape the synthetic state of a freshly built model (ours or the reference's)."""
+        import torch
+        if self.name == 'nerf':
+            model.load_state_dict({k: torch.from_numpy(v) for k, v in W.make_state(0).items()})
+            assert model.nSamples == 440 and float(model.stepSize) == float(W.step_size())
+        else:
+            W.density_offset_(model)
+        return model
+
+
+V = Variant('nerf')
+
+
 def latest_field_capture():
     """The newest committed `ncu --set full` summary of the field kernels (profiles/rNN_ncu_field*.json) -> (dict, path)."""
     import glob
@@ -101,13 +137,16 @@ def _ref_stepper(device):
     sys.path.insert(0, os.path.join(ROOT, 'baseline'))
     import ref_step
     if ref_step.available():
-        rs = ref_step.RefStep(W.make_state(0), W.AABB, device, W.N_SAMPLES)
-        assert rs.model.nSamples == 440 and float(rs.model.stepSize) == float(W.step_size())
+        rs = ref_step.RefStep(None, V.aabb, device, V.n_samples, overrides=V.overrides)
+        V.prepare(rs.model)
 
         def step(rays, target, jitter):
             # the reference draws its own per-ray jitter from the torch CPU generator (FactorFields.py:593-595)
             return rs.train_step(rays, target.to(device))
         return step, 'reference', lambda: rs.stats
+    if V.name != 'nerf':
+        raise RuntimeError('the operator-level port covers the grid x grid field only; the -vm / -CP presets need the reference checkout '
+                           '(baseline/_ref/factor-fields, staged by __graft_entry__.build())')
     from oracle.torch_port import TorchPort
     tp = TorchPort(W.make_state(0), W.AABB, W.FREQ_BANDS, W.step_size(), W.RCFG, device=device)
 
@@ -131,7 +170,7 @@ def run_reference(args):
     torch.set_num_threads(cores)
     torch.manual_seed(20211202)
     step, kind, stats = _ref_stepper('cpu')
-    rays, target, jitter = W.make_rays(W.BATCH * 2, seed=1)
+    rays, target, jitter = V.rays(W.BATCH * 2, seed=1)
     rays, target, jitter = torch.from_numpy(rays), torch.from_numpy(target), torch.from_numpy(jitter)
     # bounded sample: size the per-step ray count so the whole run stays within a few minutes
     t0 = time.perf_counter()
@@ -150,9 +189,9 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     sample = f'{n} of {W.BATCH} rays per step x {args.steps} steps (rays/s is per-ray, so the sample size does not bias it)'
-    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+    line = {'impl': 'reference', 'metric': V.metric, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'rays_per_step': n},
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': V.workload, 'rays_per_step': n},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample, 'note': REF_NOTE, 'stats': stats()},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -163,7 +202,7 @@ def cpu_baseline_leg(n=256, steps=2):
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     step, kind, _ = _ref_stepper('cpu')
-    rays, target, jitter = W.make_rays(n * (steps + 1), seed=1)
+    rays, target, jitter = V.rays(n * (steps + 1), seed=1)
     rays, target, jitter = torch.from_numpy(rays), torch.from_numpy(target), torch.from_numpy(jitter)
     step(rays[:n], target[:n], jitter[:n])
     t0 = time.perf_counter()
@@ -205,14 +244,11 @@ def run_ours(args):
     torch.manual_seed(20211202)
     np.random.seed(20211202)
 
-    cfg = ffb200.load_cfg('nerf.yaml')
-    cfg.dataset.aabb = W.AABB
-    model = FactorFields(cfg, f'cuda:{local}')
-    sd = {k: torch.from_numpy(v) for k, v in W.make_state(0).items()}
-    model.load_state_dict(sd)
+    cfg = ffb200.load_cfg('nerf.yaml', V.cfg_overrides())
+    cfg.dataset.aabb = V.aabb
+    model = V.prepare(FactorFields(cfg, f'cuda:{local}'))
     model.lazy_counts = not args.exact_counts   # no host round trips for the data-dependent sample counts
-    assert model.nSamples == 440 and float(model.stepSize) == float(W.step_size())
-    B, S = W.BATCH, W.N_SAMPLES
+    B, S = W.BATCH, V.n_samples
     if args.scaling == 'strong':       # fixed global batch: 4096 rays split across the ranks
         assert W.BATCH % world == 0
         B = W.BATCH // world
@@ -222,7 +258,7 @@ def run_ours(args):
     eager = args.exact_counts or args.eager
 
     nb = 16                                                # distinct batches in the pool (weak scaling: 4096 rays per GPU)
-    rays_np, target_np, jitter_np = W.make_rays(B * nb, seed=100 + rank)
+    rays_np, target_np, jitter_np = V.rays(B * nb, seed=100 + rank)
     rays_h = torch.from_numpy(rays_np).pin_memory()
     target_h = torch.from_numpy(target_np).pin_memory()
     jitter_h = torch.from_numpy(jitter_np).pin_memory()
@@ -354,7 +390,7 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     kern = {}
-    alg = {'field_fwd': n_valid * B_FWD, 'field_bwd': n_valid * B_BWD}
+    alg = {'field_fwd': n_valid * V.b_fwd, 'field_bwd': n_valid * V.b_bwd}
     for k, ms in sec.items():
         kern[k] = {'ms_per_step': round(ms, 4)}
         if k == 'field_fwd':
@@ -362,7 +398,7 @@ def run_ours(args):
             kern[k]['frac_hbm'] = round(alg[k] / (ms * 1e-3) / 1e9 / pk['hbm'], 4)
         elif k == 'field_bwd':       # no HBM fraction: the kernel is L2-reduction bound (see roofline_bwd)
             kern[k]['hbm_model_GBps'] = round(alg[k] / (ms * 1e-3) / 1e9, 1)
-    flops = {'mlp_fwd': n_valid * FLOP_LINEAR_MAT, 'mlp_bwd': 2 * n_valid * FLOP_LINEAR_MAT, 'rgbmlp_fwd': n_app * FLOP_RGB,
+    flops = {'mlp_fwd': n_valid * V.flop_lm, 'mlp_bwd': 2 * n_valid * V.flop_lm, 'rgbmlp_fwd': n_app * FLOP_RGB,
              'rgbmlp_bwd': 2 * n_app * FLOP_RGB}
     for k, f in flops.items():
         if k in sec and sec[k] > 0:
@@ -370,14 +406,14 @@ def run_ours(args):
     # ---- roofline.  The HBM model applies to the GATHER kernel: every algorithmic byte of the forward query is a real
     # load or store.  The scatter kernel is bound by L2 reductions (ncu: DRAM ~12 %, red sectors the busiest unit) and is reported
     # against a live-measured L2-reduction throughput (roofline_bwd) instead of an HBM fraction it cannot be a fraction of.
-    cap, cap_src = latest_field_capture()
+    cap, cap_src = latest_field_capture() if V.name == 'nerf' else ({}, None)      # the committed captures are of the nerf.yaml kernels
     dom = 'field_fwd'
     ach = alg[dom] / (sec[dom] * 1e-3) / 1e9
-    fwd_cap = next((rec for name, rec in cap.items() if 'fwd' in name and rec.get('traffic_bytes')), None)
+    fwd_cap = next((rec for name, rec in cap.items() if 'fast_fwd' in name and rec.get('traffic_bytes')), None)
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 4),
                 'traffic': int(fwd_cap['traffic_bytes']) if fwd_cap else None,
                 'traffic_source': (cap_src + ' (dram__bytes_read.sum + dram__bytes_write.sum, one launch)') if fwd_cap else None,
-                'peak_source': pk['src'], 'algorithmic_bytes_per_query': B_FWD,
+                'peak_source': pk['src'], 'algorithmic_bytes_per_query': V.b_fwd,
                 'algorithmic_bytes_per_launch': alg[dom], 'queries_per_launch': n_valid, 'launch_ms': round(sec[dom], 4),
                 'share_of_step': round(sec[dom] / (ms_total / args.steps), 4)}
     roofline_bwd = None
@@ -385,7 +421,7 @@ def run_ours(args):
         sys.path.insert(0, os.path.join(ROOT, 'scratch'))
         import probe_red
         probe = probe_red.measure()
-        bwd_cap = next((rec for name, rec in cap.items() if 'bwd' in name and rec.get('lts__t_sectors_srcunit_tex_op_red.sum')), None)
+        bwd_cap = next((rec for name, rec in cap.items() if 'fast_bwd' in name and rec.get('lts__t_sectors_srcunit_tex_op_red.sum')), None)
         if bwd_cap and 'field_bwd' in sec:
             red = float(bwd_cap['lts__t_sectors_srcunit_tex_op_red.sum']['value'])
             q_cap = float(bwd_cap.get('queries_per_launch', 986959))
@@ -397,14 +433,14 @@ def run_ours(args):
                             ' (lts__t_sectors_srcunit_tex_op_red.sum, one launch)', 'peak_source': 'ffb_probe_red, measured in this run '
                             '(red.global.add.v4.f32 into an L2-resident 21 MB buffer; best of the two address patterns)', 'probe': probe,
                             'launch_ms': round(sec['field_bwd'], 4), 'share_of_step': round(sec['field_bwd'] / (ms_total / args.steps), 4),
-                            'hbm_model_note': f'SURVEY 8(d) charges this kernel {B_BWD} B/query; it reads saved rows instead of re-gathering and its '
+                            'hbm_model_note': f'SURVEY 8(d) charges this kernel {V.b_bwd} B/query; it reads saved rows instead of re-gathering and its '
                                               'read-modify-write lands in L2, so an HBM fraction would be an accounting figure, not a bound'}
     except Exception as e:      # the probe is informational; the headline roofline never depends on it
         roofline_bwd = {'error': repr(e)}
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+    line = {'metric': V.metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'rays_per_gpu_per_step': B, 'samples_per_ray': S, 'valid_fraction': round(n_valid / (B * S), 4),
+            'config': {'workload': V.workload, 'rays_per_gpu_per_step': B, 'samples_per_ray': S, 'valid_fraction': round(n_valid / (B * S), 4),
                        'shaded_fraction_of_valid': round(n_app / max(n_valid, 1), 4), 'field_queries_per_step_per_gpu': n_valid,
                        'host_syncs_per_step': 2 if args.exact_counts else 0, 'cuda_graph': not eager, 'launches_per_step': launches_per_step,
                        'parallelism': (f'ray-sharded dp{world}; gradient arena all-reduced in two NCCL calls per step, the first (fine basis levels + MLPs, '
@@ -436,7 +472,7 @@ def cuda_eager_leg(steps=5):
     train_per_scene.py:151-156), loss read back every step (:164)."""
     import torch
     step, kind, stats = _ref_stepper('cuda')
-    rays, target, jitter = W.make_rays(W.BATCH * (steps + 2), seed=1)
+    rays, target, jitter = V.rays(W.BATCH * (steps + 2), seed=1)
     rays, target, jitter = (torch.from_numpy(a) for a in (rays, target, jitter))
     sl = lambda i: slice(i * W.BATCH, (i + 1) * W.BATCH)
     for i in range(2):
@@ -765,7 +801,7 @@ def run_eval(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--eval-chunk', type=int, default=65536)
-    ap.add_argument('--workload', default='nerf', choices=['nerf', 'nerf_eval'] + list(REGRESS), help='nerf (the headline, default) or a regression driver')
+    ap.add_argument('--workload', default='nerf', choices=['nerf', 'nerf_vm', 'nerf_cp', 'nerf_eval'] + list(REGRESS), help='nerf (the headline, default) or a regression driver')
     ap.add_argument('--no-dropout', action='store_true', help='image_set: disable F.dropout on the MLP input')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='weak: 4096 rays per GPU (default); strong: 4096 rays in total')
     ap.add_argument('--gpus', type=int, default=1)
@@ -783,9 +819,12 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}', '--master-addr', '127.0.0.1',
                '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    global V
+    if args.workload in ('nerf_vm', 'nerf_cp'):
+        V = Variant(args.workload)
     if args.workload == 'nerf_eval':
         run_eval(args)
-    elif args.workload != 'nerf':
+    elif args.workload in REGRESS:
         run_regress(args)
     elif args.impl == 'reference':
         run_reference(args)

@@ -51,8 +51,9 @@ def make_state(seed=0, blob_gain=16.0):
     return sd
 
 
-def make_rays(n, seed=0, radius=4.0 / 1.5):
-    """Blender-shaped rays (dataLoader/blender.py:50-90 conventions), vectorised."""
+def make_rays(n, seed=0, radius=4.0 / 1.5, wh=(800, 800), focal=1111.11):
+    """Blender-shaped rays (dataLoader/blender.py:50-90 conventions), vectorised.  wh / focal / radius: image size, focal
+    length and camera distance (the Tanks&Temples-shaped variants use 1920x1080)."""
     rng = np.random.RandomState(seed)
     th, ph = rng.uniform(0, 2 * np.pi, n), rng.uniform(0.1, 0.45 * np.pi, n)
     c = radius * np.stack([np.cos(th) * np.sin(ph), np.sin(th) * np.sin(ph), np.cos(ph)], -1)
@@ -60,8 +61,8 @@ def make_rays(n, seed=0, radius=4.0 / 1.5):
     right = np.cross(fwd, np.array([0, 0, 1.0]))
     right /= np.linalg.norm(right, axis=-1, keepdims=True)
     up = np.cross(right, fwd)
-    px, py = rng.uniform(0, 800, n), rng.uniform(0, 800, n)
-    d = fwd + ((px - 400) / 1111.11)[:, None] * right + ((py - 400) / 1111.11)[:, None] * up
+    px, py = rng.uniform(0, wh[0], n), rng.uniform(0, wh[1], n)
+    d = fwd + ((px - wh[0] / 2) / focal)[:, None] * right + ((py - wh[1] / 2) / focal)[:, None] * up
     d /= np.linalg.norm(d, axis=-1, keepdims=True)
     rays = np.concatenate([c, d], -1).astype(np.float32)
     target = rng.uniform(0, 1, (n, 3)).astype(np.float32)
@@ -92,3 +93,32 @@ def regress_state(cfg, shapes, seed=0):
         if l != L - 1:
             sd[f'linear_mat.backbone.{l}.bias'] = _uniform(rng, (fo,), fi)
     return sd
+
+
+# ---- BASELINE config 4: the -vm / -CP presets of README_FactorField.md:12-32 on Tanks&Temples-shaped rays ------------------------
+TNT_AABB = (1.2 * np.array([[-1.5, -0.6, -1.8], [1.5, 0.9, 1.8]])).tolist()      # non-cubic box
+TNT_N_SAMPLES = 498                                                              # cal_n_samples(N_to_reso(128^3, aabb), 0.5)
+PRESETS = {
+    # name: (model overrides as run_batch.py:43 passes them, Fdim, B_fwd, B_bwd, linear_mat flop/query)   [SURVEY 8d table]
+    'nerf_vm': ({'coeff_type': 'vm', 'basis_type': 'vm'}, 54, 1524, 4104, 11008),
+    'nerf_cp': ({'coeff_type': 'vec', 'basis_type': 'cp', 'freq_bands': [1.] * 6, 'basis_resos': [512] * 6, 'basis_dims': [32] * 6}, 192, 5388, 14592, 28672),
+}
+
+
+def tnt_rays(n, seed=0):
+    return make_rays(n, seed, radius=4.2, wh=(1920, 1080), focal=1165.0)
+
+
+def density_offset_(model, value=10.2):
+    """Mid-training-like state for a freshly initialised model (ours or the reference's: same module names): hidden unit 63 of
+    linear_mat becomes the constant 1 and feeds `value` into the density feature, so that sigma = softplus(f0 - 10) is of
+    order 1 and a few percent of the samples of every ray pass rayMarch_weight_thres and reach the appearance MLP (at init
+    density_shift = -10 shades nothing).  In place, no_grad."""
+    import torch
+    with torch.no_grad():
+        lm = model.linear_mat.backbone
+        lm[0].weight[63].zero_()
+        lm[0].bias[63] = 1.0
+        lm[-1].weight[0].mul_(0.1)
+        lm[-1].weight[0, 63] = value
+    return model
