@@ -153,6 +153,16 @@ int ffb_allreduce_symm(float* local, const uint64_t* d_peer_ptrs, uint64_t multi
  * throughput instead of the HBM roofline.  pattern 0: random 16-byte slots; 1: 512 contiguous bytes per warp. */
 int ffb_probe_red(float* buf, int64_t n_floats, int32_t blocks, int32_t iters, int32_t pattern,
                   int64_t* n_ops_out, void* stream);
+/* Vector-coefficient x line-product (CP) fields — coeff_type 'vec', basis_type 'cp' (FactorFields.py:437-441,497-509) — with
+ * the factors resident in shared memory one level at a time (TMA bulk copies; shared-memory-privatised gradient
+ * accumulation, one vector reduction per touched 16 bytes per CTA).  The ffb_field_query_* entry points pick them when
+ * ffb_field_lines_eligible(f) == 1; ffb_set_field_lines(0) forces the generic kernels (tests compare both). */
+int ffb_set_field_lines(int enabled);
+int ffb_field_lines_eligible(ffb_field_t f);
+int ffb_field_lines_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff,
+                        float* basis, void* stream);
+int ffb_field_lines_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
+                        const float* g_coeff, float* const* h_grads, void* stream);
 /* The descriptor-driven generic kernels, callable directly (parity tests compare both paths).
  * basis_out: optional [n, W] copy of the (re-ordered) basis row. */
 int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,

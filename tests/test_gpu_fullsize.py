@@ -231,3 +231,70 @@ def test_render_golden_nerf_scale(lazy):
         ref = g['grad.' + n]
         got = G.npy(gr) if gr is not None else np.zeros_like(ref)
         assert H.rel_err(got, ref) < 2e-4, n
+
+
+PRESET_FULL = {
+    # BASELINE config 4 at its real shapes: (model overrides, expected specialised path)
+    'nerf_cp': (['model.coeff_type=vec', 'model.basis_type=cp', 'model.freq_bands=[1.,1.,1.,1.,1.,1.]', 'model.basis_resos=[512,512,512,512,512,512]',
+                 'model.basis_dims=[32,32,32,32,32,32]'], 'lines'),
+    'nerf_vm': (['model.coeff_type=vm', 'model.basis_type=vm'], 'planes'),
+}
+
+
+@pytest.mark.parametrize('name', list(PRESET_FULL))
+def test_preset_kernels_full_shape(name):
+    """The -CP / -vm presets (README_FactorField.md:12-32) at the Tanks&Temples bench shapes (non-cubic box, 1 M ray-ordered
+    queries): the specialised kernels the ffb_field_query_* entry points dispatch to, element-wise against the descriptor-driven
+    generic kernels (every output, every factor gradient, with and without an upstream coefficient gradient) and against the
+    oracle on a 200 k subset."""
+    import bench_workload as W
+    import ffb200
+    from ffb200 import native as nv
+    from ffb200.models.FactorFields import FactorFields
+    from tests import gpu_helpers as G
+    ov, kind = PRESET_FULL[name]
+    cfg = ffb200.load_cfg('nerf.yaml', ov)
+    cfg.dataset.aabb = W.TNT_AABB
+    torch.manual_seed(1)
+    m = FactorFields(cfg, 'cuda')
+    with torch.no_grad():
+        for p in list(m.coeffs) + list(m.basises):
+            p.add_(0.3 * torch.randn_like(p))
+    lib = nv.lib()
+    plan = m._plan('coding')
+    if kind == 'lines':
+        assert lib.ffb_field_lines_eligible(plan.handle) == 1
+    lo, hi = (np.array(a, np.float64) for a in W.TNT_AABB)
+    x = _ray_ordered_points(4096, 256, lo, hi, 21, float(m.stepSize))
+    N, Wd = x.shape[0], plan.width
+    rng = np.random.RandomState(6)
+    xd = G.t(x)
+    gf = G.t(rng.randn(N, Wd).astype(np.float32))
+    gc = G.t(rng.randn(N, Wd).astype(np.float32))
+
+    def run(fwd, bwd, with_gc):
+        f, c = torch.empty(N, Wd, device='cuda'), torch.empty(N, Wd, device='cuda')
+        nv.check(fwd(plan.handle, nv.ptr(xd), C.c_int64(N), None, nv.ptr(f), nv.ptr(c), nv.stream()))
+        grads = [torch.zeros_like(t) for t in plan.tensors]
+        arr = (C.c_void_p * nv.MAX_OPS)(*[g.data_ptr() for g in grads])
+        nv.check(bwd(plan.handle, nv.ptr(xd), C.c_int64(N), None, nv.ptr(gf), nv.ptr(gc) if with_gc else None, arr, nv.stream()))
+        return f, c, grads
+
+    gen_fwd = lambda h, x_, n, nd, f, c, s: lib.ffb_field_generic_fwd(h, x_, n, nd, f, c, None, s)
+    for with_gc in (False, True):
+        fp, cp, gp = run(lib.ffb_field_query_fwd, lib.ffb_field_query_bwd, with_gc)          # product dispatch
+        fg, cg, gg = run(gen_fwd, lib.ffb_field_generic_bwd, with_gc)
+        assert H.rel_err(G.npy(fp), G.npy(fg)) < 2e-6 and H.rel_err(G.npy(cp), G.npy(cg)) < 2e-6
+        for a, b, t in zip(gg, gp, plan.tensors):
+            assert H.rel_err(G.npy(b), G.npy(a)) < 5e-5, (name, with_gc, tuple(t.shape))
+    ns = 800 * 256
+    fo = _oracle_for(m, cfg)
+    f_ref, c_ref = fo.get_coding(x[:ns])
+    feats, coeff = m.get_coding(G.t(x[:ns]))
+    assert H.rel_err(G.npy(feats), f_ref) < TOL_FWD and H.rel_err(G.npy(coeff), c_ref) < TOL_FWD
+    ref = fo.get_coding_bwd(x[:ns], G.npy(gf[:ns]))
+    params = [(n_, p) for n_, p in m.named_parameters() if n_.startswith(('coeffs', 'basises'))]
+    grads = torch.autograd.grad((feats * gf[:ns]).sum(), [p for _, p in params])
+    for (n_, p), gr in zip(params, grads):
+        kind_, i = n_.split('.')[:2]
+        assert H.rel_err(G.npy(gr), ref[kind_][int(i)]) < TOL_BWD, (name, n_)
