@@ -22,11 +22,18 @@ int ffb_field_lines_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t*
 int ffb_field_lines_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
                         float* const* h_grads, void* stream);
 
+// vector-matrix (vm) fields: coefficient lines x per-level plane triples (field_planes.cu)
+int ffb_field_planes_eligible(ffb_field_t f);
+int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis, void* stream);
+int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                         float* const* h_grads, void* stream);
+
 // Training forward: also writes the concatenated basis row (needed by ffb_field_query_bwd_saved).
 int ffb_field_query_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
                               void* stream) {
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_fwd_train(f, x, n, n_dev, feats, coeff, basis, stream);
   if (ffb_field_lines_eligible(f) == 1) return ffb_field_lines_fwd(f, x, n, n_dev, feats, coeff, basis, stream);
+  if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_fwd(f, x, n, n_dev, feats, coeff, basis, stream);
   return ffb_field_generic_fwd(f, x, n, n_dev, feats, coeff, basis, stream);
 }
 
@@ -36,12 +43,14 @@ int ffb_field_query_bwd_saved(ffb_field_t f, const float* x, int64_t n, const in
                               const float* coeff, const float* basis, float* const* h_grads, void* stream) {
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_bwd_saved(f, x, n, n_dev, g_feats, g_coeff, coeff, basis, h_grads, stream);
   if (ffb_field_lines_eligible(f) == 1) return ffb_field_lines_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
+  if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
 }
 
 int ffb_field_query_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, void* stream) {
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_fwd(f, x, n, n_dev, feats, coeff, stream);
   if (ffb_field_lines_eligible(f) == 1) return ffb_field_lines_fwd(f, x, n, n_dev, feats, coeff, nullptr, stream);
+  if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_fwd(f, x, n, n_dev, feats, coeff, nullptr, stream);
   return ffb_field_generic_fwd(f, x, n, n_dev, feats, coeff, nullptr, stream);
 }
 
@@ -49,6 +58,7 @@ int ffb_field_query_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t*
                         float* const* h_grads, void* stream) {
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   if (ffb_field_lines_eligible(f) == 1) return ffb_field_lines_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
+  if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
 }
 }

@@ -78,20 +78,31 @@ __device__ __forceinline__ void make_taps(const ffb_field_desc& D, const ffb_gat
   }
 }
 
-// acc[j] = sum_corners w * data[off + c0 + j]   (ATen accumulation order)
+// acc[j] = sum_corners w * data[off + c0 + j]   (ATen accumulation order).  Texels are read with the widest vector their
+// alignment allows (16 bytes when C % 4 == 0, 8 bytes when C % 2 == 0: c0 is a multiple of CH = 8 and the tensors are 16-byte
+// aligned) — the vm planes (C = 4 / 2) and the 18-channel coefficient lines used to go through scalar loads.
 __device__ __forceinline__ void gather_chunk(const ffb_gather_op& op, const Taps& t, int c0, int nc, float acc[CH]) {
 #pragma unroll
   for (int j = 0; j < CH; ++j) acc[j] = 0.0f;
-  const bool vec = (op.C % 4 == 0) && (nc == CH);
+  const int vw = ((op.C & 3) == 0 && (nc & 3) == 0) ? 4 : (((op.C & 1) == 0 && (nc & 1) == 0) ? 2 : 1);
   for (int cn = 0; cn < t.n; ++cn) {
     if (t.off[cn] < 0) continue;
     const float* p = op.data + t.off[cn] + c0;
     const float w = t.w[cn];
-    if (vec) {
-      float4 a = __ldg(reinterpret_cast<const float4*>(p));
-      float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      acc[0] += a.x * w; acc[1] += a.y * w; acc[2] += a.z * w; acc[3] += a.w * w;
-      acc[4] += b.x * w; acc[5] += b.y * w; acc[6] += b.z * w; acc[7] += b.w * w;
+    if (vw == 4) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 4)
+        if (j < nc) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p + j));
+          acc[j] += a.x * w; acc[j + 1] += a.y * w; acc[j + 2] += a.z * w; acc[j + 3] += a.w * w;
+        }
+    } else if (vw == 2) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 2)
+        if (j < nc) {
+          const float2 a = __ldg(reinterpret_cast<const float2*>(p + j));
+          acc[j] += a.x * w; acc[j + 1] += a.y * w;
+        }
     } else {
       for (int j = 0; j < nc; ++j) acc[j] += __ldg(p + j) * w;
     }
@@ -196,15 +207,35 @@ struct GradPtrs {
   float* p[FFB_MAX_OPS];
 };
 
-__device__ __forceinline__ void scatter_chunk(float* grad, const Taps& t, int c0, int nc, const float g[CH]) {
+// grad[off + c0 + j] += w * g[j] with vector reductions (red.global.add.v4 / v2.f32) wherever the texel alignment allows:
+// one 16-byte reduction per corner of a 4-channel plane texel instead of four scalar atomics.
+__device__ __forceinline__ void scatter_chunk(float* grad, int C, const Taps& t, int c0, int nc, const float g[CH]) {
   if (!grad) return;
+  const int vw = ((C & 3) == 0 && (nc & 3) == 0) ? 4 : (((C & 1) == 0 && (nc & 1) == 0) ? 2 : 1);
   for (int cn = 0; cn < t.n; ++cn) {
     if (t.off[cn] < 0) continue;
     float* p = grad + t.off[cn] + c0;
     const float w = t.w[cn];
-    for (int j = 0; j < nc; ++j) {
-      float v = g[j] * w;
-      if (v != 0.0f) atomicAdd(p + j, v);
+    if (vw == 4) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 4)
+        if (j < nc) {
+          const float a = g[j] * w, b = g[j + 1] * w, c = g[j + 2] * w, d = g[j + 3] * w;
+          if (a != 0.0f || b != 0.0f || c != 0.0f || d != 0.0f)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + j), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+        }
+    } else if (vw == 2) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 2)
+        if (j < nc) {
+          const float a = g[j] * w, b = g[j + 1] * w;
+          if (a != 0.0f || b != 0.0f) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p + j), "f"(a), "f"(b) : "memory");
+        }
+    } else {
+      for (int j = 0; j < nc; ++j) {
+        float v = g[j] * w;
+        if (v != 0.0f) atomicAdd(p + j, v);
+      }
     }
   }
 }
@@ -225,7 +256,7 @@ __device__ __forceinline__ void bwd_term(const ffb_field_desc& D, const ffb_term
       g[j] = grow[perm ? perm[q] : q];
     }
     if (T.n_ops == 1) {
-      scatter_chunk(G.p[T.op[0]], taps[0], c0, nc, g);
+      scatter_chunk(G.p[T.op[0]], D.ops[T.op[0]].C, taps[0], c0, nc, g);
     } else {
       float vals[3][CH];
       for (int o = 0; o < T.n_ops; ++o) gather_chunk(D.ops[T.op[o]], taps[o], c0, nc, vals[o]);
@@ -238,7 +269,7 @@ __device__ __forceinline__ void bwd_term(const ffb_field_desc& D, const ffb_term
             if (oo != o) v *= vals[oo][j];
           go[j] = v;
         }
-        scatter_chunk(G.p[T.op[o]], taps[o], c0, nc, go);
+        scatter_chunk(G.p[T.op[o]], D.ops[T.op[o]].C, taps[o], c0, nc, go);
       }
     }
   }
@@ -376,6 +407,7 @@ int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_
   FFB_REQUIRE(f && x, "null argument");
   if (n <= 0) return FFB_OK;
   FFB_REQUIRE(!(f->h.coeff_width > 0 && f->h.basis_width > 0) || coeff, "coeff buffer required when both factors exist");
+  for (int i = 0; i < f->h.n_ops; ++i) FFB_REQUIRE(((uintptr_t)f->h.ops[i].data & 15) == 0, "factor tensors must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   field_generic_fwd<<<blocks_for(n, 128, sm_count() * 32), 128, 0, s>>>(f->d, x, n, n_dev, feats, coeff, basis_out);
   FFB_LAUNCHED();
@@ -388,6 +420,8 @@ int ffb_field_generic_bwd(ffb_field_t f, const float* x, int64_t n, const int32_
   if (n <= 0) return FFB_OK;
   GradPtrs G;
   for (int i = 0; i < FFB_MAX_OPS; ++i) G.p[i] = i < f->h.n_ops ? (h_grads ? h_grads[i] : f->h.ops[i].grad) : nullptr;
+  for (int i = 0; i < f->h.n_ops; ++i)
+    FFB_REQUIRE(((uintptr_t)f->h.ops[i].data & 15) == 0 && ((uintptr_t)G.p[i] & 15) == 0, "factor and gradient tensors must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const int W = f->h.basis_width > 0 ? f->h.basis_width : f->h.coeff_width;
   float *c = nullptr, *b = nullptr;

@@ -1,0 +1,300 @@
+// field_planes.cu — specialised field kernels for the vector-matrix (VM, TensoRF-style) preset of README_FactorField.md (`-vm`:
+// coeff_type 'vm' = three coefficient LINES [1, Cc, H, 1] along the axes vecMode = [2, 1, 0], concatenated (FactorFields.py:
+// 443-450); basis_type 'vm' = three PLANES [1, C_l, H, W] per level over the axis pairs matMode = [[0,1],[0,2],[1,2]], followed by
+// the global column re-ordering view(N, F, -1).permute(0, 2, 1) (:491-496, :514-515)).
+//
+// Same design as field_fast.cu (one thread per query, consecutive threads = consecutive samples of a ray, channels-last texels
+// read as float4 / float2, x-neighbour corners adjacent, scatter with red.global.add.v4/v2.f32), adapted to the factorisation:
+// the 3 x Cc coefficient row of a query is interpolated first and parked in shared memory (one column of a [W][threads] tile
+// per thread: conflict-free), because the re-ordering scatters the basis columns across it; every plane sample is then combined
+// with its coefficient, and in the backward pass REPLACED by the coefficient gradient in place, so one shared-memory row per
+// thread serves both directions.  The backward pass re-gathers (no saved rows: all factors are L2 resident).
+#include "field_fast.cuh"
+
+namespace ffb {
+
+constexpr int VM_MAX_LEVELS = 8;
+constexpr int VM_NT = 128;
+
+struct VmLevel {
+  const float* plane[3];
+  int pw[3], ph[3];      // plane m: [ph, pw] texels, x (W) <- axis ax0[m], y (H) <- axis ax1[m]
+  int C, col;            // channels per plane; basis column of plane 0 (plane m starts at col + m * C)
+  float freq;
+  int op[3];
+};
+
+struct VmParams {
+  int mapping, n_levels, W, Cc, Hc;
+  float lo[3], hi[3];
+  const float* cline[3];
+  int caxis[3], cop[3];
+  int ax0[3], ax1[3];
+  const int32_t* perm;   // device: output column of basis column q
+  VmLevel lv[VM_MAX_LEVELS];
+};
+
+struct VmGrads {
+  float* cline[3];
+  float* plane[VM_MAX_LEVELS][3];
+};
+
+struct LTap {
+  int i0;
+  float w0, w1;
+  bool ok0, ok1;
+};
+
+__device__ __forceinline__ LTap vm_line_tap(const VmParams& P, int m, const float* xr) {
+  const int a = P.caxis[m];
+  const Axis ax = linear_axis(source_index(normalize_coord(xr[a], P.lo[a], P.hi[a]), P.Hc, 0, 1));
+  LTap t;
+  t.i0 = ax.i0; t.w0 = ax.w0; t.w1 = ax.w1;
+  t.ok0 = ax.i0 >= 0 && ax.i0 < P.Hc;
+  t.ok1 = ax.i0 + 1 >= 0 && ax.i0 + 1 < P.Hc;
+  return t;
+}
+
+__device__ __forceinline__ float vm_msize(const VmParams& P) {
+  float m = FFB_SUB(P.hi[0], P.lo[0]);
+  for (int k = 1; k < 3; ++k) m = fmaxf(m, FFB_SUB(P.hi[k], P.lo[k]));
+  return m;
+}
+
+// coefficient row of this thread's query -> srow[c * VM_NT] (c < 3 Cc)
+__device__ __forceinline__ void vm_coeff_row(const VmParams& P, const float* xr, float* srow) {
+#pragma unroll 1
+  for (int m = 0; m < 3; ++m) {
+    const LTap t = vm_line_tap(P, m, xr);
+    const float* base = P.cline[m];
+    for (int c = 0; c < P.Cc; c += 2) {
+      float2 v = make_float2(0.f, 0.f);
+      if (t.ok0) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(base + (size_t)t.i0 * P.Cc + c));
+        v.x += a.x * t.w0; v.y += a.y * t.w0;
+      }
+      if (t.ok1) {
+        const float2 b = __ldg(reinterpret_cast<const float2*>(base + (size_t)(t.i0 + 1) * P.Cc + c));
+        v.x += b.x * t.w1; v.y += b.y * t.w1;
+      }
+      srow[(m * P.Cc + c) * VM_NT] = v.x;
+      srow[(m * P.Cc + c + 1) * VM_NT] = v.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void vm_plane_taps(const VmParams& P, const VmLevel& L, int m, const float u[3], TapSet<2, false>& t) {
+  float c[3];
+  const int size[3] = {L.pw[m], L.ph[m], 1};
+  c[0] = source_index(u[P.ax0[m]], L.pw[m], 1, 0);
+  c[1] = source_index(u[P.ax1[m]], L.ph[m], 1, 0);
+  make_tapset<2, false>(c, size, t);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(VM_NT, MINB) vm_fwd_kernel(const VmParams P, const float* __restrict__ x, int64_t n_cap,
+                                                             const int32_t* __restrict__ n_dev, float* __restrict__ feats,
+                                                             float* __restrict__ coeff_out, float* __restrict__ basis_out) {
+  extern __shared__ float vm_smem[];
+  const int64_t n = resolve_n(n_cap, n_dev);
+  const float msize = vm_msize(P);
+  float* srow = vm_smem + threadIdx.x;
+  const int W = P.W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float xr[3];
+    for (int k = 0; k < 3; ++k) xr[k] = x[i * 3 + k];
+    vm_coeff_row(P, xr, srow);
+    if (coeff_out)
+      for (int c = 0; c < W; c += 2) *reinterpret_cast<float2*>(coeff_out + i * W + c) = make_float2(srow[c * VM_NT], srow[(c + 1) * VM_NT]);
+#pragma unroll 1
+    for (int l = 0; l < P.n_levels; ++l) {
+      const VmLevel& L = P.lv[l];
+      const float scale = FFB_DIV(msize, L.freq);
+      float u[3];
+      for (int k = 0; k < 3; ++k) u[k] = map_coord(xr[k], P.lo[k], scale, P.mapping, nullptr);
+#pragma unroll 1
+      for (int m = 0; m < 3; ++m) {
+        TapSet<2, false> tb;
+        vm_plane_taps(P, L, m, u, tb);
+        float b[4];
+        if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb, b);
+        else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb, b);
+        const int q0 = L.col + m * L.C;
+        for (int j = 0; j < L.C; ++j) {
+          const int p = __ldg(P.perm + q0 + j);
+          if (basis_out) basis_out[i * W + p] = b[j];
+          srow[p * VM_NT] *= b[j];                   // coefficient -> feature, in place
+        }
+      }
+    }
+    if (feats)
+      for (int c = 0; c < W; c += 2) *reinterpret_cast<float2*>(feats + i * W + c) = make_float2(srow[c * VM_NT], srow[(c + 1) * VM_NT]);
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(VM_NT, MINB) vm_bwd_kernel(const VmParams P, const VmGrads G, const float* __restrict__ x, int64_t n_cap,
+                                                             const int32_t* __restrict__ n_dev, const float* __restrict__ g_feats,
+                                                             const float* __restrict__ g_coeff) {
+  extern __shared__ float vm_smem[];
+  const int64_t n = resolve_n(n_cap, n_dev);
+  const float msize = vm_msize(P);
+  float* srow = vm_smem + threadIdx.x;
+  const int W = P.W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float xr[3];
+    for (int k = 0; k < 3; ++k) xr[k] = x[i * 3 + k];
+    vm_coeff_row(P, xr, srow);
+    const float* gf = g_feats ? g_feats + i * W : nullptr;
+    const float* gcf = g_coeff ? g_coeff + i * W : nullptr;
+#pragma unroll 1
+    for (int l = 0; l < P.n_levels; ++l) {
+      const VmLevel& L = P.lv[l];
+      const float scale = FFB_DIV(msize, L.freq);
+      float u[3];
+      for (int k = 0; k < 3; ++k) u[k] = map_coord(xr[k], P.lo[k], scale, P.mapping, nullptr);
+#pragma unroll 1
+      for (int m = 0; m < 3; ++m) {
+        TapSet<2, false> tb;
+        vm_plane_taps(P, L, m, u, tb);
+        float b[4], gb[4];
+        if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb, b);
+        else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb, b);
+        const int q0 = L.col + m * L.C;
+        for (int j = 0; j < 4; ++j) {
+          gb[j] = 0.0f;
+          if (j < L.C) {
+            const int p = __ldg(P.perm + q0 + j);
+            const float g = gf ? gf[p] : 0.0f;
+            gb[j] = g * srow[p * VM_NT];                                   // d/d basis = g * coefficient
+            srow[p * VM_NT] = g * b[j] + (gcf ? gcf[p] : 0.0f);            // d/d coefficient, in place
+          }
+        }
+        if (G.plane[l][m]) {
+          if (L.C == 4) scatter_vec<2, false, 4>(G.plane[l][m], 4, 0, tb, gb);
+          else scatter_vec<2, false, 2>(G.plane[l][m], 2, 0, tb, gb);
+        }
+      }
+    }
+    // coefficient lines: 1-D scatter of the 3 x Cc gradient row
+#pragma unroll 1
+    for (int m = 0; m < 3; ++m) {
+      float* gl = G.cline[m];
+      if (!gl) continue;
+      const LTap t = vm_line_tap(P, m, xr);
+      for (int c = 0; c < P.Cc; c += 2) {
+        const float g0 = srow[(m * P.Cc + c) * VM_NT], g1 = srow[(m * P.Cc + c + 1) * VM_NT];
+        if (t.ok0 && t.w0 != 0.0f) red_add_v2(gl + (size_t)t.i0 * P.Cc + c, g0 * t.w0, g1 * t.w0);
+        if (t.ok1 && t.w1 != 0.0f) red_add_v2(gl + (size_t)(t.i0 + 1) * P.Cc + c, g0 * t.w1, g1 * t.w1);
+      }
+    }
+  }
+}
+
+static bool build_vm_params(const ffb_field_desc& d, VmParams& P) {
+  if (d.xdim != 3 || d.in_dim != 3 || d.mapping == FFB_MAP_TRIG || d.basis_is_x || !d.basis_perm) return false;
+  if (d.n_cterms != 3 || d.n_bterms < 3 || d.n_bterms % 3 || d.n_bterms / 3 > VM_MAX_LEVELS) return false;
+  if (d.coeff_width <= 0 || d.coeff_width != d.basis_width || d.coeff_width > 96 || (d.coeff_width & 1)) return false;
+  int col = 0;
+  for (int m = 0; m < 3; ++m) {
+    const ffb_term& T = d.cterms[m];
+    if (T.n_ops != 1 || T.col != col) return false;
+    const ffb_gather_op& o = d.ops[T.op[0]];
+    if (o.nd != 2 || o.size[0] != 1 || o.src[0] >= 0 || o.cst[0] != 0.0f || o.src[1] < 0 || o.src[1] > 2) return false;
+    if (o.space != 0 || o.align_corners || !o.border || o.nearest || (o.C & 1) || ((uintptr_t)o.data & 15)) return false;
+    if (m > 0 && (o.C != P.Cc || o.size[1] != P.Hc)) return false;
+    P.Cc = o.C; P.Hc = o.size[1];
+    P.cline[m] = o.data; P.caxis[m] = o.src[1]; P.cop[m] = T.op[0];
+    col += o.C;
+  }
+  if (col != d.coeff_width) return false;
+  col = 0;
+  const int F = d.n_bterms / 3;
+  for (int t = 0; t < d.n_bterms; ++t) {
+    const ffb_term& T = d.bterms[t];
+    const int l = t / 3, m = t % 3;
+    if (T.n_ops != 1 || T.col != col) return false;
+    const ffb_gather_op& o = d.ops[T.op[0]];
+    if (o.nd != 2 || o.space != 1 || o.level != l || !o.align_corners || o.border || o.nearest || ((uintptr_t)o.data & 15)) return false;
+    if (o.C != 2 && o.C != 4) return false;
+    if (o.src[0] < 0 || o.src[0] > 2 || o.src[1] < 0 || o.src[1] > 2) return false;
+    if (l == 0) { P.ax0[m] = o.src[0]; P.ax1[m] = o.src[1]; }
+    else if (P.ax0[m] != o.src[0] || P.ax1[m] != o.src[1]) return false;
+    VmLevel& L = P.lv[l];
+    if (m == 0) { L.C = o.C; L.col = col; L.freq = d.freq[l]; }
+    else if (o.C != L.C) return false;
+    L.plane[m] = o.data; L.pw[m] = o.size[0]; L.ph[m] = o.size[1]; L.op[m] = T.op[0];
+    col += o.C;
+  }
+  if (col != d.basis_width) return false;
+  P.mapping = d.mapping; P.n_levels = F; P.W = d.coeff_width; P.perm = d.basis_perm;
+  for (int k = 0; k < 3; ++k) { P.lo[k] = d.aabb_min[k]; P.hi[k] = d.aabb_max[k]; }
+  return true;
+}
+
+static int g_planes_enabled = 1;
+
+}  // namespace ffb
+
+using namespace ffb;
+
+extern "C" {
+
+int ffb_set_field_planes(int enabled) {
+  g_planes_enabled = enabled ? 1 : 0;
+  return FFB_OK;
+}
+
+int ffb_field_planes_eligible(ffb_field_t f) {
+  if (!f || !g_planes_enabled) return 0;
+  VmParams P;
+  return build_vm_params(f->h, P) ? 1 : 0;
+}
+
+int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis, void* stream) {
+  FFB_REQUIRE(f && x, "null argument");
+  VmParams P;
+  FFB_REQUIRE(g_planes_enabled && build_vm_params(f->h, P), "descriptor is not a vector-matrix (vm) field");
+  if (n <= 0) return FFB_OK;
+  const size_t smem = (size_t)P.W * VM_NT * sizeof(float);
+  static PerDeviceOnce once;
+  if (once.first()) {
+    FFB_CUDA(cudaFuncSetAttribute(vm_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  }
+  FFB_REQUIRE(smem <= 64 * 1024, "coefficient row too wide");
+  vm_fwd_kernel<6><<<blocks_for(n, VM_NT, (int64_t)sm_count() * 64), VM_NT, smem, (cudaStream_t)stream>>>(P, x, n, n_dev, feats, coeff, basis);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                         float* const* h_grads, void* stream) {
+  FFB_REQUIRE(f && x, "null argument");
+  VmParams P;
+  FFB_REQUIRE(g_planes_enabled && build_vm_params(f->h, P), "descriptor is not a vector-matrix (vm) field");
+  if (n <= 0) return FFB_OK;
+  VmGrads G;
+  auto grad_of = [&](int op) { return h_grads ? h_grads[op] : f->h.ops[op].grad; };
+  bool aligned = true;
+  for (int m = 0; m < 3; ++m) {
+    G.cline[m] = grad_of(P.cop[m]);
+    aligned = aligned && ((uintptr_t)G.cline[m] & 15) == 0;
+  }
+  for (int l = 0; l < VM_MAX_LEVELS; ++l)
+    for (int m = 0; m < 3; ++m) {
+      G.plane[l][m] = l < P.n_levels ? grad_of(P.lv[l].op[m]) : nullptr;
+      aligned = aligned && ((uintptr_t)G.plane[l][m] & 15) == 0;
+    }
+  FFB_REQUIRE(aligned, "gradient tensors must be 16-byte aligned");
+  const size_t smem = (size_t)P.W * VM_NT * sizeof(float);
+  FFB_REQUIRE(smem <= 64 * 1024, "coefficient row too wide");
+  static PerDeviceOnce once;
+  if (once.first()) {
+    FFB_CUDA(cudaFuncSetAttribute(vm_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  }
+  vm_bwd_kernel<6><<<blocks_for(n, VM_NT, (int64_t)sm_count() * 64), VM_NT, smem, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, g_coeff);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+}  // extern "C"

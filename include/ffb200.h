@@ -163,6 +163,15 @@ int ffb_field_lines_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t*
                         float* basis, void* stream);
 int ffb_field_lines_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
                         const float* g_coeff, float* const* h_grads, void* stream);
+/* Vector-matrix (vm) fields — coeff_type 'vm' (three coefficient lines, FactorFields.py:443-450) x basis_type 'vm' (three planes
+ * per level + the column re-ordering of :514-515) — as specialised gather / vector-reduction kernels (field_planes.cu); picked by
+ * the ffb_field_query_* entry points when ffb_field_planes_eligible(f) == 1 (2- or 4-channel planes, single scene). */
+int ffb_set_field_planes(int enabled);
+int ffb_field_planes_eligible(ffb_field_t f);
+int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff,
+                         float* basis, void* stream);
+int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
+                         const float* g_coeff, float* const* h_grads, void* stream);
 /* The descriptor-driven generic kernels, callable directly (parity tests compare both paths).
  * basis_out: optional [n, W] copy of the (re-ordered) basis row. */
 int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,

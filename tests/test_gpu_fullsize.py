@@ -264,6 +264,8 @@ def test_preset_kernels_full_shape(name):
     plan = m._plan('coding')
     if kind == 'lines':
         assert lib.ffb_field_lines_eligible(plan.handle) == 1
+    if kind == 'planes':
+        assert lib.ffb_field_planes_eligible(plan.handle) == 1
     lo, hi = (np.array(a, np.float64) for a in W.TNT_AABB)
     x = _ray_ordered_points(4096, 256, lo, hi, 21, float(m.stepSize))
     N, Wd = x.shape[0], plan.width
