@@ -684,32 +684,46 @@ class FactorFields(torch.nn.Module):
         return alpha.view(shape)
 
     @torch.no_grad()
-    def getDenseAlpha(self, gridSize=None, times=16, sharded=True):
-        """FactorFields.py:730-755.  With torch.distributed initialised (and sharded=True) the lattice slices are sharded round-robin across
-        the ranks (16 x prod(gridSize) field queries per event) and the partial volumes are summed with one
-        all-reduce; every rank still draws the jitter of EVERY slice from the CPU generator, so the random stream — and
-        therefore the volume — is the one a single process produces."""
+    def getDenseAlpha(self, gridSize=None, times=16, sharded=True, chunk_points=1 << 22):
+        """FactorFields.py:730-755: alpha of the voxel-centre lattice, averaged over `times` jittered evaluations.
+
+        GPU-side formulation: the lattice [Z, Y, X, 3] is built on the device by broadcasting, and every round is evaluated
+        in a few launches over slabs of up to `chunk_points` points (157 M field queries per event at 214^3 used to be 16 x 214
+        Python iterations with a CPU draw, a host->device copy and a launch chain each).  The jitter keeps the reference's
+        random stream: one `torch.rand(Z, Y, X, 3)` per round on the CPU generator yields exactly the numbers of the
+        reference's Z per-slice draws (same generator, same order), so the volume is bit-identical to the per-slice loop.
+        Under torch.distributed (sharded=True) rank r evaluates a contiguous block of slices and the partial volumes are summed
+        with one all-reduce; every rank still draws every round's full jitter, keeping the ranks' generators in step."""
         rank, world = 0, 1
         if sharded and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        gridSize = self.gridSize.tolist() if gridSize is None else gridSize
-        aabbSize = self.inward_aabb[1] - self.inward_aabb[0]
-        units = aabbSize / (torch.LongTensor(gridSize).to(self.device) - 1)
-        units_half = 1.0 / (torch.LongTensor(gridSize) - 1) * 0.5
-        stepSize = torch.mean(units.cpu())   # host evaluation, see update_renderParams
-        axes = [torch.linspace(units_half[k], 1 - units_half[k], gridSize[k]) for k in range(3)]
-        samples = torch.stack(torch.meshgrid(axes, indexing='ij'), -1).to(self.device)
-        dense_xyz = self.inward_aabb[0] * (1 - samples) + self.inward_aabb[1] * samples
-        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
-        alpha = torch.zeros_like(dense_xyz[..., 0])
+        gridSize = [int(g) for g in (self.gridSize.tolist() if gridSize is None else gridSize)]
+        X, Y, Z = gridSize
+        dev = self.device
+        lo, hi = self.inward_aabb[0], self.inward_aabb[1]
+        cells = torch.LongTensor(gridSize) - 1
+        units = (hi - lo) / cells.to(dev)
+        half = 0.5 / cells.float()
+        length = torch.mean(units.cpu()) * self.cfg.renderer.distance_scale     # host evaluation, see update_renderParams
+        # voxel centres per axis (host linspace, as the reference's), blended with the box corners on the device
+        s = [torch.linspace(float(half[k]), float(1 - half[k]), gridSize[k]).to(dev) for k in range(3)]
+        ax = [lo[k] * (1 - s[k]) + hi[k] * s[k] for k in range(3)]
+        dense_xyz = torch.stack([ax[0].view(1, 1, X).expand(Z, Y, X), ax[1].view(1, Y, 1).expand(Z, Y, X),
+                                 ax[2].view(Z, 1, 1).expand(Z, Y, X)], -1).contiguous()
+        alpha = torch.zeros((Z, Y, X), device=dev)
+        base, rem = divmod(Z, world)
+        z_lo = rank * base + min(rank, rem)
+        z_hi = z_lo + base + (1 if rank < rem else 0)
+        slab = max(1, int(chunk_points) // max(1, X * Y))
+        amp = units / 2 * 1.2
         for _ in range(times):
-            for i in range(gridSize[2]):
-                shiftment = torch.rand(dense_xyz[i].shape) if times > 1 else None       # drawn on every rank (same stream)
-                if i % world != rank:
-                    continue
-                shiftment = (shiftment * 2 - 1).to(self.device) * (units / 2 * 1.2) if times > 1 else 0.0
-                alpha[i] += self.compute_alpha((dense_xyz[i] + shiftment).view(-1, 3),
-                                               stepSize * self.cfg.renderer.distance_scale).view((gridSize[1], gridSize[0]))
+            shift = torch.rand(Z, Y, X, 3) if times > 1 else None          # drawn on every rank: the same stream everywhere
+            for z0 in range(z_lo, z_hi, slab):
+                z1 = min(z0 + slab, z_hi)
+                pts = dense_xyz[z0:z1]
+                if shift is not None:
+                    pts = pts + (shift[z0:z1].to(dev, non_blocking=True) * 2 - 1) * amp
+                alpha[z0:z1] += self.compute_alpha(pts.reshape(-1, 3), length).view(z1 - z0, Y, X)
         if world > 1:
             torch.distributed.all_reduce(alpha, op=torch.distributed.ReduceOp.SUM)
         return alpha / times, dense_xyz

@@ -292,3 +292,65 @@ def test_random_background_coin_is_not_frozen_in_the_graph():
         ts.step(rays, target, jitter)
         got.append(int(ts.bg_s.item()))
     assert got == want and 0 in got and 1 in got
+
+
+def test_scheduled_run_matches_the_unmodified_reference():
+    """reconstruction() through EVERY schedule event — shrink (500), two upsamples (1000, 1400), two alpha-mask updates that
+    install the mask (1550, 1650; the reference hard-codes `iteration >= 1500`) and the ray filtering after the first — against
+    the unmodified reference driven through the same loop on the host cores (tests/ref_driver.py), same initial weights, same
+    numpy / torch CPU random streams.  Bar: end-of-run PSNR within 0.1 dB (north_star); plus the discrete outcomes of the
+    events (box after the shrink, sample count, rays kept by the filter, occupied voxels of the mask)."""
+    from tests import ref_driver
+    if not ref_driver.available():
+        pytest.skip('reference checkout not staged (baseline/_ref/factor-fields)')
+    import ffb200
+    from ffb200.models.FactorFields import FactorFields
+    from ffb200.train import reconstruction
+    from tests.synth_scene import sphere_scene
+    steps, B = 1700, 256
+    ov = {'model.total_params': 150000, 'model.coeff_reso': 8, 'training.volume_resoInit': 32, 'training.volume_resoFinal': 48,
+          'training.batch_size': B, 'training.n_iters': steps, 'renderer.density_shift': -4.0}
+    sched = dict(upsamp_list=[1000, 1400], update_AlphaMask_list=[1550, 1650], shrinking_list=[500])
+    cfg = ffb200.load_cfg('nerf.yaml', [f'{k}={v}' for k, v in ov.items()])
+    cfg.dataset.aabb = [[-1., -1., -1.], [1., 1., 1.]]
+    for k, v in sched.items():
+        setattr(cfg.training, k, list(v))
+    torch.manual_seed(11)
+    m = FactorFields(cfg, 'cuda:0')
+    state = {k: v.detach().cpu().contiguous().clone() for k, v in m.state_dict().items()}
+    rays, rgbs = sphere_scene(30000, 1)
+    test_rays, test_rgbs = sphere_scene(4096, 2)
+    T = lambda a: torch.from_numpy(a)
+
+    np.random.seed(5)
+    torch.manual_seed(6)
+    res = reconstruction(cfg, m, T(rays).clone(), T(rgbs).clone(), white_bg=True, n_iters=steps, test=(T(test_rays), T(test_rgbs)))
+
+    load_cfg, RefFF, ref_render_ray, ref_utils = ref_driver.load()
+    rcfg = load_cfg('nerf.yaml')
+    for k, v in ov.items():
+        sec, key = k.split('.')
+        rcfg[sec][key] = v
+    rcfg.dataset.aabb = [[-1., -1., -1.], [1., 1., 1.]]
+    for k, v in sched.items():
+        rcfg.training[k] = list(v)
+    torch.manual_seed(11)
+    rm = RefFF(rcfg, 'cpu')
+    rm.load_state_dict(state)
+    np.random.seed(5)
+    torch.manual_seed(6)
+    ref = ref_driver.reconstruction(rcfg, rm, ref_render_ray, ref_utils, T(rays).clone(), T(rgbs).clone(), steps)
+    with torch.no_grad():
+        rgb_map, _ = ref_render_ray(T(test_rays), rm, chunk=4096, N_samples=-1, white_bg=True, is_train=False, device='cpu')
+    ref_test = -10.0 * np.log10(float(torch.mean((rgb_map - T(test_rgbs)) ** 2)))
+
+    ours_tr, ref_tr = float(np.mean(res['psnr_train'][-50:])), float(np.mean(ref['psnr_train'][-50:]))
+    print(f'scheduled run: train PSNR (last 50) ours {ours_tr:.3f} / reference {ref_tr:.3f} dB; test PSNR ours {res["psnr_test"]:.3f} / reference '
+          f'{ref_test:.3f} dB; box ours {m.aabb.cpu().numpy().round(4).tolist()} / reference {rm.aabb.numpy().round(4).tolist()}')
+    assert abs(res['psnr_train'][0] - ref['psnr_train'][0]) < 1e-3
+    assert np.allclose(m.aabb.cpu().numpy(), rm.aabb.numpy(), atol=2e-3)                      # the shrink found the same box
+    assert m.nSamples == rm.nSamples and list(m.gridSize.tolist()) == list(rm.gridSize.tolist())
+    assert m.alphaMask is not None and rm.alphaMask is not None
+    va, vb = m.alphaMask.alpha_volume.cpu().numpy() > 0.5, rm.alphaMask.alpha_volume.numpy() > 0.5
+    assert va.shape == vb.shape and (va != vb).mean() < 0.01                                   # same occupancy up to boundary voxels
+    assert abs(ours_tr - ref_tr) < 0.1 and abs(res['psnr_test'] - ref_test) < 0.1
