@@ -12,6 +12,7 @@ extern std::atomic<uint64_t> g_launches;
 int sm_count();             // of the current device (cached per device)
 int smem_optin_bytes();     // cudaDevAttrMaxSharedMemoryPerBlockOptin of the current device (cached per device)
 int current_device();
+extern int g_deterministic;   // knob "field_deterministic": bit-reproducible (serial) scatter-add for debugging / gradient tests
 void keep_pool_cached();
 
 // Function attributes (cudaFuncSetAttribute) are per device: `static PerDeviceOnce once; if (once.first()) { ... }`

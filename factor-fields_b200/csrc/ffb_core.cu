@@ -6,6 +6,7 @@
 namespace ffb {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+int g_deterministic = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -41,6 +41,7 @@ int ffb_field_query_fwd_train(ffb_field_t f, const float* x, int64_t n, const in
 // identical to ffb_field_query_bwd.
 int ffb_field_query_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
                               const float* coeff, const float* basis, float* const* h_grads, void* stream) {
+  if (ffb::g_deterministic) return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_bwd_saved(f, x, n, n_dev, g_feats, g_coeff, coeff, basis, h_grads, stream);
   if (ffb_field_lines_eligible(f) == 1) return ffb_field_lines_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
@@ -56,6 +57,7 @@ int ffb_field_query_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t*
 
 int ffb_field_query_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
                         float* const* h_grads, void* stream) {
+  if (ffb::g_deterministic) return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   if (ffb_field_lines_eligible(f) == 1) return ffb_field_lines_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);

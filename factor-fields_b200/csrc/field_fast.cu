@@ -556,6 +556,7 @@ int ffb_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "field_level_parallel")) g_lpar = value;
   else if (!strcmp(key, "field_bwd_agg_levels")) g_agg_levels = value;
   else if (!strcmp(key, "field_fwd_lpar_all")) g_fwd_lpar_all = value;
+  else if (!strcmp(key, "field_deterministic")) ffb::g_deterministic = value;
   else { set_error("ffb_set_tuning: unknown key %s", key); return FFB_EINVAL; }
   return FFB_OK;
 }

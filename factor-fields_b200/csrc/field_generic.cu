@@ -435,7 +435,11 @@ int ffb_field_generic_bwd(ffb_field_t f, const float* x, int64_t n, const int32_
   const unsigned blocks = blocks_for(n, 128, sm_count() * 32);
   field_generic_fwd<<<blocks, 128, 0, s>>>(f->d, x, n, n_dev, nullptr, c, b);
   g_launches.fetch_add(1);
-  field_generic_bwd<<<blocks, 128, 0, s>>>(f->d, x, n, n_dev, g_feats, g_coeff, c, b, G);
+  // "field_deterministic": ONE thread walks the queries in order, so every gradient element is summed in a fixed order and
+  // the result is bit-reproducible run to run (the reference's CUDA backward is not; its CPU backward is).  For debugging and
+  // gradient tests at small sizes — it is serial.
+  if (g_deterministic) field_generic_bwd<<<1, 1, 0, s>>>(f->d, x, n, n_dev, g_feats, g_coeff, c, b, G);
+  else field_generic_bwd<<<blocks, 128, 0, s>>>(f->d, x, n, n_dev, g_feats, g_coeff, c, b, G);
   g_launches.fetch_add(1);
   cudaError_t le = cudaGetLastError();
   cudaFreeAsync(c, s);

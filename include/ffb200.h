@@ -134,7 +134,9 @@ int ffb_field_fast_fwd_train(ffb_field_t f, const float* x, int64_t n, const int
 int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
                              const float* g_feats, const float* g_coeff, const float* coeff,
                              const float* basis, float* const* h_grads, void* stream);
-/* Experiment knobs (launch configurations of the field kernels): "field_fwd_cfg", "field_bwd_cfg". */
+/* Knobs: launch configurations of the field kernels ("field_fwd_cfg", "field_bwd_cfg", "field_level_parallel", ...) and
+ * "field_deterministic" (1: the scatter-add of every field runs serially in query order -> bit-reproducible gradients; for
+ * debugging and gradient tests at small sizes). */
 int ffb_set_tuning(const char* key, int value);
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange: in-place sum all-reduce of the flat fp32 gradient arena as ONE kernel over

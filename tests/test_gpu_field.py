@@ -175,3 +175,43 @@ def test_fast_path_matches_generic(name):
         res.append(grads)
     for a, b in zip(*res):
         assert H.rel_err(G.npy(b), G.npy(a)) < 5e-5
+
+
+@pytest.mark.parametrize('name', ['nerf_grid_box', 'nerf_vm', 'nerf_CP'])
+def test_deterministic_scatter_mode(name):
+    """ffb_set_tuning("field_deterministic", 1): the scatter-add runs serially in query order — two runs give bit-identical
+    gradients (the atomic path only agrees to rounding), and they equal the reference's within the usual tolerance."""
+    from ffb200 import native as nv
+    from tests import gpu_helpers as G
+    g = H.golden('field_' + name)
+    cfg, m = G.build_model(g)
+    rng = np.random.RandomState(17)
+    lo, hi = g['fact.aabb'][0], g['fact.aabb'][1]
+    x = G.t((lo + rng.rand(6000, lo.size) * (hi - lo)).astype(np.float32))
+    x[:g['x'].shape[0]] = G.t(g['x'])
+    Gm = G.t(rng.randn(6000, g['feats'].shape[1]).astype(np.float32))
+    Gm[:g['x'].shape[0]] = G.t(g['G'])
+    params = [(n, p) for n, p in m.named_parameters() if n.startswith('coeffs') or n.startswith('basises')]
+    runs = []
+    nv.check(nv.lib().ffb_set_tuning(b'field_deterministic', 1))
+    try:
+        for _ in range(2):
+            feats, _ = m.get_coding(x)
+            runs.append(torch.autograd.grad((feats * Gm).sum(), [p for _, p in params]))
+    finally:
+        nv.check(nv.lib().ffb_set_tuning(b'field_deterministic', 0))
+    feats, _ = m.get_coding(x)
+    atomic = torch.autograd.grad((feats * Gm).sum(), [p for _, p in params])
+    for a, b, c in zip(runs[0], runs[1], atomic):
+        assert torch.equal(a, b)                                    # bit-reproducible
+        assert H.rel_err(G.npy(c), G.npy(a)) < TOL_BWD
+    # the golden points alone reproduce the reference's gradients
+    nv.check(nv.lib().ffb_set_tuning(b'field_deterministic', 1))
+    try:
+        n0 = g['x'].shape[0]
+        f0, _ = m.get_coding(x[:n0])
+        gr = torch.autograd.grad((f0 * Gm[:n0]).sum(), [p for _, p in params])
+    finally:
+        nv.check(nv.lib().ffb_set_tuning(b'field_deterministic', 0))
+    for (n, p), a in zip(params, gr):
+        assert H.rel_err(G.npy(a), g['grad.' + n]) < TOL_BWD, n
