@@ -27,6 +27,8 @@ int ffb_field_planes_eligible(ffb_field_t f);
 int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis, void* stream);
 int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
                          float* const* h_grads, void* stream);
+int ffb_field_planes_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                               const float* coeff, const float* basis, float* const* h_grads, void* stream);
 
 // Training forward: also writes the concatenated basis row (needed by ffb_field_query_bwd_saved).
 int ffb_field_query_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
@@ -44,7 +46,7 @@ int ffb_field_query_bwd_saved(ffb_field_t f, const float* x, int64_t n, const in
   if (ffb::g_deterministic) return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
   if (ffb_field_fast_eligible(f) == 1) return ffb_field_fast_bwd_saved(f, x, n, n_dev, g_feats, g_coeff, coeff, basis, h_grads, stream);
   if (ffb_field_lines_eligible(f) == 1) return ffb_field_lines_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
-  if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
+  if (ffb_field_planes_eligible(f) == 1) return ffb_field_planes_bwd_saved(f, x, n, n_dev, g_feats, g_coeff, coeff, basis, h_grads, stream);
   return ffb_field_generic_bwd(f, x, n, n_dev, g_feats, g_coeff, h_grads, stream);
 }
 

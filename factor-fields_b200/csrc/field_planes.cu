@@ -135,16 +135,28 @@ __global__ void __launch_bounds__(VM_NT, MINB) vm_fwd_kernel(const VmParams P, c
 template <int MINB>
 __global__ void __launch_bounds__(VM_NT, MINB) vm_bwd_kernel(const VmParams P, const VmGrads G, const float* __restrict__ x, int64_t n_cap,
                                                              const int32_t* __restrict__ n_dev, const float* __restrict__ g_feats,
-                                                             const float* __restrict__ g_coeff) {
+                                                             const float* __restrict__ g_coeff, const float* __restrict__ coeff_saved,
+                                                             const float* __restrict__ basis_saved) {
+  // coeff_saved / basis_saved (both or neither): the [n, W] rows the training forward wrote — the backward then only
+  // recomputes tap indices / weights and scatters, instead of re-gathering 126 texel vectors per query
   extern __shared__ float vm_smem[];
   const int64_t n = resolve_n(n_cap, n_dev);
   const float msize = vm_msize(P);
   float* srow = vm_smem + threadIdx.x;
   const int W = P.W;
+  const bool saved = coeff_saved && basis_saved;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float xr[3];
     for (int k = 0; k < 3; ++k) xr[k] = x[i * 3 + k];
-    vm_coeff_row(P, xr, srow);
+    if (saved) {
+      for (int c = 0; c < W; c += 2) {
+        const float2 v = *reinterpret_cast<const float2*>(coeff_saved + i * W + c);
+        srow[c * VM_NT] = v.x;
+        srow[(c + 1) * VM_NT] = v.y;
+      }
+    } else {
+      vm_coeff_row(P, xr, srow);
+    }
     const float* gf = g_feats ? g_feats + i * W : nullptr;
     const float* gcf = g_coeff ? g_coeff + i * W : nullptr;
 #pragma unroll 1
@@ -158,13 +170,16 @@ __global__ void __launch_bounds__(VM_NT, MINB) vm_bwd_kernel(const VmParams P, c
         TapSet<2, false> tb;
         vm_plane_taps(P, L, m, u, tb);
         float b[4], gb[4];
-        if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb, b);
-        else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb, b);
+        if (!saved) {
+          if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb, b);
+          else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb, b);
+        }
         const int q0 = L.col + m * L.C;
         for (int j = 0; j < 4; ++j) {
           gb[j] = 0.0f;
           if (j < L.C) {
             const int p = __ldg(P.perm + q0 + j);
+            if (saved) b[j] = basis_saved[i * W + p];
             const float g = gf ? gf[p] : 0.0f;
             gb[j] = g * srow[p * VM_NT];                                   // d/d basis = g * coefficient
             srow[p * VM_NT] = g * b[j] + (gcf ? gcf[p] : 0.0f);            // d/d coefficient, in place
@@ -267,8 +282,8 @@ int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t
   return FFB_OK;
 }
 
-int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
-                         float* const* h_grads, void* stream) {
+int ffb_field_planes_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                               const float* coeff, const float* basis, float* const* h_grads, void* stream) {
   FFB_REQUIRE(f && x, "null argument");
   VmParams P;
   FFB_REQUIRE(g_planes_enabled && build_vm_params(f->h, P), "descriptor is not a vector-matrix (vm) field");
@@ -292,9 +307,14 @@ int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t
   if (once.first()) {
     FFB_CUDA(cudaFuncSetAttribute(vm_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   }
-  vm_bwd_kernel<6><<<blocks_for(n, VM_NT, (int64_t)sm_count() * 64), VM_NT, smem, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, g_coeff);
+  vm_bwd_kernel<6><<<blocks_for(n, VM_NT, (int64_t)sm_count() * 64), VM_NT, smem, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis);
   FFB_LAUNCHED();
   return FFB_OK;
+}
+
+int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats, const float* g_coeff,
+                         float* const* h_grads, void* stream) {
+  return ffb_field_planes_bwd_saved(f, x, n, n_dev, g_feats, g_coeff, nullptr, nullptr, h_grads, stream);
 }
 
 }  // extern "C"

@@ -97,6 +97,11 @@ class FieldPlan:
         nv.check(nv.lib().ffb_field_create(C.byref(desc), C.byref(self.handle)))
         self.ptrs = [t.data_ptr() if t is not None else 0 for t in tensors]
         self.fast = nv.lib().ffb_field_fast_eligible(self.handle) == 1   # specialised grid x grid kernels apply
+        # kernels whose backward scatters from rows saved by the training forward (basis row: blocked for the grid x grid kernels,
+        # row-major for the vm kernels)
+        # (measured for the vm kernels too — ffb_field_planes_bwd_saved — and left off: writing the permuted basis row costs the
+        # forward +0.16 ms at the -vm bench shape and the backward gains nothing over re-gathering L2-resident texels)
+        self.saves_rows = self.fast
 
     def stale(self):
         return any((t.data_ptr() if t is not None else 0) != p for t, p in zip(self.tensors, self.ptrs))
@@ -187,7 +192,7 @@ class FieldQuery(torch.autograd.Function):
         feats = _empty((n, plan.width), x)
         coeff = _empty((n, plan.width), x)
         # training: also keep the basis row, so the backward pass scatters without re-gathering
-        train = plan.fast and any(ctx.needs_input_grad[3:])
+        train = plan.saves_rows and any(ctx.needs_input_grad[3:])
         basis = _empty(((n + 31) // 32 * 32, plan.width), x) if train else None     # private, blocked by 32 rows (field_fast.cu: blk_idx)
         if n > 0:
             with nv.section('field_fwd'):

@@ -174,6 +174,10 @@ int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t
                          float* basis, void* stream);
 int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
                          const float* g_coeff, float* const* h_grads, void* stream);
+/* coeff / basis: the [n, W] rows written by ffb_field_planes_fwd (row-major; NULL: re-gather) */
+int ffb_field_planes_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
+                               const float* g_coeff, const float* coeff, const float* basis, float* const* h_grads,
+                               void* stream);
 /* The descriptor-driven generic kernels, callable directly (parity tests compare both paths).
  * basis_out: optional [n, W] copy of the (re-ordered) basis row. */
 int ffb_field_generic_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats,
