@@ -30,6 +30,19 @@ for lazy in (False, True):
     grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
     torch.cuda.synchronize()
     print('lazy', lazy, 'n_valid', int(m.last_stats['n_valid']), 'n_app', int(m.last_stats['n_app']), 'loss', float(loss))
+# the -CP / -vm preset kernels (field_lines.cu: TMA-staged lines + shared-memory-privatised accumulation; field_planes.cu)
+nv.check(nv.lib().ffb_set_tuning(b'field_level_parallel', 1))
+for ov in (['model.coeff_type=vec', 'model.basis_type=cp', 'model.freq_bands=[1.,1.,1.,1.,1.,1.]', 'model.basis_resos=[64,64,64,64,64,64]',
+            'model.basis_dims=[32,32,32,32,32,32]'], ['model.coeff_type=vm', 'model.basis_type=vm']):
+    c2 = ffb200.load_cfg('nerf.yaml', ['model.total_params=50000', 'model.coeff_reso=8'] + ov)
+    c2.dataset.aabb = [[-1.2, -0.7, -1.0], [1.3, 0.9, 0.8]]
+    m2 = FactorFields(c2, 'cuda:0')
+    plan = m2._plan('coding')
+    print('preset', ov[1], 'lines', nv.lib().ffb_field_lines_eligible(plan.handle), 'planes', nv.lib().ffb_field_planes_eligible(plan.handle))
+    xq = torch.rand(3000, 3, device='cuda') * torch.tensor([2.5, 1.6, 1.8], device='cuda') + torch.tensor([-1.2, -0.7, -1.0], device='cuda')
+    f2, _ = m2.get_coding(xq)
+    g2 = torch.autograd.grad((f2 ** 2).sum(), [p for n_, p in m2.named_parameters() if n_.startswith(('coeffs', 'basises'))])
+    torch.cuda.synchronize()
 # the decoupled look-back scan (> 64 K rows)
 c = torch.randint(0, 5, (70000,), device='cuda', dtype=torch.int32)
 o = ops.exclusive_scan(c)
