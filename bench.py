@@ -72,10 +72,12 @@ V = Variant('nerf')
 def latest_field_capture():
     """The newest committed `ncu --set full` summary of the field kernels (profiles/rNN_ncu_field*.json) -> (dict, path)."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_field*.json')))
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_*.json')))
     for f in reversed(files):
         try:
-            return json.load(open(f)), os.path.relpath(f, ROOT)
+            d = json.load(open(f))
+            if any('fast_fwd' in k for k in d) and any('fast_bwd' in k for k in d):
+                return d, os.path.relpath(f, ROOT)
         except Exception:
             pass
     return {}, None
@@ -165,6 +167,10 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # stdout carries exactly ONE line (the JSON): the reference prints its parameter count to stdout, route fd 1 to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     cores = os.cpu_count()
     torch.set_num_threads(cores)
@@ -194,7 +200,8 @@ def run_reference(args):
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': V.workload, 'rays_per_step': n},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample, 'note': REF_NOTE, 'stats': stats()},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
 
 
 def cpu_baseline_leg(n=256, steps=2):
