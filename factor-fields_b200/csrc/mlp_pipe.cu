@@ -45,11 +45,13 @@ __device__ __forceinline__ void mp_store2(uint8_t* row, uint32_t part_bytes, int
 
 // ---------------------------------------------------------------------------------------------------------
 // forward:  y = relu([x | 1] [W1 | b1]^T) W2^T
-// warps: 0..6 producers, 7 layer-1 issuer, 8..23 epilogue — group = (warp - 8) >> 3 takes tiles t = group mod 2; inside a group
+// warps: 0..6 producers, 7 layer-1 issuer, 8.. epilogue — group = (warp - 8) >> 3 takes tiles t = group mod MPF_NGROUPS; inside a group
 // q = warp & 3 is the TMEM lane quarter and half = ((warp - 8) >> 2) & 1 the column half.  (The SM's warp arbiter favours
 // the highest warp ids: the latency-critical epilogue warps sit there, the producers — who mostly wait for a free slot — below.)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int MPF_THREADS = 24 * 32, MPF_NPROD = 7, MPF_ISSUER = 7, MPF_EPI0 = 8, MPF_NSLOT = 3, MPF_TERMS = 3;
+constexpr int MPF_NGROUPS = 3;      // epilogue groups (tiles in the epilogue stage at once); each owns an accumulator pair and a hidden tile
+constexpr int MPF_THREADS = (8 + 8 * MPF_NGROUPS) * 32, MPF_NPROD = 7, MPF_ISSUER = 7, MPF_EPI0 = 8, MPF_NSLOT = 2, MPF_TERMS = 3;
+constexpr uint32_t MPF_TMEM_COLS = 512;      // NGROUPS x (64 + 32) accumulator columns
 constexpr uint32_t MPF_XPART = 4 * MP_SC, MPF_XSLOT = MPF_TERMS * MPF_XPART;      // 8 KB / 24 KB
 constexpr uint32_t MPF_HPART = 8 * MP_SC, MPF_HBUF = MPF_TERMS * MPF_HPART;       // 16 KB / 48 KB
 struct MpfSmem {
@@ -57,8 +59,8 @@ struct MpfSmem {
   static constexpr uint32_t W2 = W1 + MPF_TERMS * MP_H * MP_K0P * 2;
   static constexpr uint32_t X = W2 + MPF_TERMS * MP_NP * MP_H * 2;
   static constexpr uint32_t HID = X + MPF_NSLOT * MPF_XSLOT;
-  static constexpr uint32_t BAR = HID + 2 * MPF_HBUF;
-  static constexpr uint32_t N_BAR = 2 * MPF_NSLOT + 2 + 2 + 2;     // slot_full, slot_free, d1_full[2], d1_free[2], d2_full[2]
+  static constexpr uint32_t BAR = HID + MPF_NGROUPS * MPF_HBUF;
+  static constexpr uint32_t N_BAR = 2 * MPF_NSLOT + 3 * MPF_NGROUPS;     // slot_full, slot_free, d1_full[G], d1_free[G], d2_full[G]
   static constexpr uint32_t MISC = BAR + N_BAR * 8;
   static constexpr uint32_t TOTAL = MISC + 16;
 };
@@ -78,19 +80,19 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
   uint64_t* slot_full = bars;
   uint64_t* slot_free = bars + MPF_NSLOT;
   uint64_t* d1_full = bars + 2 * MPF_NSLOT;
-  uint64_t* d1_free = d1_full + 2;
-  uint64_t* d2_full = d1_free + 2;
+  uint64_t* d1_free = d1_full + MPF_NGROUPS;
+  uint64_t* d2_full = d1_free + MPF_NGROUPS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MpfSmem::MISC);
   int* next_chunk = reinterpret_cast<int*>(smem + MpfSmem::MISC + 4);
   const int K0 = S.K0, N = S.N;
 
-  if (warp == MPF_ISSUER) tmem_alloc(tmem_slot, 256u);
+  if (warp == MPF_ISSUER) tmem_alloc(tmem_slot, MPF_TMEM_COLS);
   if (tid == 0) {
     for (int s = 0; s < MPF_NSLOT; ++s) {
       mbar_init(slot_full + s, 4);
       mbar_init(slot_free + s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < MPF_NGROUPS; ++b) {
       mbar_init(d1_full + b, 1);
       mbar_init(d1_free + b, 256);
       mbar_init(d2_full + b, 1);
@@ -165,10 +167,10 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
       const uint32_t idesc1 = make_idesc(MP_H, 0, 0);
       const DescBase dW1b = desc_base(smem_u32(sW1), MP_H * 16, TILE_SR);
       for (int64_t t = 0; t < Tc; ++t) {
-        const int slot = (int)(t % MPF_NSLOT), b = (int)(t & 1);
+        const int slot = (int)(t % MPF_NSLOT), b = (int)(t % MPF_NGROUPS);
         mbar_wait(slot_full + slot, (uint32_t)((t / MPF_NSLOT) & 1));
         mp_trace(40, t);                              // slot full
-        mbar_wait(d1_free + b, (uint32_t)(((t >> 1) & 1) ^ 1));
+        mbar_wait(d1_free + b, (uint32_t)(((t / MPF_NGROUPS) & 1) ^ 1));
         mp_trace(41, t);                              // accumulator free
         tc_fence_after();
         const uint32_t aX = smem_u32(sX) + (uint32_t)slot * MPF_XSLOT;
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
     // ------------------------------ epilogue: group g handles tiles g, g+2, ...; a thread owns one row and one column half
     const int ew = warp - MPF_EPI0, g = ew >> 3, half = (ew >> 2) & 1, q = warp & 3, row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t d1 = tmem + (uint32_t)g * MP_H, d2 = tmem + 2u * MP_H + (uint32_t)g * MP_NP;
+    const uint32_t d1 = tmem + (uint32_t)g * MP_H, d2 = tmem + (uint32_t)MPF_NGROUPS * MP_H + (uint32_t)g * MP_NP;
     const uint32_t idesc2 = make_idesc(MP_NP, 0, 0);
     uint8_t* myH = sH + (uint32_t)g * MPF_HBUF;
     const DescBase dHb = desc_base(smem_u32(myH), MP_SC, TILE_SR), dW2b = desc_base(smem_u32(sW2), MP_NP * 16, TILE_SR);
@@ -212,8 +214,8 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
       }
     };
     int64_t k = 0;
-    for (int64_t t = g; t < Tc; t += 2, ++k) {
-      if (k > 0) epi2(t - 2, k - 1);          // also: layer 2 of this group's previous tile has finished reading the hidden tile
+    for (int64_t t = g; t < Tc; t += MPF_NGROUPS, ++k) {
+      if (k > 0) epi2(t - MPF_NGROUPS, k - 1);          // also: layer 2 of this group's previous tile has finished reading the hidden tile
       if (tr) mp_trace(52, t);                        // epilogue 2 done
       mbar_wait(d1_full + g, (uint32_t)(k & 1));
       if (tr) mp_trace(53, t);                        // layer 1 complete
@@ -245,11 +247,11 @@ __global__ void __launch_bounds__(MPF_THREADS, 1) mlp2p_fwd_kernel(const float* 
         umma_commit(d2_full + g);
       }
     }
-    if (k > 0) epi2(g + 2 * (k - 1), k - 1);
+    if (k > 0) epi2(g + MPF_NGROUPS * (k - 1), k - 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MPF_ISSUER) tmem_dealloc(tmem, 256u);
+  if (warp == MPF_ISSUER) tmem_dealloc(tmem, MPF_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------
