@@ -21,7 +21,41 @@ namespace ffb {
 // LPAR (small batches: the regression drivers' 40-100 k points leave most of the 148 SMs without work at one thread per
 // query): one thread per (query, level) — consecutive lanes take the levels of one query, so a query's row segments are
 // still written by neighbouring lanes; the coefficient taps are recomputed per level (ALU only).
-template <int DB, int DC, bool NEAR_B, bool NEAR_C, int NT, int MINB, bool STAGE, bool LPAR = false>
+// The whole WC-channel coefficient row of a query in one pass over its 2^DC corners, each texel fetched as ALIGNED 16-byte
+// pieces: a texel of WC = 18 floats (72 B) starts 16-byte aligned for even texel indices and 8 bytes past an aligned address for
+// odd ones, so a window of 5 float4 starting at the aligned address below it covers the texel either way (2 floats of the
+// neighbouring texel ride along: always inside the tensor when the texel count is even).  40 loads per query instead of the
+// 72 8-byte loads of the per-level gathers; same corner order and weights, so the sums are bit-identical.
+template <int DC, int WC>
+__device__ __forceinline__ void coeff_row_windows(const float* __restrict__ cdata, const TapSet<DC, false>& t, float acc[WC]) {
+  static_assert((WC & 1) == 0 && (WC % 4) == 2, "window scheme written for rows of 4k + 2 floats (8-byte aligned texels)");
+  constexpr int ROWS = 1 << (DC - 1), NQ = (WC + 2) / 4;
+#pragma unroll
+  for (int c = 0; c < WC; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (!t.row_ok[r]) continue;
+#pragma unroll
+    for (int xs = 0; xs < 2; ++xs) {
+      const float wx = xs ? t.wx1 : t.wx0;
+      if (xs ? !t.x1_ok : (wx == 0.0f)) continue;
+      const float w = t.wrow[r] * wx;
+      const size_t e0 = (size_t)(t.base[r] + xs) * WC;
+      const bool odd = (e0 & 2) != 0;
+      const float4* p = reinterpret_cast<const float4*>(cdata + (e0 - (odd ? 2 : 0)));
+      float win[NQ * 4];
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        const float4 q = __ldg(p + k);
+        win[4 * k] = q.x; win[4 * k + 1] = q.y; win[4 * k + 2] = q.z; win[4 * k + 3] = q.w;
+      }
+#pragma unroll
+      for (int c = 0; c < WC; ++c) acc[c] += (odd ? win[c + 2] : win[c]) * w;
+    }
+  }
+}
+
+template <int DB, int DC, bool NEAR_B, bool NEAR_C, int NT, int MINB, bool STAGE, bool LPAR = false, int CROW = 0>
 __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, const float* __restrict__ x, int64_t n,
                                                             const int32_t* __restrict__ n_dev, float* __restrict__ feats,
                                                             float* __restrict__ coeff, float* __restrict__ basis) {
@@ -51,6 +85,12 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
       float* frow = STAGE ? sB + lane * W : (feats ? feats + i * W : nullptr);
       float* crow = STAGE ? sC + lane * W : (coeff ? coeff + i * W : nullptr);
       float* brow = nullptr;                              // the saved basis row is written blocked, below
+      if constexpr (CROW > 0) {                           // CROW = W: the coefficient row first, by aligned 16-byte windows
+        float acc[CROW > 0 ? CROW : 2];
+        coeff_row_windows<DC, (CROW > 0 ? CROW : 2)>(P.cdata, tc, acc);
+#pragma unroll
+        for (int c = 0; c < CROW; c += 2) *reinterpret_cast<float2*>(crow + c) = make_float2(acc[c], acc[c + 1]);
+      }
       for (int l = l_begin; l < l_end; ++l) {
         const FastLevel L = P.lv[l];
         TapSet<DB, NEAR_B> tb;
@@ -59,14 +99,19 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
           for (int c0 = 0; c0 < L.C; c0 += 4) {
             float b[4], ca[2], cb[2];
             gather_vec<DB, NEAR_B, 4>(L.data, L.C, c0, tb, b);
-            gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
-            gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0 + 2, tc, cb);
             const int o = L.col + c0;
+            if (CROW > 0) {
+              const float2 t0 = *reinterpret_cast<const float2*>(crow + o), t1 = *reinterpret_cast<const float2*>(crow + o + 2);
+              ca[0] = t0.x; ca[1] = t0.y; cb[0] = t1.x; cb[1] = t1.y;
+            } else {
+              gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
+              gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0 + 2, tc, cb);
+            }
             if (frow) {
               *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
               *reinterpret_cast<float2*>(frow + o + 2) = make_float2(b[2] * cb[0], b[3] * cb[1]);
             }
-            if (crow) {
+            if (crow && CROW == 0) {
               *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
               *reinterpret_cast<float2*>(crow + o + 2) = make_float2(cb[0], cb[1]);
             }
@@ -82,10 +127,15 @@ __global__ void __launch_bounds__(NT, MINB) fast_fwd_kernel(const FastParams P, 
           for (int c0 = 0; c0 < L.C; c0 += 2) {
             float b[2], ca[2];
             gather_vec<DB, NEAR_B, 2>(L.data, L.C, c0, tb, b);
-            gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
             const int o = L.col + c0;
+            if (CROW > 0) {
+              const float2 t0 = *reinterpret_cast<const float2*>(crow + o);
+              ca[0] = t0.x; ca[1] = t0.y;
+            } else {
+              gather_vec<DC, NEAR_C, 2>(P.cdata, W, L.col + c0, tc, ca);
+            }
             if (frow) *reinterpret_cast<float2*>(frow + o) = make_float2(b[0] * ca[0], b[1] * ca[1]);
-            if (crow) *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
+            if (crow && CROW == 0) *reinterpret_cast<float2*>(crow + o) = make_float2(ca[0], ca[1]);
             if (brow) *reinterpret_cast<float2*>(brow + o) = make_float2(b[0], b[1]);
             else if (basis) { basis[blk_idx(i, o, W)] = b[0]; basis[blk_idx(i, o + 1, W)] = b[1]; }
           }
@@ -466,6 +516,7 @@ using namespace ffb;
 
 // ---- launch configuration (tunable at run time for experiments; defaults are the measured best) -------------
 static int g_fwd_cfg = 1;   // 0: 128 threads, compiler-chosen registers   1: 128 x >=8 CTAs/SM   2: 128 x >=6   3: 256 x >=4
+static int g_fwd_crow = 1;  // 1: W == 18 rows take the coefficient row by aligned 16-byte windows first (knob "field_fwd_crow")
 static int g_fwd_stage = 1; // 1: narrow rows (W <= 32) leave through shared memory as coalesced 16-byte pieces (278 -> 273 us at nerf.yaml)
 static int g_bwd_cfg = 2;   // 0: re-gathering kernel   1: saved-activation kernel (when coeff/basis rows are supplied)   2: 1 + run-aggregated coefficient scatter
 static int g_agg_levels = 0;   // leading 4-channel basis levels whose scatter is run-aggregated too (knob "field_bwd_agg_levels"): measured
@@ -485,6 +536,11 @@ static void launch_fwd_cfg(const FastParams& P, const float* x, int64_t n, const
   const unsigned grid = blocks_for(n, NT, (int64_t)sm_count() * 64);
   if (P.W <= 32 && g_fwd_stage) {
     const size_t smem = (size_t)(NT / 32) * 64 * P.W * sizeof(float);
+    const int64_t texels = (int64_t)P.csize[0] * P.csize[1] * P.csize[2];
+    if (!NC && P.W == 18 && g_fwd_crow && (texels & 1) == 0) {
+      fast_fwd_kernel<DB, DC, NB, false, NT, MINB, true, false, 18><<<grid, NT, smem, s>>>(P, x, n, n_dev, feats, coeff, basis);
+      return;
+    }
     fast_fwd_kernel<DB, DC, NB, NC, NT, MINB, true><<<grid, NT, smem, s>>>(P, x, n, n_dev, feats, coeff, basis);
   } else {
     fast_fwd_kernel<DB, DC, NB, NC, NT, MINB, false><<<grid, NT, 0, s>>>(P, x, n, n_dev, feats, coeff, basis);
@@ -553,6 +609,7 @@ int ffb_set_tuning(const char* key, int value) {
   if (!strcmp(key, "field_fwd_cfg")) g_fwd_cfg = value;
   else if (!strcmp(key, "field_bwd_cfg")) g_bwd_cfg = value;
   else if (!strcmp(key, "field_fwd_stage")) g_fwd_stage = value;
+  else if (!strcmp(key, "field_fwd_crow")) g_fwd_crow = value;
   else if (!strcmp(key, "field_level_parallel")) g_lpar = value;
   else if (!strcmp(key, "field_bwd_agg_levels")) g_agg_levels = value;
   else if (!strcmp(key, "field_fwd_lpar_all")) g_fwd_lpar_all = value;
