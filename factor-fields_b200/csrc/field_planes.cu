@@ -61,12 +61,44 @@ __device__ __forceinline__ float vm_msize(const VmParams& P) {
   return m;
 }
 
+// one texel of WC = 4k + 2 floats through aligned 16-byte loads (see coeff_row_windows in field_fast.cu): out[c] = texel[c]
+template <int WC>
+__device__ __forceinline__ void texel_window(const float* __restrict__ data, size_t texel, float out[WC]) {
+  constexpr int NQ = (WC + 2) / 4;
+  const size_t e0 = texel * WC;
+  const bool odd = (e0 & 2) != 0;
+  const float4* p = reinterpret_cast<const float4*>(data + (e0 - (odd ? 2 : 0)));
+  float win[NQ * 4];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    const float4 q = __ldg(p + k);
+    win[4 * k] = q.x; win[4 * k + 1] = q.y; win[4 * k + 2] = q.z; win[4 * k + 3] = q.w;
+  }
+#pragma unroll
+  for (int c = 0; c < WC; ++c) out[c] = odd ? win[c + 2] : win[c];
+}
+
 // coefficient row of this thread's query -> srow[c * VM_NT] (c < 3 Cc)
 __device__ __forceinline__ void vm_coeff_row(const VmParams& P, const float* xr, float* srow) {
 #pragma unroll 1
   for (int m = 0; m < 3; ++m) {
     const LTap t = vm_line_tap(P, m, xr);
     const float* base = P.cline[m];
+    if (P.Cc == 18 && (P.Hc & 1) == 0) {          // 72-byte texels: 5 aligned 16-byte loads per tap instead of 9 8-byte ones
+      float a[18], b[18];
+#pragma unroll
+      for (int c = 0; c < 18; ++c) a[c] = b[c] = 0.0f;
+      if (t.ok0) texel_window<18>(base, (size_t)t.i0, a);
+      if (t.ok1) texel_window<18>(base, (size_t)(t.i0 + 1), b);
+#pragma unroll
+      for (int c = 0; c < 18; ++c) {
+        float v = 0.0f;
+        if (t.ok0) v += a[c] * t.w0;
+        if (t.ok1) v += b[c] * t.w1;
+        srow[(m * 18 + c) * VM_NT] = v;
+      }
+      continue;
+    }
     for (int c = 0; c < P.Cc; c += 2) {
       float2 v = make_float2(0.f, 0.f);
       if (t.ok0) {
