@@ -510,6 +510,101 @@ __global__ void __launch_bounds__(NT, MINB) fast_bwd_saved_agg_kernel(const Fast
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Wide rows (image.yaml / image_set.yaml: W = 144 channels, levels of 32 / 16): one thread per (query, 16-byte column group).
+// Consecutive lanes are consecutive column groups of one query, so every access of a warp is coalesced: the texel of a query
+// (W floats of the coefficient grid, C_l floats of a basis level) is read as contiguous float4 pieces by neighbouring lanes and
+// the feats / coeff / basis rows leave as contiguous 512-byte pieces — one thread per query (or per (query, level)) walks its
+// 576-byte row alone, 32 lanes 576 bytes apart (image.yaml forward 157 us for 102 400 points = 0.17 of the HBM model).  The
+// coordinate arithmetic is repeated by the W / 4 lanes of a query (ALU only; same ffb_math.h sequence, identical tap indices).
+// The saved basis row of this kernel pair is ROW-MAJOR [n, W] (the narrow kernels store theirs blocked by 32 queries).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wide_level(const FastParams& P, int c) {
+  int l = 0;
+  while (l + 1 < P.n_levels && P.lv[l + 1].col <= c) ++l;
+  return l;
+}
+
+template <int DB, int DC, bool NEAR_B, bool NEAR_C>
+__global__ void __launch_bounds__(256) wide_fwd_kernel(const FastParams P, const float* __restrict__ x, int64_t n,
+                                                       const int32_t* __restrict__ n_dev, float* __restrict__ feats,
+                                                       float* __restrict__ coeff, float* __restrict__ basis) {
+  n = resolve_n(n, n_dev);
+  const float msize = fast_msize(P);
+  const unsigned W4 = (unsigned)P.W >> 2;
+  const unsigned n_items = (unsigned)n * W4;                       // < 2^31 (checked by the launcher)
+  for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+    const unsigned i = item / W4;
+    const int c = (int)(item - i * W4) * 4;
+    const int l = wide_level(P, c);
+    const FastLevel& L = P.lv[l];
+    float xr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < DC; ++d) xr[d] = x[(size_t)i * DC + d];
+    TapSet<DC, NEAR_C> tc;
+    coeff_taps<DC, NEAR_C>(P, xr, tc);
+    TapSet<DB, NEAR_B> tb;
+    basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
+    float b[4], ca[4];
+    gather_vec<DB, NEAR_B, 4>(L.data, L.C, c - L.col, tb, b);
+    gather_vec<DC, NEAR_C, 4>(P.cdata, P.W, c, tc, ca);
+    const size_t o = (size_t)i * P.W + c;
+    if (feats) *reinterpret_cast<float4*>(feats + o) = make_float4(b[0] * ca[0], b[1] * ca[1], b[2] * ca[2], b[3] * ca[3]);
+    if (coeff) *reinterpret_cast<float4*>(coeff + o) = make_float4(ca[0], ca[1], ca[2], ca[3]);
+    if (basis) *reinterpret_cast<float4*>(basis + o) = make_float4(b[0], b[1], b[2], b[3]);
+  }
+}
+
+// coeff / basis (both or neither): the rows saved by wide_fwd_kernel; otherwise the texels are re-gathered (coalesced as well)
+template <int DB, int DC, bool NEAR_B, bool NEAR_C>
+__global__ void __launch_bounds__(256) wide_bwd_kernel(const FastParams P, const FastGrads G, const float* __restrict__ x, int64_t n,
+                                                       const int32_t* __restrict__ n_dev, const float* __restrict__ g_feats,
+                                                       const float* __restrict__ g_coeff, const float* __restrict__ coeff,
+                                                       const float* __restrict__ basis) {
+  n = resolve_n(n, n_dev);
+  const float msize = fast_msize(P);
+  const unsigned W4 = (unsigned)P.W >> 2;
+  const unsigned n_items = (unsigned)n * W4;
+  const bool saved = coeff && basis;
+  for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+    const unsigned i = item / W4;
+    const int c = (int)(item - i * W4) * 4;
+    const int l = wide_level(P, c);
+    const FastLevel& L = P.lv[l];
+    float xr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < DC; ++d) xr[d] = x[(size_t)i * DC + d];
+    TapSet<DC, NEAR_C> tc;
+    coeff_taps<DC, NEAR_C>(P, xr, tc);
+    TapSet<DB, NEAR_B> tb;
+    basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
+    const size_t o = (size_t)i * P.W + c;
+    float b[4], ca[4];
+    if (saved) {
+      const float4 bv = *reinterpret_cast<const float4*>(basis + o), cv = *reinterpret_cast<const float4*>(coeff + o);
+      b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+      ca[0] = cv.x; ca[1] = cv.y; ca[2] = cv.z; ca[3] = cv.w;
+    } else {
+      gather_vec<DB, NEAR_B, 4>(L.data, L.C, c - L.col, tb, b);
+      gather_vec<DC, NEAR_C, 4>(P.cdata, P.W, c, tc, ca);
+    }
+    const float4 g = g_feats ? *reinterpret_cast<const float4*>(g_feats + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float gc[4] = {g.x * b[0], g.y * b[1], g.z * b[2], g.w * b[3]};
+    if (g_coeff) {
+      const float4 g2 = *reinterpret_cast<const float4*>(g_coeff + o);
+      gc[0] += g2.x; gc[1] += g2.y; gc[2] += g2.z; gc[3] += g2.w;
+    }
+    const float gb[4] = {g.x * ca[0], g.y * ca[1], g.z * ca[2], g.w * ca[3]};
+    float* gbl = nullptr;                       // G.b[l] without indexing the parameter struct dynamically (local-memory copy)
+#pragma unroll
+    for (int k = 0; k < FAST_MAX_LEVELS; ++k)
+      if (k == l) gbl = G.b[k];
+    if (G.c) scatter_vec<DC, NEAR_C, 4>(G.c, P.W, c, tc, gc);
+    if (gbl) scatter_vec<DB, NEAR_B, 4>(gbl, L.C, c - L.col, tb, gb);
+  }
+}
+
 }  // namespace ffb
 
 using namespace ffb;
@@ -524,10 +619,27 @@ static int g_agg_levels = 0;   // leading 4-channel basis levels whose scatter i
 static int g_fwd_lpar_all = 0;  // experiment knob "field_fwd_lpar_all": level-parallel forward at every batch size
 static int g_lpar = 1;      // 1: batches of at most LPAR_MAX_ITEMS (query, level) pairs use the level-parallel kernels
 constexpr int64_t LPAR_MAX_ITEMS = 148 * 2048 * 3;   // ~3 full waves of resident threads; above that one thread per query wins
+static int g_wide = 1;      // knob "field_wide": rows of >= 64 channels in 16-byte texel pieces take the column-parallel kernels
+
+// wide rows: every level's channels and offset a multiple of 4 floats (16-byte pieces never straddle a level or a texel)
+// (a function of the field and the batch size only: the forward and the backward launch must agree on the saved-row layout)
+static bool wide_eligible(const FastParams& P, int64_t n) {
+  if (!g_wide || P.W < 64 || (P.W & 3) || n * (P.W >> 2) >= ((int64_t)1 << 31)) return false;
+  for (int l = 0; l < P.n_levels; ++l)
+    if ((P.lv[l].C & 3) || (P.lv[l].col & 3)) return false;
+  return true;
+}
+static bool aligned16(const void* a, const void* b, const void* c, const void* d) {
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+}
 
 template <int DB, int DC, bool NB, bool NC, int NT, int MINB>
 static void launch_fwd_cfg(const FastParams& P, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
                            cudaStream_t s) {
+  if (wide_eligible(P, n)) {
+    wide_fwd_kernel<DB, DC, NB, NC><<<blocks_for(n * (P.W >> 2), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(P, x, n, n_dev, feats, coeff, basis);
+    return;
+  }
   if (n * P.n_levels <= (g_fwd_lpar_all ? (int64_t)1 << 40 : LPAR_MAX_ITEMS) && g_lpar) {      // small batch: one thread per (query, level)
     fast_fwd_kernel<DB, DC, NB, NC, NT, MINB, false, true><<<blocks_for(n * P.n_levels, NT, (int64_t)sm_count() * 64), NT, 0, s>>>(
         P, x, n, n_dev, feats, coeff, basis);
@@ -562,6 +674,12 @@ template <int DB, int DC, bool NB, bool NC>
 static void launch_bwd(const FastParams& P, const FastGrads& G, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
                        const float* g_coeff, const float* coeff, const float* basis, cudaStream_t s) {
   const int64_t cap = (int64_t)sm_count() * 64;
+  if (wide_eligible(P, n)) {
+    const bool saved = coeff && basis;
+    wide_bwd_kernel<DB, DC, NB, NC><<<blocks_for(n * (P.W >> 2), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(
+        P, G, x, n, n_dev, g_feats, g_coeff, saved ? coeff : nullptr, saved ? basis : nullptr);
+    return;
+  }
   if (coeff && basis && g_bwd_cfg != 0 && n * P.n_levels <= LPAR_MAX_ITEMS && g_lpar) {
     fast_bwd_saved_kernel<DB, DC, NB, NC, 0, 128, 6, true><<<blocks_for(n * P.n_levels, 128, cap), 128, 0, s>>>(P, G, x, n, n_dev, g_feats, g_coeff,
                                                                                                             coeff, basis);
@@ -602,6 +720,8 @@ static bool mode_supported(ffb_field_t f, const FastParams& P) {
   return false;
 }
 
+extern "C" int ffb_set_field_planes_tuning(int which, int value);
+
 extern "C" {
 
 int ffb_set_tuning(const char* key, int value) {
@@ -613,7 +733,10 @@ int ffb_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "field_level_parallel")) g_lpar = value;
   else if (!strcmp(key, "field_bwd_agg_levels")) g_agg_levels = value;
   else if (!strcmp(key, "field_fwd_lpar_all")) g_fwd_lpar_all = value;
+  else if (!strcmp(key, "field_wide")) g_wide = value;
   else if (!strcmp(key, "field_deterministic")) ffb::g_deterministic = value;
+  else if (!strcmp(key, "field_planes_v2")) return ffb_set_field_planes_tuning(0, value);
+  else if (!strcmp(key, "field_planes_unroll")) return ffb_set_field_planes_tuning(1, value);
   else { set_error("ffb_set_tuning: unknown key %s", key); return FFB_EINVAL; }
   return FFB_OK;
 }
@@ -625,6 +748,14 @@ int ffb_field_fast_eligible(ffb_field_t f) {
   return (build_params(f->h, P, idx) && mode_supported(f, P)) ? 1 : 0;
 }
 
+int ffb_field_saved_basis_layout(ffb_field_t f, int64_t n) {
+  if (!f) return -1;
+  FastParams P;
+  int idx[FAST_MAX_LEVELS + 1];
+  if (!(build_params(f->h, P, idx) && mode_supported(f, P))) return -1;
+  return wide_eligible(P, n) ? 1 : 0;
+}
+
 int ffb_field_fast_fwd_train(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
                              void* stream) {
   FFB_REQUIRE(f && x, "null argument");
@@ -632,6 +763,7 @@ int ffb_field_fast_fwd_train(ffb_field_t f, const float* x, int64_t n, const int
   int idx[FAST_MAX_LEVELS + 1];
   FFB_REQUIRE(build_params(f->h, P, idx) && mode_supported(f, P), "descriptor is not eligible for the fast path");
   if (n <= 0) return FFB_OK;
+  FFB_REQUIRE(!wide_eligible(P, n) || aligned16(feats, coeff, basis, nullptr), "feats / coeff / basis rows must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   FAST_DISPATCH(launch_fwd, P, x, n, n_dev, feats, coeff, basis, s);
   FFB_LAUNCHED();
@@ -657,6 +789,7 @@ int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int
     aligned = aligned && ((uintptr_t)G.b[l] & 15) == 0;
   }
   FFB_REQUIRE(aligned, "gradient tensors must be 16-byte aligned");
+  FFB_REQUIRE(!wide_eligible(P, n) || aligned16(g_feats, g_coeff, coeff, basis), "gradient / saved rows must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   FAST_DISPATCH(launch_bwd, P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis, s);
   FFB_LAUNCHED();

@@ -45,9 +45,12 @@ struct LTap {
   bool ok0, ok1;
 };
 
+// v[a] for a run-time axis a without indexing a register array dynamically (that would put it in local memory)
+__device__ __forceinline__ float pick3(const float* v, int a) { return a == 0 ? v[0] : (a == 1 ? v[1] : v[2]); }
+
 __device__ __forceinline__ LTap vm_line_tap(const VmParams& P, int m, const float* xr) {
   const int a = P.caxis[m];
-  const Axis ax = linear_axis(source_index(normalize_coord(xr[a], P.lo[a], P.hi[a]), P.Hc, 0, 1));
+  const Axis ax = linear_axis(source_index(normalize_coord(pick3(xr, a), P.lo[a], P.hi[a]), P.Hc, 0, 1));
   LTap t;
   t.i0 = ax.i0; t.w0 = ax.w0; t.w1 = ax.w1;
   t.ok0 = ax.i0 >= 0 && ax.i0 < P.Hc;
@@ -78,7 +81,9 @@ __device__ __forceinline__ void texel_window(const float* __restrict__ data, siz
   for (int c = 0; c < WC; ++c) out[c] = odd ? win[c + 2] : win[c];
 }
 
-// coefficient row of this thread's query -> srow[c * VM_NT] (c < 3 Cc)
+// coefficient row of this thread's query -> srow[c * CS] (c < 3 Cc); CS = VM_NT: one column of a [W][threads] tile per thread,
+// CS = 1: one row of a [32][W + 1] warp tile per lane
+template <int CS = VM_NT>
 __device__ __forceinline__ void vm_coeff_row(const VmParams& P, const float* xr, float* srow) {
 #pragma unroll 1
   for (int m = 0; m < 3; ++m) {
@@ -95,7 +100,7 @@ __device__ __forceinline__ void vm_coeff_row(const VmParams& P, const float* xr,
         float v = 0.0f;
         if (t.ok0) v += a[c] * t.w0;
         if (t.ok1) v += b[c] * t.w1;
-        srow[(m * 18 + c) * VM_NT] = v;
+        srow[(m * 18 + c) * CS] = v;
       }
       continue;
     }
@@ -109,8 +114,8 @@ __device__ __forceinline__ void vm_coeff_row(const VmParams& P, const float* xr,
         const float2 b = __ldg(reinterpret_cast<const float2*>(base + (size_t)(t.i0 + 1) * P.Cc + c));
         v.x += b.x * t.w1; v.y += b.y * t.w1;
       }
-      srow[(m * P.Cc + c) * VM_NT] = v.x;
-      srow[(m * P.Cc + c + 1) * VM_NT] = v.y;
+      srow[(m * P.Cc + c) * CS] = v.x;
+      srow[(m * P.Cc + c + 1) * CS] = v.y;
     }
   }
 }
@@ -118,8 +123,9 @@ __device__ __forceinline__ void vm_coeff_row(const VmParams& P, const float* xr,
 __device__ __forceinline__ void vm_plane_taps(const VmParams& P, const VmLevel& L, int m, const float u[3], TapSet<2, false>& t) {
   float c[3];
   const int size[3] = {L.pw[m], L.ph[m], 1};
-  c[0] = source_index(u[P.ax0[m]], L.pw[m], 1, 0);
-  c[1] = source_index(u[P.ax1[m]], L.ph[m], 1, 0);
+  c[0] = source_index(pick3(u, P.ax0[m]), L.pw[m], 1, 0);
+  c[1] = source_index(pick3(u, P.ax1[m]), L.ph[m], 1, 0);
+  c[2] = 0.0f;
   make_tapset<2, false>(c, size, t);
 }
 
@@ -134,6 +140,7 @@ __global__ void __launch_bounds__(VM_NT, MINB) vm_fwd_kernel(const VmParams P, c
   const int W = P.W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float xr[3];
+#pragma unroll
     for (int k = 0; k < 3; ++k) xr[k] = x[i * 3 + k];
     vm_coeff_row(P, xr, srow);
     if (coeff_out)
@@ -143,6 +150,7 @@ __global__ void __launch_bounds__(VM_NT, MINB) vm_fwd_kernel(const VmParams P, c
       const VmLevel& L = P.lv[l];
       const float scale = FFB_DIV(msize, L.freq);
       float u[3];
+#pragma unroll
       for (int k = 0; k < 3; ++k) u[k] = map_coord(xr[k], P.lo[k], scale, P.mapping, nullptr);
 #pragma unroll 1
       for (int m = 0; m < 3; ++m) {
@@ -179,6 +187,7 @@ __global__ void __launch_bounds__(VM_NT, MINB) vm_bwd_kernel(const VmParams P, c
   const bool saved = coeff_saved && basis_saved;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float xr[3];
+#pragma unroll
     for (int k = 0; k < 3; ++k) xr[k] = x[i * 3 + k];
     if (saved) {
       for (int c = 0; c < W; c += 2) {
@@ -196,6 +205,7 @@ __global__ void __launch_bounds__(VM_NT, MINB) vm_bwd_kernel(const VmParams P, c
       const VmLevel& L = P.lv[l];
       const float scale = FFB_DIV(msize, L.freq);
       float u[3];
+#pragma unroll
       for (int k = 0; k < 3; ++k) u[k] = map_coord(xr[k], P.lo[k], scale, P.mapping, nullptr);
 #pragma unroll 1
       for (int m = 0; m < 3; ++m) {
@@ -235,6 +245,241 @@ __global__ void __launch_bounds__(VM_NT, MINB) vm_bwd_kernel(const VmParams P, c
         if (t.ok1 && t.w1 != 0.0f) red_add_v2(gl + (size_t)(t.i0 + 1) * P.Cc + c, g0 * t.w1, g1 * t.w1);
       }
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Second generation (default; knob "field_planes_v2"): rows through WARP TILES.  A warp owns 32 consecutive queries; their
+// [32, W] rows are one contiguous piece of every [n, W] tensor.  Each lane keeps its row in a shared-memory tile of 32 rows x
+// (W + 1) floats (odd stride: a column read across the lanes and a row walk by one lane are both conflict-free), and the warp
+// moves whole tiles to / from global memory as coalesced 16-byte pieces — one row per lane reads / writes 8-byte pieces 4 W
+// bytes apart (forward: 26 M L2 write sectors for 5.7 M of payload; backward: the permuted scalar reads of the upstream
+// gradient row hit a different sector per lane, L1 hit rate 16 %, 46 warps stalled on long_scoreboard).
+// The backward pass reads the coefficient row the forward returned anyway (`coeff`, public output) instead of re-gathering
+// the three lines, and scatters the line gradient as 16-byte reductions (72-byte texels: {v4 x4, v2} / {v2, v4 x4}).
+// ---------------------------------------------------------------------------------------------------------
+// global [rows, W] chunk (contiguous, 16-byte aligned) <-> warp tile [32][W + 1]
+template <bool STORE>
+__device__ __forceinline__ void tile_rows_io(float* __restrict__ g, float* __restrict__ tile, int rows, int W, int lane) {
+  const int total = rows * W, nvec = total >> 2;
+  int q = (lane * 4) / W, c = lane * 4 - q * W;
+  for (int t = lane; t < nvec; t += 32) {
+    int idx[4];
+    int qq = q, cc = c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      idx[j] = qq * (W + 1) + cc;
+      if (++cc == W) { cc = 0; ++qq; }
+    }
+    if (STORE) {
+      *reinterpret_cast<float4*>(g + 4 * t) = make_float4(tile[idx[0]], tile[idx[1]], tile[idx[2]], tile[idx[3]]);
+    } else {
+      const float4 v = *reinterpret_cast<const float4*>(g + 4 * t);
+      tile[idx[0]] = v.x; tile[idx[1]] = v.y; tile[idx[2]] = v.z; tile[idx[3]] = v.w;
+    }
+    c += 128;
+    while (c >= W) { c -= W; ++q; }
+  }
+  for (int e = (nvec << 2) + lane; e < total; e += 32) {          // tail of a partial last chunk
+    const int qq = e / W, cc = e - qq * W;
+    if (STORE) g[e] = tile[qq * (W + 1) + cc];
+    else tile[qq * (W + 1) + cc] = g[e];
+  }
+}
+
+template <int MINB, bool UNROLL>
+__global__ void __launch_bounds__(VM_NT, MINB) vm_fwd2_kernel(const VmParams P, const float* __restrict__ x, int64_t n_cap,
+                                                              const int32_t* __restrict__ n_dev, float* __restrict__ feats,
+                                                              float* __restrict__ coeff_out) {
+  extern __shared__ float vm_smem[];
+  const int64_t n = resolve_n(n_cap, n_dev);
+  const float msize = vm_msize(P);
+  const int lane = threadIdx.x & 31, W = P.W, TS = W + 1;
+  float* tile = vm_smem + (size_t)(threadIdx.x >> 5) * 32 * TS;
+  float* row = tile + lane * TS;
+  const int64_t n_chunks = (n + 31) / 32;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp0; k < n_chunks; k += nwarps) {
+    const int64_t i = k * 32 + lane;
+    const bool active = i < n;
+    const int rows = (n - k * 32) < 32 ? (int)(n - k * 32) : 32;
+    float xr[3] = {0.f, 0.f, 0.f};
+    if (active) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xr[d] = x[i * 3 + d];
+      vm_coeff_row<1>(P, xr, row);
+    }
+    __syncwarp();
+    if (coeff_out) tile_rows_io<true>(coeff_out + k * 32 * W, tile, rows, W, lane);
+    __syncwarp();
+    if (active) {
+#pragma unroll 1
+      for (int l = 0; l < P.n_levels; ++l) {
+        const VmLevel& L = P.lv[l];
+        const float scale = FFB_DIV(msize, L.freq);
+        float u[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] = map_coord(xr[d], P.lo[d], scale, P.mapping, nullptr);
+        if (UNROLL) {                       // the three planes of a level in flight together (12 vector loads per thread)
+          float b[3][4];
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            TapSet<2, false> tb;
+            vm_plane_taps(P, L, m, u, tb);
+            if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb, b[m]);
+            else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb, b[m]);
+          }
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            const int q0 = L.col + m * L.C;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < L.C) row[__ldg(P.perm + q0 + j)] *= b[m][j];
+          }
+        } else {
+#pragma unroll 1
+          for (int m = 0; m < 3; ++m) {
+            TapSet<2, false> tb;
+            vm_plane_taps(P, L, m, u, tb);
+            float b[4];
+            if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb, b);
+            else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb, b);
+            const int q0 = L.col + m * L.C;
+            for (int j = 0; j < L.C; ++j) row[__ldg(P.perm + q0 + j)] *= b[j];       // coefficient -> feature, in place
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (feats) tile_rows_io<true>(feats + k * 32 * W, tile, rows, W, lane);
+    __syncwarp();
+  }
+}
+
+// one 18-float (72-byte) line texel: += w * g[0..17] as 16-byte reductions wherever the address allows
+__device__ __forceinline__ void red_texel18(float* __restrict__ p, size_t texel, const float* g, float w) {
+  float* q = p + texel * 18;
+  if ((texel & 1) == 0) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) red_add_v4(q + c, g[c] * w, g[c + 1] * w, g[c + 2] * w, g[c + 3] * w);
+    red_add_v2(q + 16, g[16] * w, g[17] * w);
+  } else {
+    red_add_v2(q, g[0] * w, g[1] * w);
+#pragma unroll
+    for (int c = 2; c < 18; c += 4) red_add_v4(q + c, g[c] * w, g[c + 1] * w, g[c + 2] * w, g[c + 3] * w);
+  }
+}
+
+template <int MINB, bool UNROLL>
+__global__ void __launch_bounds__(VM_NT, MINB) vm_bwd2_kernel(const VmParams P, const VmGrads G, const float* __restrict__ x, int64_t n_cap,
+                                                              const int32_t* __restrict__ n_dev, const float* __restrict__ g_feats,
+                                                              const float* __restrict__ coeff_saved) {
+  extern __shared__ float vm_smem[];
+  const int64_t n = resolve_n(n_cap, n_dev);
+  const float msize = vm_msize(P);
+  const int lane = threadIdx.x & 31, W = P.W, TS = W + 1;
+  float* tileA = vm_smem + (size_t)(threadIdx.x >> 5) * 64 * TS;      // coefficient row, replaced by its gradient in place
+  float* tileG = tileA + 32 * TS;                                      // upstream gradient row
+  float* rowA = tileA + lane * TS;
+  const float* rowG = tileG + lane * TS;
+  const int64_t n_chunks = (n + 31) / 32;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp0; k < n_chunks; k += nwarps) {
+    const int64_t i = k * 32 + lane;
+    const bool active = i < n;
+    const int rows = (n - k * 32) < 32 ? (int)(n - k * 32) : 32;
+    float xr[3] = {0.f, 0.f, 0.f};
+    if (active)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xr[d] = x[i * 3 + d];
+    tile_rows_io<false>(const_cast<float*>(g_feats) + k * 32 * W, tileG, rows, W, lane);
+    if (coeff_saved) tile_rows_io<false>(const_cast<float*>(coeff_saved) + k * 32 * W, tileA, rows, W, lane);
+    else if (active) vm_coeff_row<1>(P, xr, rowA);
+    __syncwarp();
+    if (active) {
+#pragma unroll 1
+      for (int l = 0; l < P.n_levels; ++l) {
+        const VmLevel& L = P.lv[l];
+        const float scale = FFB_DIV(msize, L.freq);
+        float u[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] = map_coord(xr[d], P.lo[d], scale, P.mapping, nullptr);
+        if (UNROLL) {
+          TapSet<2, false> tb[3];
+          float b[3][4];
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            vm_plane_taps(P, L, m, u, tb[m]);
+            if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb[m], b[m]);
+            else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb[m], b[m]);
+          }
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            const int q0 = L.col + m * L.C;
+            float gb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              gb[j] = 0.0f;
+              if (j < L.C) {
+                const int p = __ldg(P.perm + q0 + j);
+                const float g = rowG[p];
+                gb[j] = g * rowA[p];                   // d/d basis = g * coefficient
+                rowA[p] = g * b[m][j];                 // d/d coefficient, in place
+              }
+            }
+            if (G.plane[l][m]) {
+              if (L.C == 4) scatter_vec<2, false, 4>(G.plane[l][m], 4, 0, tb[m], gb);
+              else scatter_vec<2, false, 2>(G.plane[l][m], 2, 0, tb[m], gb);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int m = 0; m < 3; ++m) {
+            TapSet<2, false> tb;
+            vm_plane_taps(P, L, m, u, tb);
+            float b[4], gb[4];
+            if (L.C == 4) gather_vec<2, false, 4>(L.plane[m], 4, 0, tb, b);
+            else gather_vec<2, false, 2>(L.plane[m], 2, 0, tb, b);
+            const int q0 = L.col + m * L.C;
+            for (int j = 0; j < 4; ++j) {
+              gb[j] = 0.0f;
+              if (j < L.C) {
+                const int p = __ldg(P.perm + q0 + j);
+                const float g = rowG[p];
+                gb[j] = g * rowA[p];
+                rowA[p] = g * b[j];
+              }
+            }
+            if (G.plane[l][m]) {
+              if (L.C == 4) scatter_vec<2, false, 4>(G.plane[l][m], 4, 0, tb, gb);
+              else scatter_vec<2, false, 2>(G.plane[l][m], 2, 0, tb, gb);
+            }
+          }
+        }
+      }
+      // coefficient lines: 1-D scatter of the 3 x Cc gradient row
+#pragma unroll 1
+      for (int m = 0; m < 3; ++m) {
+        float* gl = G.cline[m];
+        if (!gl) continue;
+        const LTap t = vm_line_tap(P, m, xr);
+        if (P.Cc == 18) {
+          float g[18];
+#pragma unroll
+          for (int c = 0; c < 18; ++c) g[c] = rowA[m * 18 + c];
+          if (t.ok0 && t.w0 != 0.0f) red_texel18(gl, (size_t)t.i0, g, t.w0);
+          if (t.ok1 && t.w1 != 0.0f) red_texel18(gl, (size_t)(t.i0 + 1), g, t.w1);
+        } else {
+          for (int c = 0; c < P.Cc; c += 2) {
+            const float g0 = rowA[m * P.Cc + c], g1 = rowA[m * P.Cc + c + 1];
+            if (t.ok0 && t.w0 != 0.0f) red_add_v2(gl + (size_t)t.i0 * P.Cc + c, g0 * t.w0, g1 * t.w0);
+            if (t.ok1 && t.w1 != 0.0f) red_add_v2(gl + (size_t)(t.i0 + 1) * P.Cc + c, g0 * t.w1, g1 * t.w1);
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -280,6 +525,10 @@ static bool build_vm_params(const ffb_field_desc& d, VmParams& P) {
 }
 
 static int g_planes_enabled = 1;
+static int g_planes_v2 = 1;        // knob "field_planes_v2": warp-tile kernels (coalesced row traffic); 0: first-generation kernels
+static int g_planes_unroll = 1;    // knob "field_planes_unroll": bit 0 forward, bit 1 backward — the three planes of a level in flight together
+// measured at the -vm bench shape (423 k queries): forward 275 us (first generation) -> 220 (warp tiles) -> 175 us (+ unrolled planes);
+// backward 722 -> 482 us (unrolled: 514 us, left off)
 
 }  // namespace ffb
 
@@ -289,6 +538,12 @@ extern "C" {
 
 int ffb_set_field_planes(int enabled) {
   g_planes_enabled = enabled ? 1 : 0;
+  return FFB_OK;
+}
+
+int ffb_set_field_planes_tuning(int which, int value) {     // reached through ffb_set_tuning("field_planes_v2" | "field_planes_unroll")
+  if (which == 0) g_planes_v2 = value;
+  else g_planes_unroll = value;
   return FFB_OK;
 }
 
@@ -303,11 +558,23 @@ int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t
   VmParams P;
   FFB_REQUIRE(g_planes_enabled && build_vm_params(f->h, P), "descriptor is not a vector-matrix (vm) field");
   if (n <= 0) return FFB_OK;
-  const size_t smem = (size_t)P.W * VM_NT * sizeof(float);
   static PerDeviceOnce once;
   if (once.first()) {
     FFB_CUDA(cudaFuncSetAttribute(vm_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    FFB_CUDA(cudaFuncSetAttribute(vm_fwd2_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    FFB_CUDA(cudaFuncSetAttribute(vm_fwd2_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   }
+  const bool rows16 = (((uintptr_t)feats | (uintptr_t)coeff) & 15) == 0;
+  if (g_planes_v2 && !basis && rows16) {
+    const size_t smem2 = (size_t)(P.W + 1) * VM_NT * sizeof(float);
+    FFB_REQUIRE(smem2 <= 64 * 1024, "coefficient row too wide");
+    const int blocks = blocks_for(n, VM_NT, (int64_t)sm_count() * 64);
+    if (g_planes_unroll & 1) vm_fwd2_kernel<6, true><<<blocks, VM_NT, smem2, (cudaStream_t)stream>>>(P, x, n, n_dev, feats, coeff);
+    else vm_fwd2_kernel<8, false><<<blocks, VM_NT, smem2, (cudaStream_t)stream>>>(P, x, n, n_dev, feats, coeff);
+    FFB_LAUNCHED();
+    return FFB_OK;
+  }
+  const size_t smem = (size_t)P.W * VM_NT * sizeof(float);
   FFB_REQUIRE(smem <= 64 * 1024, "coefficient row too wide");
   vm_fwd_kernel<6><<<blocks_for(n, VM_NT, (int64_t)sm_count() * 64), VM_NT, smem, (cudaStream_t)stream>>>(P, x, n, n_dev, feats, coeff, basis);
   FFB_LAUNCHED();
@@ -338,7 +605,19 @@ int ffb_field_planes_bwd_saved(ffb_field_t f, const float* x, int64_t n, const i
   static PerDeviceOnce once;
   if (once.first()) {
     FFB_CUDA(cudaFuncSetAttribute(vm_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    FFB_CUDA(cudaFuncSetAttribute(vm_bwd2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    FFB_CUDA(cudaFuncSetAttribute(vm_bwd2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   }
+  const size_t smem2 = (size_t)(P.W + 1) * VM_NT * 2 * sizeof(float);
+  if (g_planes_v2 && g_feats && !g_coeff && !basis && smem2 <= 64 * 1024 && (((uintptr_t)g_feats | (uintptr_t)coeff) & 15) == 0) {
+    // upstream gradient of the features only (the render / regression paths): warp-tile kernel; coeff = the row the forward returned
+    const int blocks = blocks_for(n, VM_NT, (int64_t)sm_count() * 64);
+    if (g_planes_unroll & 2) vm_bwd2_kernel<4, true><<<blocks, VM_NT, smem2, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, coeff);
+    else vm_bwd2_kernel<4, false><<<blocks, VM_NT, smem2, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, coeff);
+    FFB_LAUNCHED();
+    return FFB_OK;
+  }
+  if (!basis) coeff = nullptr;      // the first-generation kernel takes both saved rows or neither
   vm_bwd_kernel<6><<<blocks_for(n, VM_NT, (int64_t)sm_count() * 64), VM_NT, smem, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, g_coeff, coeff, basis);
   FFB_LAUNCHED();
   return FFB_OK;

@@ -102,6 +102,10 @@ def lib():
         _lib.ffb_rgbmlp_stream_bytes.restype = C.c_int64
         if _lib.ffb_abi_version() != 1:
             raise RuntimeError('libffb200.so ABI version mismatch')
+        for kv in filter(None, os.environ.get('FFB_TUNING', '').split(',')):      # experiment knobs: FFB_TUNING=key=value,key=value
+            k, v = kv.split('=')
+            if _lib.ffb_set_tuning(k.strip().encode(), int(v)) != 0:
+                raise RuntimeError(f'ffb200: unknown tuning key {k!r} in FFB_TUNING')
     return _lib
 
 

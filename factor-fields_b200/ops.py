@@ -102,6 +102,9 @@ class FieldPlan:
         # (measured for the vm kernels too — ffb_field_planes_bwd_saved — and left off: writing the permuted basis row costs the
         # forward +0.16 ms at the -vm bench shape and the backward gains nothing over re-gathering L2-resident texels)
         self.saves_rows = self.fast
+        # the vm kernels' backward reads the coefficient row the forward returns anyway (a coalesced stream instead of re-gathering
+        # the three lines); the plane texels are re-gathered
+        self.keeps_coeff = (not self.fast) and nv.lib().ffb_field_planes_eligible(self.handle) == 1
 
     def stale(self):
         return any((t.data_ptr() if t is not None else 0) != p for t, p in zip(self.tensors, self.ptrs))
@@ -203,9 +206,12 @@ class FieldQuery(torch.autograd.Function):
                     nv.check(nv.lib().ffb_field_query_fwd(plan.handle, nv.ptr(x), C.c_int64(n), nv.i32p(n_dev), nv.ptr(feats), nv.ptr(coeff),
                                                           nv.stream()))
         ctx.plan, ctx.n_dev, ctx.train = plan, n_dev, train
+        ctx.keep_coeff = (not train) and plan.keeps_coeff and any(ctx.needs_input_grad[3:])
         ctx.set_materialize_grads(False)     # an unused output (the coefficient row in the render path) arrives as None, not as zeros
         if train:
             ctx.save_for_backward(x, coeff, basis)
+        elif ctx.keep_coeff:
+            ctx.save_for_backward(x, coeff)
         else:
             ctx.save_for_backward(x)
         return feats, coeff
@@ -215,6 +221,8 @@ class FieldQuery(torch.autograd.Function):
         plan = ctx.plan
         x = ctx.saved_tensors[0]
         coeff, basis = (ctx.saved_tensors[1], ctx.saved_tensors[2]) if ctx.train else (None, None)
+        if ctx.keep_coeff:
+            coeff = ctx.saved_tensors[1]
         n = x.shape[0]
         if g_feats is None and g_coeff is None:
             return (None, None, None, *[None] * len(plan.tensors))

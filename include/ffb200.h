@@ -117,6 +117,10 @@ int ffb_field_query_fwd_train(ffb_field_t f, const float* x, int64_t n, const in
 int ffb_field_query_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
                               const float* g_feats, const float* g_coeff, const float* coeff,
                               const float* basis, float* const* h_grads, void* stream);
+/* How the training pair lays the opaque `basis` buffer out for a batch of n queries (for tests that inspect it):
+ * 0 = blocked by 32 queries (narrow rows), 1 = row-major [n, W] (rows of >= 64 channels: the column-parallel kernels of
+ * image.yaml / image_set.yaml), -1 = the field does not use saved rows. */
+int ffb_field_saved_basis_layout(ffb_field_t f, int64_t n);
 /* grid_mapping (:11-33) on its own: x [n, in_dim] -> out [n, in_dim, F] (trig: [n, in_dim, 2F]). */
 int ffb_grid_mapping(const float* x, int64_t n, int32_t in_dim, const float* h_aabb_min,
                      const float* h_aabb_max, const float* h_freq, int32_t n_freq, int32_t mapping,

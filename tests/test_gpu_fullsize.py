@@ -76,7 +76,10 @@ def _run_fast_and_generic(m, x, gf, gc):
     nv.check(lib.ffb_field_query_fwd_train(plan.handle, nv.ptr(x), C.c_int64(N), None, nv.ptr(out['ff']), nv.ptr(out['cf']), nv.ptr(basis), nv.stream()))
     nv.check(lib.ffb_field_generic_fwd(plan.handle, nv.ptr(x), C.c_int64(N), None, nv.ptr(out['fg']), nv.ptr(out['cg']), None, nv.stream()))
     # un-block the saved basis row: element (i, c) at (i / 32) * 32 W + c * 32 + i % 32   (field_fast.cu: blk_idx)
-    out['basis'] = basis.view(-1, W, 32).permute(0, 2, 1).reshape(-1, W)[:N]
+    # (rows of >= 64 channels — image.yaml / image_set.yaml — are saved row-major by the column-parallel kernels)
+    layout = lib.ffb_field_saved_basis_layout(plan.handle, C.c_int64(N))
+    assert layout in (0, 1)
+    out['basis'] = basis[:N] if layout == 1 else basis.view(-1, W, 32).permute(0, 2, 1).reshape(-1, W)[:N]
     g_fast = [torch.zeros_like(t) for t in plan.tensors]
     arr = (C.c_void_p * nv.MAX_OPS)(*[g.data_ptr() for g in g_fast])
     nv.check(lib.ffb_field_query_bwd_saved(plan.handle, nv.ptr(x), C.c_int64(N), None, nv.ptr(gf), nv.ptr(gc, allow_none=True),
