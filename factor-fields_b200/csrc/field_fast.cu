@@ -721,6 +721,7 @@ static bool mode_supported(ffb_field_t f, const FastParams& P) {
 }
 
 extern "C" int ffb_set_field_planes_tuning(int which, int value);
+extern "C" int ffb_set_field_lines_walk(int value);
 
 extern "C" {
 
@@ -735,6 +736,7 @@ int ffb_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "field_fwd_lpar_all")) g_fwd_lpar_all = value;
   else if (!strcmp(key, "field_wide")) g_wide = value;
   else if (!strcmp(key, "field_deterministic")) ffb::g_deterministic = value;
+  else if (!strcmp(key, "field_lines_walk")) return ffb_set_field_lines_walk(value);
   else if (!strcmp(key, "field_planes_v2")) return ffb_set_field_planes_tuning(0, value);
   else if (!strcmp(key, "field_planes_unroll")) return ffb_set_field_planes_tuning(1, value);
   else { set_error("ffb_set_tuning: unknown key %s", key); return FFB_EINVAL; }

@@ -158,7 +158,7 @@ struct LineGrads {
 __global__ void __launch_bounds__(LN_THREADS, 1) lines_bwd_kernel(const LineParams P, const LineGrads G, const float* __restrict__ x,
                                                                   int64_t n_cap, const int32_t* __restrict__ n_dev,
                                                                   const float* __restrict__ g_feats, const float* __restrict__ g_coeff,
-                                                                  int CB) {
+                                                                  int CB, int walk) {
   extern __shared__ __align__(128) float ln_smem[];
   const int64_t n = resolve_n(n_cap, n_dev);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -192,7 +192,14 @@ __global__ void __launch_bounds__(LN_THREADS, 1) lines_bwd_kernel(const LinePara
     for (int idx = tid; idx < total / 4; idx += LN_THREADS) reinterpret_cast<float4*>(gA)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const int c0 = (lane % lpq) * 4;
-    for (int64_t q = q0 + warp * qpw + lane / lpq; q < q1; q += (LN_THREADS / 32) * qpw) {
+    // walk = 1: every query slot of every warp ("walker") owns one contiguous piece of the CTA's range, so the queries in flight
+    // at any moment are far apart; walk = 0: a warp takes qpw CONSECUTIVE queries per step — neighbouring samples of a ray, which
+    // add into the same rows, and the compare-and-swap loops of the shared-memory float adds then retry against each other
+    const int walkers = (LN_THREADS / 32) * qpw, wid = warp * qpw + lane / lpq;
+    const int64_t sub = (q1 - q0 + walkers - 1) / walkers;
+    int64_t qb = q0 + wid, qe = q1, qs = walkers;
+    if (walk) { qb = q0 + wid * sub; qe = qb + sub < q1 ? qb + sub : q1; qs = 1; }
+    for (int64_t q = qb; q < qe; q += qs) {
       float xr[3];
       for (int k = 0; k < P.xdim; ++k) xr[k] = x[q * P.xdim + k];
       const Tap1 tc = line_tap(P, P.coeff, xr, msize), ta = line_tap(P, P.line[l][0], xr, msize);
@@ -297,6 +304,7 @@ static int lines_bwd_cb(const LineParams& P) {      // widest channel block whos
 }
 
 static int g_lines_enabled = 1;
+static int g_lines_walk = 0;       // knob "field_lines_walk" (see lines_bwd_kernel): measured SLOWER at the -CP bench shape (1.55 vs 1.29 ms), left off
 
 }  // namespace ffb
 
@@ -306,6 +314,11 @@ extern "C" {
 
 int ffb_set_field_lines(int enabled) {
   g_lines_enabled = enabled ? 1 : 0;
+  return FFB_OK;
+}
+
+int ffb_set_field_lines_walk(int value) {        // reached through ffb_set_tuning("field_lines_walk")
+  g_lines_walk = value;
   return FFB_OK;
 }
 
@@ -357,7 +370,7 @@ int ffb_field_lines_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t*
   const int64_t min_per_cta = 512;
   int64_t grid = (n + min_per_cta - 1) / min_per_cta;
   if (grid > sm_count()) grid = sm_count();
-  lines_bwd_kernel<<<(unsigned)grid, LN_THREADS, smem, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, g_coeff, cb);
+  lines_bwd_kernel<<<(unsigned)grid, LN_THREADS, smem, (cudaStream_t)stream>>>(P, G, x, n, n_dev, g_feats, g_coeff, cb, g_lines_walk);
   FFB_LAUNCHED();
   return FFB_OK;
 }
