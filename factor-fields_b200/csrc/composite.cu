@@ -19,6 +19,8 @@ __device__ __forceinline__ float density_act_grad(const ffb_composite_desc& D, f
   return x > 0.0f ? 1.0f : 0.0f;
 }
 
+constexpr int CU = 4;      // chunks of 32 samples whose loads a warp issues together
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -36,33 +38,46 @@ __global__ void __launch_bounds__(256) composite_weights_kernel(ffb_composite_de
     const int64_t beg = offsets[r], end = offsets[r + 1];
     float carry = 1.0f;
     int napp = 0;
-    for (int64_t c0 = beg; c0 < end; c0 += 32) {
-      const int64_t i = c0 + lane;
-      const bool act = i < end;
-      float sg = 0.0f, alpha = 0.0f, fac = 1.0f;
-      if (act) {
-        sg = density_act(D, feat0[i * ld_feat]);
-        const float delta = FFB_MUL(dist[i], D.distance_scale);
-        alpha = FFB_SUB(1.0f, expf(-FFB_MUL(sg, delta)));
-        fac = FFB_ADD(FFB_SUB(1.0f, alpha), 1e-10f);
-      }
-      float p = fac;
+    for (int64_t s0 = beg; s0 < end; s0 += 32 * CU) {
+      // the loads of CU chunks are issued together (a ray's chunks are otherwise a chain of load -> scan -> load ...: ~1 us each)
+      float fv[CU], dv[CU];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float y = __shfl_up_sync(0xffffffffu, p, o);
-        if (lane >= o) p *= y;
+      for (int u = 0; u < CU; ++u) {
+        const int64_t i = s0 + u * 32 + lane;
+        fv[u] = 0.0f; dv[u] = 0.0f;
+        if (i < end) { fv[u] = feat0[i * ld_feat]; dv[u] = dist[i]; }
       }
-      float excl = __shfl_up_sync(0xffffffffu, p, 1);
-      if (lane == 0) excl = 1.0f;
-      const float T = carry * excl;
-      const float w = alpha * T;
-      carry *= __shfl_sync(0xffffffffu, p, 31);
-      if (act) {
-        sigma[i] = sg;
-        trans[i] = T;
-        weight[i] = w;
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int64_t c0 = s0 + u * 32;
+        if (c0 >= end) break;
+        const int64_t i = c0 + lane;
+        const bool act = i < end;
+        float sg = 0.0f, alpha = 0.0f, fac = 1.0f;
+        if (act) {
+          sg = density_act(D, fv[u]);
+          const float delta = FFB_MUL(dv[u], D.distance_scale);
+          alpha = FFB_SUB(1.0f, expf(-FFB_MUL(sg, delta)));
+          fac = FFB_ADD(FFB_SUB(1.0f, alpha), 1e-10f);
+        }
+        float p = fac;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float y = __shfl_up_sync(0xffffffffu, p, o);
+          if (lane >= o) p *= y;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, p, 1);
+        if (lane == 0) excl = 1.0f;
+        const float T = carry * excl;
+        const float w = alpha * T;
+        carry *= __shfl_sync(0xffffffffu, p, 31);
+        if (act) {
+          sigma[i] = sg;
+          trans[i] = T;
+          weight[i] = w;
+        }
+        napp += __popc(__ballot_sync(0xffffffffu, act && w > D.weight_thres));
       }
-      napp += __popc(__ballot_sync(0xffffffffu, act && w > D.weight_thres));
     }
     if (lane == 0) app_counts[r] = napp;
   }
@@ -78,12 +93,22 @@ __global__ void __launch_bounds__(256) composite_app_fill_kernel(const float* __
   for (int64_t r = warp; r < R; r += nwarps) {
     const int64_t beg = offsets[r], end = offsets[r + 1];
     int64_t base = app_offsets[r];
-    for (int64_t c0 = beg; c0 < end; c0 += 32) {
-      const int64_t i = c0 + lane;
-      const bool f = i < end && weight[i] > thres;
-      const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) app_idx[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
-      base += __popc(m);
+    for (int64_t s0 = beg; s0 < end; s0 += 32 * CU) {
+      float wv[CU];
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int64_t i = s0 + u * 32 + lane;
+        wv[u] = i < end ? weight[i] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int64_t i = s0 + u * 32 + lane;
+        if (s0 + u * 32 >= end) break;
+        const bool f = i < end && wv[u] > thres;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (f) app_idx[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+        base += __popc(m);
+      }
     }
   }
 }
@@ -100,23 +125,39 @@ __global__ void __launch_bounds__(256) composite_accum_kernel(ffb_composite_desc
     const int64_t beg = offsets[r], end = offsets[r + 1];
     int64_t abase = app_offsets[r];
     float acc = 0.0f, dep = 0.0f, c0s = 0.0f, c1s = 0.0f, c2s = 0.0f;
-    for (int64_t c0 = beg; c0 < end; c0 += 32) {
-      const int64_t i = c0 + lane;
-      const bool act = i < end;
-      const float w = act ? weight[i] : 0.0f;
-      const bool f = act && w > D.weight_thres;
-      const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (act) {
-        acc += w;
-        if (z) dep += w * z[i];
+    for (int64_t s0 = beg; s0 < end; s0 += 32 * CU) {
+      float wv[CU], zv[CU], cr[CU][3];
+      bool fl[CU];
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int64_t i = s0 + u * 32 + lane;
+        const bool act = i < end;
+        wv[u] = act ? weight[i] : 0.0f;
+        zv[u] = (act && z) ? z[i] : 0.0f;
       }
-      if (f) {
-        const int64_t j = abase + __popc(m & ((1u << lane) - 1u));
-        c0s += w * rgb[j * 3 + 0];
-        c1s += w * rgb[j * 3 + 1];
-        c2s += w * rgb[j * 3 + 2];
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {           // shaded-sample slots of the CU chunks, then their colours in one batch of loads
+        fl[u] = (s0 + u * 32 + lane < end) && wv[u] > D.weight_thres;
+        const unsigned m = __ballot_sync(0xffffffffu, fl[u]);
+        cr[u][0] = cr[u][1] = cr[u][2] = 0.0f;
+        if (fl[u]) {
+          const int64_t j = abase + __popc(m & ((1u << lane) - 1u));
+          cr[u][0] = rgb[j * 3 + 0]; cr[u][1] = rgb[j * 3 + 1]; cr[u][2] = rgb[j * 3 + 2];
+        }
+        abase += __popc(m);
       }
-      abase += __popc(m);
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        if (s0 + u * 32 + lane < end) {
+          acc += wv[u];
+          if (z) dep += wv[u] * zv[u];
+        }
+        if (fl[u]) {
+          c0s += wv[u] * cr[u][0];
+          c1s += wv[u] * cr[u][1];
+          c2s += wv[u] * cr[u][2];
+        }
+      }
     }
     acc = warp_sum(acc);
     dep = warp_sum(dep);
@@ -159,55 +200,80 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(ffb_composite_desc D
     int64_t aend = app_offsets[r + 1];   // one past the last shaded sample of this ray
     float suffix = 0.0f;                 // sum_{k > chunk} g_w_k * w_k
     const int64_t nchunks = (end - beg + 31) / 32;
-    for (int64_t ch = nchunks - 1; ch >= 0; --ch) {
-      const int64_t i = beg + ch * 32 + lane;
-      const bool act = i < end;
-      const float w = act ? weight[i] : 0.0f;
-      const bool f = act && w > D.weight_thres;
-      const unsigned m = __ballot_sync(0xffffffffu, f);
-      float gw = -gsum;
-      if (f) {
-        const unsigned upper = (lane == 31) ? 0u : (m & ~((2u << lane) - 1u));
-        const int64_t j = aend - 1 - __popc(upper);
-        const float c0 = rgb[j * 3 + 0], c1 = rgb[j * 3 + 1], c2 = rgb[j * 3 + 2];
-        gw += g[0] * c0 + g[1] * c1 + g[2] * c2;
-        g_rgb[j * 3 + 0] = w * g[0];
-        g_rgb[j * 3 + 1] = w * g[1];
-        g_rgb[j * 3 + 2] = w * g[2];
-      }
-      aend -= __popc(m);
-      const float gww = act ? gw * w : 0.0f;
-      // reverse inclusive scan over lanes
-      float s = gww;
+    for (int64_t ch_hi = nchunks - 1; ch_hi >= 0; ch_hi -= CU) {
+      // the loads of CU chunks (walking down from ch_hi) are issued together, then the shaded samples' colours, then the scans
+      float wv[CU], sv[CU], dv[CU], tv[CU], fv[CU], cr[CU][3];
+      int64_t jv[CU];
+      bool fl[CU];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float y = __shfl_down_sync(0xffffffffu, s, o);
-        if (lane + o < 32) s += y;
+      for (int u = 0; u < CU; ++u) {
+        const int64_t ch = ch_hi - u, i = beg + ch * 32 + lane;
+        const bool act = ch >= 0 && i < end;
+        wv[u] = sv[u] = dv[u] = tv[u] = fv[u] = 0.0f;
+        if (act) { wv[u] = weight[i]; sv[u] = sigma[i]; dv[u] = dist[i]; tv[u] = trans[i]; fv[u] = feat0[i * ld_feat]; }
       }
-      const float after = suffix + (s - gww);   // sum over samples after i
-      suffix += __shfl_sync(0xffffffffu, s, 0);
-      float g0 = 0.0f;
-      if (act) {
-        const float sg = sigma[i];
-        const float delta = FFB_MUL(dist[i], D.distance_scale);
-        const float e = expf(-FFB_MUL(sg, delta));          // 1 - alpha
-        const float fac = FFB_ADD(FFB_SUB(1.0f, FFB_SUB(1.0f, e)), 1e-10f);
-        const float g_alpha = gw * trans[i] - after / fac;
-        const float g_sigma = g_alpha * e * delta;
-        g0 = g_sigma * density_act_grad(D, feat0[i * ld_feat]);
-        if (!zero_rest) g_feat0[i * ld_g] = g0;
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int64_t ch = ch_hi - u, i = beg + ch * 32 + lane;
+        fl[u] = ch >= 0 && i < end && wv[u] > D.weight_thres;
+        const unsigned m = __ballot_sync(0xffffffffu, fl[u]);
+        jv[u] = 0;
+        cr[u][0] = cr[u][1] = cr[u][2] = 0.0f;
+        if (fl[u]) {
+          const unsigned upper = (lane == 31) ? 0u : (m & ~((2u << lane) - 1u));
+          jv[u] = aend - 1 - __popc(upper);
+          cr[u][0] = rgb[jv[u] * 3 + 0]; cr[u][1] = rgb[jv[u] * 3 + 1]; cr[u][2] = rgb[jv[u] * 3 + 2];
+        }
+        aend -= __popc(m);
       }
-      if (zero_rest) {
-        // the whole gradient rows of this chunk: density column + zeros (the caller skips its memset of [Nv, ld_g]).  The chunk's
-        // rows are contiguous in memory, so the warp writes them as coalesced 16-byte pieces; piece t = row t / q4, quad t % q4.
-        const int q4 = ld_g >> 2;
-        const int64_t cbase = beg + ch * 32;
-        const int rows = (int)((end - cbase) < 32 ? (end - cbase) : 32);
-        float4* dst = reinterpret_cast<float4*>(g_feat0 + cbase * ld_g);
-        for (int t0 = 0; t0 < 32 * q4; t0 += 32) {
-          const int t = t0 + lane, r = t / q4, q = t - r * q4;
-          const float gr = __shfl_sync(0xffffffffu, g0, r & 31);
-          if (r < rows) dst[t] = make_float4(q == 0 ? gr : 0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int64_t ch = ch_hi - u;
+        if (ch < 0) break;
+        const int64_t i = beg + ch * 32 + lane;
+        const bool act = i < end;
+        const float w = wv[u];
+        float gw = -gsum;
+        if (fl[u]) {
+          const int64_t j = jv[u];
+          gw += g[0] * cr[u][0] + g[1] * cr[u][1] + g[2] * cr[u][2];
+          g_rgb[j * 3 + 0] = w * g[0];
+          g_rgb[j * 3 + 1] = w * g[1];
+          g_rgb[j * 3 + 2] = w * g[2];
+        }
+        const float gww = act ? gw * w : 0.0f;
+        // reverse inclusive scan over lanes
+        float s = gww;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float y = __shfl_down_sync(0xffffffffu, s, o);
+          if (lane + o < 32) s += y;
+        }
+        const float after = suffix + (s - gww);   // sum over samples after i
+        suffix += __shfl_sync(0xffffffffu, s, 0);
+        float g0 = 0.0f;
+        if (act) {
+          const float sg = sv[u];
+          const float delta = FFB_MUL(dv[u], D.distance_scale);
+          const float e = expf(-FFB_MUL(sg, delta));          // 1 - alpha
+          const float fac = FFB_ADD(FFB_SUB(1.0f, FFB_SUB(1.0f, e)), 1e-10f);
+          const float g_alpha = gw * tv[u] - after / fac;
+          const float g_sigma = g_alpha * e * delta;
+          g0 = g_sigma * density_act_grad(D, fv[u]);
+          if (!zero_rest) g_feat0[i * ld_g] = g0;
+        }
+        if (zero_rest) {
+          // the whole gradient rows of this chunk: density column + zeros (the caller skips its memset of [Nv, ld_g]).  The chunk's
+          // rows are contiguous in memory, so the warp writes them as coalesced 16-byte pieces; piece t = row t / q4, quad t % q4.
+          const int q4 = ld_g >> 2;
+          const int64_t cbase = beg + ch * 32;
+          const int rows = (int)((end - cbase) < 32 ? (end - cbase) : 32);
+          float4* dst = reinterpret_cast<float4*>(g_feat0 + cbase * ld_g);
+          for (int t0 = 0; t0 < 32 * q4; t0 += 32) {
+            const int t = t0 + lane, r = t / q4, q = t - r * q4;
+            const float gr = __shfl_sync(0xffffffffu, g0, r & 31);
+            if (r < rows) dst[t] = make_float4(q == 0 ? gr : 0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
     }
