@@ -204,6 +204,17 @@ def run_reference(args):
     os.write(json_fd, (json.dumps(line) + '\n').encode())
 
 
+def comm_label(ts, world, eager):
+    """config.parallelism: which transport all-reduces the gradient arena in this run."""
+    mb = ts.bucket.flat.numel() * 4 / 1e6 if getattr(ts, 'bucket', None) is not None else 21.4
+    symm = getattr(ts, 'symm', None)
+    if symm is not None and not eager:
+        path = 'multimem.ld_reduce / multimem.st through the NVSwitch' if getattr(symm, 'multicast', 0) else 'peer loads / stores over NVLink'
+        return (f'ray-sharded dp{world}; the flat fp32 gradient arena ({mb:.1f} MB) all-reduced in place by one kernel over symmetric memory '
+                f'({path}; csrc/allreduce.cu) inside the step\'s CUDA graph')
+    return f'ray-sharded dp{world}, one NCCL all-reduce of the flat fp32 gradient arena ({mb:.1f} MB) per step'
+
+
 def gpu_backlog(ms=60.0):
     """Park the stream behind a spinning kernel so that the Python-driven launches of the per-section profile pass queue up and then
     run back to back: the CUDA events around a section then bracket device time only (without it, sections of a few tens of
@@ -461,8 +472,7 @@ def run_ours(args):
                        'host_syncs_per_step': 2 if args.exact_counts else 0, 'cuda_graph': not eager, 'launches_per_step': launches_per_step,
                        'parallelism': (f'ray-sharded dp{world}; gradient arena all-reduced in two NCCL calls per step, the first (fine basis levels + MLPs, '
                                        f'{(ts.bucket.flat.numel() - ts.late_end) * 4 / 1e6:.1f} MB) overlapped with the second phase of the scatter, the second '
-                                       f'({ts.late_end * 4 / 1e6:.1f} MB) exposed' if (not eager and ts.late) else f'ray-sharded dp{world}, one NCCL all-reduce of the flat '
-                                       'fp32 gradient bucket per step') if world > 1 else 'single GPU',
+                                       f'({ts.late_end * 4 / 1e6:.1f} MB) exposed' if (not eager and ts.late) else comm_label(None if eager else ts, world, eager)) if world > 1 else 'single GPU',
                        'global_rays_per_step': world * B,
                        'l2': 'per-step inputs+intermediates (~0.5 GB) exceed the 126 MB L2; no explicit flush; the 21 MB of parameters stay '
                              'L2-resident across steps as in training'},

@@ -138,7 +138,8 @@ int ffb_field_fast_fwd_train(ffb_field_t f, const float* x, int64_t n, const int
 int ffb_field_fast_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev,
                              const float* g_feats, const float* g_coeff, const float* coeff,
                              const float* basis, float* const* h_grads, void* stream);
-/* Knobs: launch configurations of the field kernels ("field_fwd_cfg", "field_bwd_cfg", "field_level_parallel", ...) and
+/* Knobs: launch configurations / kernel generations of the field kernels ("field_fwd_cfg", "field_bwd_cfg", "field_level_parallel",
+ * "field_wide", "field_planes_v2", "field_planes_unroll", "field_lines_walk", ...; also FFB_TUNING=key=value,... in the environment) and
  * "field_deterministic" (1: the scatter-add of every field runs serially in query order -> bit-reproducible gradients; for
  * debugging and gradient tests at small sizes). */
 int ffb_set_tuning(const char* key, int value);
@@ -178,7 +179,9 @@ int ffb_field_planes_fwd(ffb_field_t f, const float* x, int64_t n, const int32_t
                          float* basis, void* stream);
 int ffb_field_planes_bwd(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
                          const float* g_coeff, float* const* h_grads, void* stream);
-/* coeff / basis: the [n, W] rows written by ffb_field_planes_fwd (row-major; NULL: re-gather) */
+/* coeff: the [n, W] coefficient rows ffb_field_planes_fwd returned (row-major); with basis == NULL — what the training path
+ * passes — the kernel streams them in instead of re-gathering the three lines and re-gathers only the (L2-resident) planes.
+ * coeff == NULL: everything is re-gathered.  basis != NULL (rows of a forward that was asked for them): first-generation kernel. */
 int ffb_field_planes_bwd_saved(ffb_field_t f, const float* x, int64_t n, const int32_t* n_dev, const float* g_feats,
                                const float* g_coeff, const float* coeff, const float* basis, float* const* h_grads,
                                void* stream);
