@@ -215,3 +215,55 @@ def test_deterministic_scatter_mode(name):
         nv.check(nv.lib().ffb_set_tuning(b'field_deterministic', 0))
     for (n, p), a in zip(params, gr):
         assert H.rel_err(G.npy(a), g['grad.' + n]) < TOL_BWD, n
+
+
+@pytest.mark.parametrize('name', ['nerf_grid_box', 'nerf_vm', 'nerf_CP', 'image', 'image_set'])
+@pytest.mark.parametrize('n_live', [0, 1, 31, 33, 701])
+def test_specialised_kernels_ragged_batches_and_device_counts(name, n_live):
+    """Ragged sizes (empty, one query, one short of / one past a warp tile, a partial last tile) and the TrainStep calling
+    convention — capacity-sized buffers with the live count in device memory (n_dev) — through the product dispatch
+    (fast / wide-row / vm / CP kernels), against the generic kernels on exactly n_live rows.  Rows past the live count must
+    not contribute to any gradient."""
+    import ctypes as C
+    from ffb200 import native as nv
+    from tests import gpu_helpers as G
+    g = H.golden('field_' + name)
+    cfg, m = G.build_model(g)
+    lib = nv.lib()
+    plan = m._plan('coding')
+    rng = np.random.RandomState(3 + n_live)
+    lo, hi = g['fact.aabb'][0], g['fact.aabb'][1]
+    cap = 777
+    x = (lo + rng.rand(cap, lo.size) * (hi - lo)).astype(np.float32)
+    if name == 'image':
+        x = np.floor(x) + 0.5
+    if name == 'image_set':
+        x[:, -1] = np.clip(np.floor(x[:, -1]) + 0.5, 0.5, hi[-1] - 0.5)
+    W = plan.width
+    xd, gf = G.t(x), G.t(rng.randn(cap, W).astype(np.float32))
+    n_dev = torch.tensor([n_live], dtype=torch.int32, device='cuda')
+
+    def run(train_pair, n, nd):
+        f = torch.full((cap, W), 7.0, device='cuda')
+        c = torch.full((cap, W), 7.0, device='cuda')
+        basis = torch.zeros((cap + 31) // 32 * 32, W, device='cuda')
+        grads = [torch.zeros_like(t) for t in plan.tensors]
+        arr = (C.c_void_p * nv.MAX_OPS)(*[t.data_ptr() for t in grads])
+        if train_pair:
+            nv.check(lib.ffb_field_query_fwd_train(plan.handle, nv.ptr(xd), C.c_int64(n), nv.i32p(nd), nv.ptr(f), nv.ptr(c), nv.ptr(basis), nv.stream()))
+            nv.check(lib.ffb_field_query_bwd_saved(plan.handle, nv.ptr(xd), C.c_int64(n), nv.i32p(nd), nv.ptr(gf), None, nv.ptr(c), nv.ptr(basis), arr,
+                                                   nv.stream()))
+        else:
+            nv.check(lib.ffb_field_generic_fwd(plan.handle, nv.ptr(xd), C.c_int64(n), nv.i32p(nd), nv.ptr(f), nv.ptr(c), None, nv.stream()))
+            nv.check(lib.ffb_field_generic_bwd(plan.handle, nv.ptr(xd), C.c_int64(n), nv.i32p(nd), nv.ptr(gf), None, arr, nv.stream()))
+        return f, c, grads
+
+    fp, cp, gp = run(True, cap, n_dev)              # capacity-sized launch, live count on the device
+    fg, cg, gg = run(False, n_live, None)           # exactly n_live rows through the generic kernels
+    if n_live:
+        assert H.rel_err(G.npy(fp[:n_live]), G.npy(fg[:n_live])) < 2e-6
+        assert H.rel_err(G.npy(cp[:n_live]), G.npy(cg[:n_live])) < 2e-6
+    assert bool((fp[n_live:] == 7.0).all()) and bool((cp[n_live:] == 7.0).all())      # nothing written past the live count
+    for a, b, t in zip(gg, gp, plan.tensors):
+        scale = max(float(a.abs().max()), 1e-30)
+        assert float((a - b).abs().max()) <= 5e-5 * scale, (name, n_live, tuple(t.shape))
