@@ -526,17 +526,19 @@ __device__ __forceinline__ int wide_level(const FastParams& P, int c) {
   return l;
 }
 
-template <int DB, int DC, bool NEAR_B, bool NEAR_C>
+// V = 16-byte pieces per thread (2 when every level's channel count and offset is a multiple of 8: half the repeated
+// coordinate arithmetic per byte moved; a thread's two pieces are adjacent, so a warp still covers contiguous memory)
+template <int DB, int DC, bool NEAR_B, bool NEAR_C, int V>
 __global__ void __launch_bounds__(256) wide_fwd_kernel(const FastParams P, const float* __restrict__ x, int64_t n,
                                                        const int32_t* __restrict__ n_dev, float* __restrict__ feats,
                                                        float* __restrict__ coeff, float* __restrict__ basis) {
   n = resolve_n(n, n_dev);
   const float msize = fast_msize(P);
-  const unsigned W4 = (unsigned)P.W >> 2;
-  const unsigned n_items = (unsigned)n * W4;                       // < 2^31 (checked by the launcher)
+  const unsigned WG = (unsigned)P.W / (4 * V);
+  const unsigned n_items = (unsigned)n * WG;                       // < 2^31 (checked by the launcher)
   for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
-    const unsigned i = item / W4;
-    const int c = (int)(item - i * W4) * 4;
+    const unsigned i = item / WG;
+    const int c = (int)(item - i * WG) * 4 * V;
     const int l = wide_level(P, c);
     const FastLevel& L = P.lv[l];
     float xr[3] = {0.f, 0.f, 0.f};
@@ -546,30 +548,36 @@ __global__ void __launch_bounds__(256) wide_fwd_kernel(const FastParams P, const
     coeff_taps<DC, NEAR_C>(P, xr, tc);
     TapSet<DB, NEAR_B> tb;
     basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
-    float b[4], ca[4];
-    gather_vec<DB, NEAR_B, 4>(L.data, L.C, c - L.col, tb, b);
-    gather_vec<DC, NEAR_C, 4>(P.cdata, P.W, c, tc, ca);
-    const size_t o = (size_t)i * P.W + c;
-    if (feats) *reinterpret_cast<float4*>(feats + o) = make_float4(b[0] * ca[0], b[1] * ca[1], b[2] * ca[2], b[3] * ca[3]);
-    if (coeff) *reinterpret_cast<float4*>(coeff + o) = make_float4(ca[0], ca[1], ca[2], ca[3]);
-    if (basis) *reinterpret_cast<float4*>(basis + o) = make_float4(b[0], b[1], b[2], b[3]);
+    float b[V][4], ca[V][4];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      gather_vec<DB, NEAR_B, 4>(L.data, L.C, c + 4 * v - L.col, tb, b[v]);
+      gather_vec<DC, NEAR_C, 4>(P.cdata, P.W, c + 4 * v, tc, ca[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const size_t o = (size_t)i * P.W + c + 4 * v;
+      if (feats) *reinterpret_cast<float4*>(feats + o) = make_float4(b[v][0] * ca[v][0], b[v][1] * ca[v][1], b[v][2] * ca[v][2], b[v][3] * ca[v][3]);
+      if (coeff) *reinterpret_cast<float4*>(coeff + o) = make_float4(ca[v][0], ca[v][1], ca[v][2], ca[v][3]);
+      if (basis) *reinterpret_cast<float4*>(basis + o) = make_float4(b[v][0], b[v][1], b[v][2], b[v][3]);
+    }
   }
 }
 
 // coeff / basis (both or neither): the rows saved by wide_fwd_kernel; otherwise the texels are re-gathered (coalesced as well)
-template <int DB, int DC, bool NEAR_B, bool NEAR_C>
+template <int DB, int DC, bool NEAR_B, bool NEAR_C, int V>
 __global__ void __launch_bounds__(256) wide_bwd_kernel(const FastParams P, const FastGrads G, const float* __restrict__ x, int64_t n,
                                                        const int32_t* __restrict__ n_dev, const float* __restrict__ g_feats,
                                                        const float* __restrict__ g_coeff, const float* __restrict__ coeff,
                                                        const float* __restrict__ basis) {
   n = resolve_n(n, n_dev);
   const float msize = fast_msize(P);
-  const unsigned W4 = (unsigned)P.W >> 2;
-  const unsigned n_items = (unsigned)n * W4;
+  const unsigned WG = (unsigned)P.W / (4 * V);
+  const unsigned n_items = (unsigned)n * WG;
   const bool saved = coeff && basis;
   for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
-    const unsigned i = item / W4;
-    const int c = (int)(item - i * W4) * 4;
+    const unsigned i = item / WG;
+    const int c = (int)(item - i * WG) * 4 * V;
     const int l = wide_level(P, c);
     const FastLevel& L = P.lv[l];
     float xr[3] = {0.f, 0.f, 0.f};
@@ -579,29 +587,33 @@ __global__ void __launch_bounds__(256) wide_bwd_kernel(const FastParams P, const
     coeff_taps<DC, NEAR_C>(P, xr, tc);
     TapSet<DB, NEAR_B> tb;
     basis_taps<DB, NEAR_B>(P, L, xr, msize, tb);
-    const size_t o = (size_t)i * P.W + c;
-    float b[4], ca[4];
-    if (saved) {
-      const float4 bv = *reinterpret_cast<const float4*>(basis + o), cv = *reinterpret_cast<const float4*>(coeff + o);
-      b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
-      ca[0] = cv.x; ca[1] = cv.y; ca[2] = cv.z; ca[3] = cv.w;
-    } else {
-      gather_vec<DB, NEAR_B, 4>(L.data, L.C, c - L.col, tb, b);
-      gather_vec<DC, NEAR_C, 4>(P.cdata, P.W, c, tc, ca);
-    }
-    const float4 g = g_feats ? *reinterpret_cast<const float4*>(g_feats + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float gc[4] = {g.x * b[0], g.y * b[1], g.z * b[2], g.w * b[3]};
-    if (g_coeff) {
-      const float4 g2 = *reinterpret_cast<const float4*>(g_coeff + o);
-      gc[0] += g2.x; gc[1] += g2.y; gc[2] += g2.z; gc[3] += g2.w;
-    }
-    const float gb[4] = {g.x * ca[0], g.y * ca[1], g.z * ca[2], g.w * ca[3]};
     float* gbl = nullptr;                       // G.b[l] without indexing the parameter struct dynamically (local-memory copy)
 #pragma unroll
     for (int k = 0; k < FAST_MAX_LEVELS; ++k)
       if (k == l) gbl = G.b[k];
-    if (G.c) scatter_vec<DC, NEAR_C, 4>(G.c, P.W, c, tc, gc);
-    if (gbl) scatter_vec<DB, NEAR_B, 4>(gbl, L.C, c - L.col, tb, gb);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int cv = c + 4 * v;
+      const size_t o = (size_t)i * P.W + cv;
+      float b[4], ca[4];
+      if (saved) {
+        const float4 bv = *reinterpret_cast<const float4*>(basis + o), cf = *reinterpret_cast<const float4*>(coeff + o);
+        b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+        ca[0] = cf.x; ca[1] = cf.y; ca[2] = cf.z; ca[3] = cf.w;
+      } else {
+        gather_vec<DB, NEAR_B, 4>(L.data, L.C, cv - L.col, tb, b);
+        gather_vec<DC, NEAR_C, 4>(P.cdata, P.W, cv, tc, ca);
+      }
+      const float4 g = g_feats ? *reinterpret_cast<const float4*>(g_feats + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float gc[4] = {g.x * b[0], g.y * b[1], g.z * b[2], g.w * b[3]};
+      if (g_coeff) {
+        const float4 g2 = *reinterpret_cast<const float4*>(g_coeff + o);
+        gc[0] += g2.x; gc[1] += g2.y; gc[2] += g2.z; gc[3] += g2.w;
+      }
+      const float gb[4] = {g.x * ca[0], g.y * ca[1], g.z * ca[2], g.w * ca[3]};
+      if (G.c) scatter_vec<DC, NEAR_C, 4>(G.c, P.W, cv, tc, gc);
+      if (gbl) scatter_vec<DB, NEAR_B, 4>(gbl, L.C, cv - L.col, tb, gb);
+    }
   }
 }
 
@@ -629,6 +641,13 @@ static bool wide_eligible(const FastParams& P, int64_t n) {
     if ((P.lv[l].C & 3) || (P.lv[l].col & 3)) return false;
   return true;
 }
+static int g_wide_pairs = 1;    // knob "field_wide_pairs": two adjacent 16-byte pieces per thread where the level widths allow
+static bool wide_pairs(const FastParams& P) {
+  if (!g_wide_pairs || (P.W & 7)) return false;
+  for (int l = 0; l < P.n_levels; ++l)
+    if ((P.lv[l].C & 7) || (P.lv[l].col & 7)) return false;
+  return true;
+}
 static bool aligned16(const void* a, const void* b, const void* c, const void* d) {
   return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
 }
@@ -637,7 +656,10 @@ template <int DB, int DC, bool NB, bool NC, int NT, int MINB>
 static void launch_fwd_cfg(const FastParams& P, const float* x, int64_t n, const int32_t* n_dev, float* feats, float* coeff, float* basis,
                            cudaStream_t s) {
   if (wide_eligible(P, n)) {
-    wide_fwd_kernel<DB, DC, NB, NC><<<blocks_for(n * (P.W >> 2), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(P, x, n, n_dev, feats, coeff, basis);
+    if (NB && NC && wide_pairs(P))        // nearest taps only (measured: image.yaml 62 + 72 -> 58 + 57 us; with linear taps — image_set — 82 + 100 -> 86 + 133 us)
+      wide_fwd_kernel<DB, DC, NB, NC, 2><<<blocks_for(n * (P.W >> 3), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(P, x, n, n_dev, feats, coeff, basis);
+    else
+      wide_fwd_kernel<DB, DC, NB, NC, 1><<<blocks_for(n * (P.W >> 2), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(P, x, n, n_dev, feats, coeff, basis);
     return;
   }
   if (n * P.n_levels <= (g_fwd_lpar_all ? (int64_t)1 << 40 : LPAR_MAX_ITEMS) && g_lpar) {      // small batch: one thread per (query, level)
@@ -676,8 +698,12 @@ static void launch_bwd(const FastParams& P, const FastGrads& G, const float* x, 
   const int64_t cap = (int64_t)sm_count() * 64;
   if (wide_eligible(P, n)) {
     const bool saved = coeff && basis;
-    wide_bwd_kernel<DB, DC, NB, NC><<<blocks_for(n * (P.W >> 2), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(
-        P, G, x, n, n_dev, g_feats, g_coeff, saved ? coeff : nullptr, saved ? basis : nullptr);
+    if (NB && NC && wide_pairs(P))        // nearest taps only (measured: image.yaml 62 + 72 -> 58 + 57 us; with linear taps — image_set — 82 + 100 -> 86 + 133 us)
+      wide_bwd_kernel<DB, DC, NB, NC, 2><<<blocks_for(n * (P.W >> 3), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(
+          P, G, x, n, n_dev, g_feats, g_coeff, saved ? coeff : nullptr, saved ? basis : nullptr);
+    else
+      wide_bwd_kernel<DB, DC, NB, NC, 1><<<blocks_for(n * (P.W >> 2), 256, (int64_t)sm_count() * 32), 256, 0, s>>>(
+          P, G, x, n, n_dev, g_feats, g_coeff, saved ? coeff : nullptr, saved ? basis : nullptr);
     return;
   }
   if (coeff && basis && g_bwd_cfg != 0 && n * P.n_levels <= LPAR_MAX_ITEMS && g_lpar) {
@@ -735,6 +761,7 @@ int ffb_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "field_bwd_agg_levels")) g_agg_levels = value;
   else if (!strcmp(key, "field_fwd_lpar_all")) g_fwd_lpar_all = value;
   else if (!strcmp(key, "field_wide")) g_wide = value;
+  else if (!strcmp(key, "field_wide_pairs")) g_wide_pairs = value;
   else if (!strcmp(key, "field_deterministic")) ffb::g_deterministic = value;
   else if (!strcmp(key, "field_lines_walk")) return ffb_set_field_lines_walk(value);
   else if (!strcmp(key, "field_planes_v2")) return ffb_set_field_planes_tuning(0, value);

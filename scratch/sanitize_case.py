@@ -43,6 +43,16 @@ for ov in (['model.coeff_type=vec', 'model.basis_type=cp', 'model.freq_bands=[1.
     f2, _ = m2.get_coding(xq)
     g2 = torch.autograd.grad((f2 ** 2).sum(), [p for n_, p in m2.named_parameters() if n_.startswith(('coeffs', 'basises'))])
     torch.cuda.synchronize()
+# the column-parallel wide-row kernels (image.yaml shapes at reduced size: 144-channel rows, nearest taps)
+c3 = ffb200.load_cfg('image.yaml', ['model.total_params=90000'])
+c3.dataset.aabb = [[0., 0.], [128., 128.]]
+m3 = FactorFields(c3, 'cuda:0')
+plan3 = m3._plan('coding')
+x3 = torch.floor(torch.rand(3001, 2, device='cuda') * 128) + 0.5
+f3, _ = m3.get_coding(x3)
+g3 = torch.autograd.grad((f3 ** 2).sum(), [p for n_, p in m3.named_parameters() if n_.startswith(('coeffs', 'basises'))])
+torch.cuda.synchronize()
+print('wide rows: width', plan3.width, 'layout', nv.lib().ffb_field_saved_basis_layout(plan3.handle, 3001))
 # the decoupled look-back scan (> 64 K rows)
 c = torch.randint(0, 5, (70000,), device='cuda', dtype=torch.int32)
 o = ops.exclusive_scan(c)
