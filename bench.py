@@ -823,7 +823,7 @@ def run_eval(args):
             'gpu_launches': launches,
             'roofline': {'kernel': 'field_fwd', 'bound': 'hbm', 'achieved': round(n_valid * B_FWD / (sec['field_fwd'] * 1e-3) / 1e9, 1), 'peak': pk['hbm'],
                          'unit': 'GB/s', 'frac': round(n_valid * B_FWD / (sec['field_fwd'] * 1e-3) / 1e9 / pk['hbm'], 4), 'traffic': None,
-                         'peak_source': pk['src'], 'note': 'field forward summed over the chunks of one image', 'queries_per_image': n_valid,
+                         'peak_source': pk['src'], 'note': 'field forward summed over the chunks of one image.  SURVEY 8(d) charges the 1 080 B of texel gathers per query to HBM; the parameters are L2-resident, so the kernel really streams x + two rows (156 B per query) and this fraction can exceed 1', 'queries_per_image': n_valid,
                          'launch_ms': round(sec['field_fwd'], 4), 'share_of_step': round(sec['field_fwd'] / (ms / args.steps), 4)},
             'kernels': {k: {'ms_per_step': round(v, 4)} for k, v in sec.items()}, 'clocks': clk}
     sys.stdout.flush()
