@@ -102,7 +102,7 @@ class SymmArena:
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
         self.pads = torch.tensor([int(p) for p in self.hdl.signal_pad_ptrs], dtype=torch.int64, device=device)
         mc = int(self.hdl.multicast_ptr or 0)         # 0 when the fabric / driver offers no multicast object for this buffer
-        # measured on B200 (scratch/dist_check_allreduce.py, 21.4 MB): 2 GPUs — peer loads / stores 52 us, multimem 71 us, NCCL 61 us;
+        # measured on B200 (tests/dist/dist_check_allreduce.py, 21.4 MB): 2 GPUs — peer loads / stores 52 us, multimem 71 us, NCCL 61 us;
         # 8 GPUs — multimem 72 us (32 CTAs), peer path 91 us, NCCL 115 us.  So: the switch reduction from 3 ranks up.
         nvls = os.environ.get('FFB_ALLREDUCE_NVLS')
         use_nvls = (self.world > 2) if nvls is None else (nvls != '0')

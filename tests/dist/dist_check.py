@@ -1,7 +1,7 @@
 """2-GPU NCCL check of the sharded evaluation render and the sharded alpha-lattice evaluation:
-torchrun --nproc-per-node 2 scratch/dist_check.py  -> both must equal the single-process result."""
+torchrun --nproc-per-node 2 tests/dist/dist_check.py  -> both must equal the single-process result."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, torch.distributed as dist
 import ffb200, bench_workload as W
 from ffb200.models.FactorFields import FactorFields

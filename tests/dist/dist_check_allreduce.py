@@ -1,7 +1,7 @@
 """N-GPU check + timing of the symmetric-memory all-reduce kernel (csrc/allreduce.cu) against NCCL on the nerf.yaml arena size:
-torchrun --nproc-per-node N scratch/dist_check_allreduce.py"""
+torchrun --nproc-per-node N tests/dist/dist_check_allreduce.py"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.distributed as dist
 from ffb200.train import SymmArena
 local = int(os.environ['LOCAL_RANK'])

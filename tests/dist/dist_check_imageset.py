@@ -1,8 +1,8 @@
 """2-GPU NCCL check of image-set training sharded by image: each rank owns N_img / W coefficient slabs, trains on
 pixels of its own images, and only the basis + MLP gradients are all-reduced.  Must equal single-process training on the
-union batch (global-mean loss):  torchrun --nproc-per-node 2 scratch/dist_check_imageset.py"""
+union batch (global-mean loss):  torchrun --nproc-per-node 2 tests/dist/dist_check_imageset.py"""
 import copy, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, torch.distributed as dist
 import ffb200
 from ffb200.models.FactorFields import FactorFields

@@ -1,8 +1,8 @@
 """2-GPU NCCL check of the data-parallel training loop (train.reconstruction under torchrun): two ranks with
-512 rays each (with an upsampling event; the sharded alpha-mask update is checked by scratch/dist_check.py) must reproduce the single-process run with
-batch 1024.   torchrun --nproc-per-node 2 scratch/dist_check_train.py"""
+512 rays each (with an upsampling event; the sharded alpha-mask update is checked by tests/dist/dist_check.py) must reproduce the single-process run with
+batch 1024.   torchrun --nproc-per-node 2 tests/dist/dist_check_train.py"""
 import copy, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, torch.distributed as dist
 import ffb200
 from ffb200.models.FactorFields import FactorFields

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _torchrun(script, nproc=2, timeout=600, args=()):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={nproc}', '--master-addr', '127.0.0.1',
-           '--master-port', str(29600 + os.getpid() % 300), os.path.join(ROOT, 'scratch', script), *args]
+           '--master-port', str(29600 + os.getpid() % 300), os.path.join(ROOT, 'tests', 'dist', script), *args]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
