@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) composite_weights_kernel(ffb_composite_de
 __global__ void __launch_bounds__(256) composite_app_fill_kernel(const float* __restrict__ weight, float thres,
                                                                  const int32_t* __restrict__ offsets,
                                                                  const int32_t* __restrict__ app_offsets, int64_t R,
-                                                                 int32_t* __restrict__ app_idx) {
+                                                                 int32_t* __restrict__ app_idx, int32_t* __restrict__ app_slot) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(256) composite_app_fill_kernel(const float* __
         if (s0 + u * 32 >= end) break;
         const bool f = i < end && wv[u] > thres;
         const unsigned m = __ballot_sync(0xffffffffu, f);
-        if (f) app_idx[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+        const int64_t j = base + __popc(m & ((1u << lane) - 1u));
+        if (f) app_idx[j] = (int32_t)i;
+        if (app_slot && i < end) app_slot[i] = f ? (int32_t)j : -1;      // the inverse map: shaded-sample slot of sample i, or -1
         base += __popc(m);
       }
     }
@@ -306,14 +308,19 @@ int ffb_composite_weights(const ffb_composite_desc* h_desc, const float* feat0, 
   return FFB_OK;
 }
 
-int ffb_composite_app_fill(const float* weight, float weight_thres, const int32_t* offsets, const int32_t* app_offsets, int64_t R,
-                           int32_t* app_idx, void* stream) {
+int ffb_composite_app_fill_ex(const float* weight, float weight_thres, const int32_t* offsets, const int32_t* app_offsets, int64_t R,
+                              int32_t* app_idx, int32_t* app_slot, void* stream) {
   FFB_REQUIRE(weight && offsets && app_offsets && app_idx, "null argument");
   if (R <= 0) return FFB_OK;
   composite_app_fill_kernel<<<blocks_for(R * 32, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(weight, weight_thres, offsets, app_offsets,
-                                                                                                 R, app_idx);
+                                                                                                 R, app_idx, app_slot);
   FFB_LAUNCHED();
   return FFB_OK;
+}
+
+int ffb_composite_app_fill(const float* weight, float weight_thres, const int32_t* offsets, const int32_t* app_offsets, int64_t R,
+                           int32_t* app_idx, void* stream) {
+  return ffb_composite_app_fill_ex(weight, weight_thres, offsets, app_offsets, R, app_idx, nullptr, stream);
 }
 
 int ffb_composite_accum(const ffb_composite_desc* h_desc, const float* weight, const float* z, const float* rgb,

@@ -383,9 +383,12 @@ __global__ void __launch_bounds__(256) render_input_fwd_kernel(const float* __re
   }
 }
 
+// g_app == nullptr: the gradient is ADDED into row app_idx[j] of the dense g_feat [*, ld_feat]; otherwise it is WRITTEN to row j of
+// the compact g_app [n, ld_app] (column 0, the density gradient, is not touched: it travels separately)
 __global__ void render_input_bwd_kernel(const float* __restrict__ feat, int ld_feat, const int32_t* __restrict__ app_idx,
                                         const float* __restrict__ g_in, int ld_gin, float* __restrict__ g_feat, int64_t n,
-                                        const int32_t* __restrict__ n_dev, int C, int viewpe, int feape) {
+                                        const int32_t* __restrict__ n_dev, int C, int viewpe, int feape,
+                                        float* __restrict__ g_app = nullptr, int ld_app = 0) {
   n = resolve_n(n, n_dev);
   const int W = ld_gin > 0 ? ld_gin : 3 + C + 6 * viewpe + 2 * feape * C;      // row stride of g_in
   const int oPF = C + 3;
@@ -405,7 +408,8 @@ __global__ void render_input_bwd_kernel(const float* __restrict__ feat, int ld_f
       sa = s2;
       ca = c2;
     }
-    g_feat[i * ld_feat + 1 + c] += s;
+    if (g_app) g_app[j * ld_app + 1 + c] = s;
+    else g_feat[i * ld_feat + 1 + c] += s;
   }
 }
 
@@ -529,6 +533,16 @@ int ffb_render_input_fwd(const float* feat, int32_t ld_feat, const float* rays, 
   FFB_REQUIRE((size_t)RIN_ROWS * W * sizeof(float) <= 48 * 1024, "input row too wide");
   render_input_fwd_kernel<<<blocks_for(n, RIN_ROWS, sm_count() * 8), 256, (size_t)RIN_ROWS * W * sizeof(float), (cudaStream_t)stream>>>(
       feat, ld_feat, rays, ray_id, app_idx, out, n, n_dev, C, viewpe, feape);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+int ffb_render_input_bwd_compact(const float* feat, int32_t ld_feat, const int32_t* app_idx, const float* g_in, int32_t ld_gin, float* g_app,
+                                 int32_t ld_app, int64_t n, const int32_t* n_dev, int32_t C, int32_t viewpe, int32_t feape, void* stream) {
+  FFB_REQUIRE(feat && g_in && g_app && C > 0 && ld_app >= C + 1, "bad argument");
+  if (n <= 0) return FFB_OK;
+  render_input_bwd_kernel<<<blocks_for(n * C, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(feat, ld_feat, app_idx, g_in, ld_gin, nullptr,
+                                                                                              n, n_dev, C, viewpe, feape, g_app, ld_app);
   FFB_LAUNCHED();
   return FFB_OK;
 }

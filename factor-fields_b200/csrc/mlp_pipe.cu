@@ -282,7 +282,11 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
                                                                    const float* __restrict__ W2, const uint16_t* __restrict__ mask,
                                                                    float* __restrict__ gx, float* __restrict__ gW1, float* __restrict__ gb1,
                                                                    float* __restrict__ gW2, int64_t n_cap, const int32_t* __restrict__ n_dev,
-                                                                   const Mlp2Shape S) {
+                                                                   const Mlp2Shape S, const float* __restrict__ g0 = nullptr,
+                                                                   const int32_t* __restrict__ row_slot = nullptr,
+                                                                   const float* __restrict__ g_rows = nullptr) {
+  // g0 != nullptr (SPARSE upstream gradient, the render path): column 0 of row i is g0[i]; columns 1.. are row row_slot[i] of the
+  // compact g_rows [*, N] when row_slot[i] >= 0 and zero otherwise (85 % of the samples at nerf.yaml) — gy is not read
   extern __shared__ __align__(128) uint8_t smem[];
   const int64_t n = resolve_n(n_cap, n_dev);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
     // ------------------------------ producers
     const int n_chunks = (int)(4 * Tc);
     const bool vecX = ((K0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
-    const bool vecG = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
+    const bool vecG = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(g0 ? g_rows : gy) & 15) == 0);
     for (;;) {
       int j = 0;
       if (lane == 0) j = atomicAdd(next_chunk, 1);
@@ -349,7 +353,25 @@ __global__ void __launch_bounds__(MPB_THREADS, 1) mlp2p_bwd_kernel(const float* 
       if (i < n) {
         const float* xr = x + i * K0;
         const float* gr = gy + i * N;
-        if (vecG) {
+        if (g0) {
+          const int sl = row_slot[i];
+          if (sl >= 0) {
+            const float* sr = g_rows + (int64_t)sl * N;
+            if (vecG) {
+#pragma unroll
+              for (int c = 0; c < MP_NP; c += 4)
+                if (c < N) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(sr + c);
+                  gv[c] = t4.x; gv[c + 1] = t4.y; gv[c + 2] = t4.z; gv[c + 3] = t4.w;
+                }
+            } else {
+#pragma unroll
+              for (int c = 0; c < MP_NP; ++c)
+                if (c < N) gv[c] = sr[c];
+            }
+          }
+          gv[0] = g0[i];
+        } else if (vecG) {
 #pragma unroll
           for (int c = 0; c < MP_NP; c += 4)
             if (c < N) {
@@ -593,6 +615,26 @@ int ffb_mlp2p_bwd(const float* x, const float* gy, const float* W1, const float*
   const int64_t tiles = (n + 127) / 128;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
   mlp2p_bwd_kernel<<<grid, MPB_THREADS, MpbSmem::TOTAL, (cudaStream_t)stream>>>(x, gy, W1, b1, W2, relu_mask, gx, gW1, gb1, gW2, n, n_dev, S);
+  FFB_LAUNCHED();
+  return FFB_OK;
+}
+
+/* The same backward for a SPARSE upstream gradient (the render path: every sample has a density gradient, only the shaded ones have
+ * feature gradients): gy[i, 0] = g0[i]; gy[i, 1:] = g_rows[row_slot[i], 1:] where row_slot[i] >= 0, zero elsewhere.  Saves the dense
+ * [n, N] gradient tensor (126 MB written and read per nerf.yaml step). */
+int ffb_mlp2p_bwd_sparse(const float* x, const float* g0, const int32_t* row_slot, const float* g_rows, const float* W1, const float* b1,
+                         const float* W2, const uint16_t* relu_mask, float* gx, float* gW1, float* gb1, float* gW2, int64_t n,
+                         const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream) {
+  FFB_REQUIRE(x && g0 && row_slot && g_rows && W1 && b1 && W2, "null argument");
+  Mlp2Shape S;
+  FFB_REQUIRE(pipe_shape_ok(K0, H, N, &S) && g_pipe_enabled, "MLP shape not eligible for the pipelined tensor-core path");
+  if (n <= 0) return FFB_OK;
+  static PerDeviceOnce once;
+  if (once.first()) FFB_CUDA(cudaFuncSetAttribute(mlp2p_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MpbSmem::TOTAL));
+  const int64_t tiles = (n + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  mlp2p_bwd_kernel<<<grid, MPB_THREADS, MpbSmem::TOTAL, (cudaStream_t)stream>>>(x, nullptr, W1, b1, W2, relu_mask, gx, gW1, gb1, gW2, n, n_dev, S,
+                                                                                g0, row_slot, g_rows);
   FFB_LAUNCHED();
   return FFB_OK;
 }

@@ -77,14 +77,18 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const int64_t* __restri
     const float4* g4 = reinterpret_cast<const float4*>(g + begin);
     float4* m4 = reinterpret_cast<float4*>(m + begin);
     float4* v4 = reinterpret_cast<float4*>(v + begin);
+    // the moments and the gradient are touched once per step: streaming (evict-first) accesses, so that this 7-stream sweep
+    // leaves the PARAMETERS — what the next step's gathers read — in L2 rather than a mix of all four arrays
     for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-      float4 pp = p4[i], mm = m4[i], vv = v4[i];
-      const float4 gg = g4[i];
+      float4 pp = p4[i], mm = __ldcs(m4 + i), vv = __ldcs(v4 + i);
+      const float4 gg = __ldcs(g4 + i);
       pp.x = upd(pp.x, gg.x, mm.x, vv.x);
       pp.y = upd(pp.y, gg.y, mm.y, vv.y);
       pp.z = upd(pp.z, gg.z, mm.z, vv.z);
       pp.w = upd(pp.w, gg.w, mm.w, vv.w);
-      p4[i] = pp; m4[i] = mm; v4[i] = vv;
+      p4[i] = pp;
+      __stcs(m4 + i, mm);
+      __stcs(v4 + i, vv);
     }
     i0 = begin + n4 * 4;
   }

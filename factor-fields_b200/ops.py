@@ -337,6 +337,22 @@ def _split_params(params, has_bias):
     return layers
 
 
+# Sparse hand-off of the compositor's gradient to linear_mat's backward.  d(loss)/d(linear_mat output) is dense only in column 0
+# (density); columns 1.. are non-zero for the shaded samples alone (~15 % at nerf.yaml).  With SPARSE_FEAT_GRAD on — train.TrainStep
+# switches it on around the graph it owns, where linear_mat's output feeds RenderComposite and nothing else — RenderComposite.backward
+# returns an UNWRITTEN dense-shaped tensor and parks (density gradient [Nv], slot map [Nv], compact rows [Na, ld]) under its
+# data_ptr; MLPFunction.backward picks them up and runs ffb_mlp2p_bwd_sparse.  Saves writing and re-reading [Nv, 32] floats
+# (2 x 126 MB per step).  `sparse_grads_pending()` lets the owner check that every parked gradient was consumed.
+SPARSE_FEAT_GRAD = False
+_sparse_grads = {}
+
+
+def sparse_grads_pending():
+    n = len(_sparse_grads)
+    _sparse_grads.clear()
+    return n
+
+
 class MLPFunction(torch.autograd.Function):
     """MLPMixer.forward (FactorFields.py:144-159): optional PE concat, Linear+ReLU ..., bias-free last layer."""
 
@@ -393,6 +409,17 @@ class MLPFunction(torch.autograd.Function):
             gW1 = _grad_like(W1) if needs[4] else None
             gb1 = _grad_like(b1) if needs[5] else None
             gW2 = _grad_like(W2) if needs[6] else None
+            sp = _sparse_grads.pop(g.data_ptr(), None) if _sparse_grads else None
+            if sp is not None:
+                g0, slot, rows, shape = sp
+                if shape != tuple(g.shape) or nv.lib().ffb_mlp2_pipelined_eligible(D, W1.shape[0], W2.shape[0]) != 1:
+                    raise RuntimeError('ffb200: a sparse compositor gradient reached an MLP that cannot consume it')
+                with nv.section('mlp_bwd'):
+                    nv.check(nv.lib().ffb_mlp2p_bwd_sparse(nv.ptr(x), nv.ptr(g0), nv.i32p(slot), nv.ptr(rows), nv.ptr(W1), nv.ptr(b1), nv.ptr(W2),
+                                                           nv.ptr(relu_bits, torch.int16), nv.ptr(gx, allow_none=True),
+                                                           nv.ptr(gW1, allow_none=True), nv.ptr(gb1, allow_none=True), nv.ptr(gW2, allow_none=True),
+                                                           C.c_int64(n), nv.i32p(ctx.n_dev), D, W1.shape[0], W2.shape[0], nv.stream()))
+                return (gx, None, None, None, gW1, gb1, gW2)
             with nv.section('mlp_bwd'):
                 nv.check(nv.lib().ffb_mlp2_bwd(nv.ptr(x), nv.ptr(g.contiguous()), nv.ptr(W1), nv.ptr(b1), nv.ptr(W2), nv.ptr(relu_bits, torch.int16),
                                                nv.ptr(gx, allow_none=True),
@@ -583,9 +610,12 @@ class RenderComposite(torch.autograd.Function):
         Cf = ld - 1
         Win = 3 + Cf + 6 * view_pe + 2 * fea_pe * Cf
         acts, kinds = [], []
+        app_slot = None
         if Na > 0:
-            nv.check(lib.ffb_composite_app_fill(nv.ptr(weight), C.c_float(cdesc.weight_thres), nv.i32p(offsets), nv.i32p(app_offsets),
-                                                C.c_int64(R), nv.i32p(app_idx), nv.stream()))
+            if SPARSE_FEAT_GRAD and ctx.needs_input_grad[0] and ld % 4 == 0:
+                app_slot = _empty((Nv,), feat, torch.int32)      # inverse of app_idx, for the sparse gradient hand-off
+            nv.check(lib.ffb_composite_app_fill_ex(nv.ptr(weight), C.c_float(cdesc.weight_thres), nv.i32p(offsets), nv.i32p(app_offsets),
+                                                   C.c_int64(R), nv.i32p(app_idx), nv.i32p(app_slot), nv.stream()))
             ws_bytes = 0
             if len(layers) == 3 and tuple(has_bias) == (True, True, False) and layers[2][0].shape[0] == 3 \
                     and layers[1][0].shape[0] == layers[1][0].shape[1] == layers[0][0].shape[0] and layers[0][0].shape[1] == Win \
@@ -633,6 +663,7 @@ class RenderComposite(torch.autograd.Function):
                                          nv.i32p(app_offsets), C.c_int64(R), nv.ptr(rgb_map), nv.ptr(pre_clamp), nv.ptr(acc),
                                          nv.ptr(depth), nv.stream()))
         ctx.cdesc, ctx.samp, ctx.has_bias, ctx.kinds = cdesc, samp, has_bias, kinds
+        ctx.app_slot = app_slot if kinds == 'fused' else None
         ctx.view_pe, ctx.fea_pe, ctx.n_acts, ctx.Na, ctx.a_dev = view_pe, fea_pe, len(acts), Na, a_dev
         ctx.save_for_backward(feat, sigma, trans, weight, rgb, app_offsets, app_idx, pre_clamp, *acts, *params)
         n_app = app_offsets[R] if lazy else torch.tensor(Na)
@@ -652,8 +683,11 @@ class RenderComposite(torch.autograd.Function):
         Nv, ld = feat.shape
         R = samp['rays'].shape[0]
         Na = ctx.Na
-        zero_rest = 1 if (ld % 4 == 0 and Nv > 0) else 0     # the composite kernel writes whole gradient rows: no memset of [Nv, ld]
-        g_feat = torch.empty_like(feat) if zero_rest else torch.zeros_like(feat)
+        sparse = ctx.app_slot is not None and Na > 0 and Nv > 0
+        zero_rest = 1 if (ld % 4 == 0 and Nv > 0 and not sparse) else 0     # the composite kernel writes whole gradient rows: no memset of [Nv, ld]
+        # sparse hand-off (SPARSE_FEAT_GRAD): g_feat stays unwritten, the density gradient goes to a compact [Nv] vector
+        g_feat = torch.empty_like(feat) if (zero_rest or sparse) else torch.zeros_like(feat)
+        g0 = _empty((Nv,), feat) if sparse else None
         g_rgb = _empty((Na, 3), feat)
         g_rgb_map = g_rgb_map.contiguous()
         if Nv > 0:
@@ -662,7 +696,7 @@ class RenderComposite(torch.autograd.Function):
                                                nv.ptr(samp['dist']), nv.ptr(sigma), nv.ptr(trans), nv.ptr(weight),
                                                nv.ptr(rgb) if Na > 0 else None,
                                                nv.i32p(samp['offsets']), nv.i32p(app_offsets), C.c_int64(R), nv.ptr(g_rgb) if Na > 0 else None,
-                                               nv.ptr(g_feat), ld, zero_rest, nv.stream()))
+                                               nv.ptr(g0 if sparse else g_feat), 1 if sparse else ld, zero_rest, nv.stream()))
         layers = _split_params(params, ctx.has_bias)
         needs = ctx.needs_input_grad[6:]
         pn, i = [], 0
@@ -687,8 +721,14 @@ class RenderComposite(torch.autograd.Function):
             else:
                 with nv.section('rgbmlp_bwd'):
                     g_in, grads = _mlp_backward(acts, layers, ctx.kinds, g_rgb, True, pn, ctx.a_dev)
-            nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), g_in.shape[1], nv.ptr(g_feat), C.c_int64(Na),
-                                              nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
+            if sparse:
+                g_app = _empty((Na, ld), feat)
+                nv.check(lib.ffb_render_input_bwd_compact(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), g_in.shape[1], nv.ptr(g_app), ld,
+                                                          C.c_int64(Na), nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
+                _sparse_grads[g_feat.data_ptr()] = (g0, ctx.app_slot, g_app, tuple(g_feat.shape))
+            else:
+                nv.check(lib.ffb_render_input_bwd(nv.ptr(feat), ld, nv.i32p(app_idx), nv.ptr(g_in), g_in.shape[1], nv.ptr(g_feat), C.c_int64(Na),
+                                                  nv.i32p(ctx.a_dev), Cf, ctx.view_pe, ctx.fea_pe, nv.stream()))
             for (gW, gb), hb in zip(grads, ctx.has_bias):
                 flat.append(gW)
                 if hb:

@@ -335,11 +335,18 @@ class TrainStep:
         m.lazy_counts = True          # device-side sample counts, scoped to this step: direct model(rays) calls stay exact-sized
         self._split = {'late': {p.data_ptr() for p in self.late}} if self.late else None
         _ops.set_field_bwd_split(self._split)
+        # in this graph linear_mat's output feeds the compositor and nothing else: its gradient can travel sparse (ops.SPARSE_FEAT_GRAD)
+        prev_sparse = _ops.SPARSE_FEAT_GRAD
+        _ops.SPARSE_FEAT_GRAD = self._sparse_ok()
+        _ops.sparse_grads_pending()
         try:
             rgb, depth, _ = m(self.rays_s, white_bg=self.white_bg, is_train=True, ndc_ray=self.ndc_ray, N_samples=self.S)
             _, g_rgb = _ops.mse_fwd_bwd(rgb, self.target_s, loss=self.loss_s)
             grads = torch.autograd.grad([rgb], self.params, grad_outputs=[g_rgb], allow_unused=True)
+            if _ops.sparse_grads_pending():
+                raise RuntimeError('ffb200: a sparse compositor gradient was not consumed by linear_mat\'s backward')
         finally:
+            _ops.SPARSE_FEAT_GRAD = prev_sparse
             _ops.set_grad_arena(None)
             _ops.set_field_bwd_split(None)
             m._z_static = None
@@ -354,6 +361,25 @@ class TrainStep:
                 v = self.bucket.view(self._arena_index[id(self.params[k])])
                 if g.data_ptr() != v.data_ptr():
                     v.copy_(g)
+
+    def _sparse_ok(self):
+        """True when linear_mat's backward can take the compositor's gradient in sparse form (ops.SPARSE_FEAT_GRAD): the plain
+        2-layer MLPMixer of the per-scene configs in a shape the pipelined tensor-core kernel runs.  FFB_SPARSE_FEAT_GRAD=0 turns
+        the hand-off off (dense gradient tensor, as a direct loss.backward() produces)."""
+        if os.environ.get('FFB_SPARSE_FEAT_GRAD', '1') == '0':
+            return False
+        from . import native as nv
+        lm = getattr(self.model, 'linear_mat', None)
+        try:
+            params, has_bias = lm._flat()
+            if lm.pe != 0 or lm.with_dropout or len(has_bias) != 2 or tuple(has_bias) != (True, False):
+                return False
+            W1, W2 = params[0], params[2]
+            if not all(p.requires_grad for p in params):
+                return False
+            return nv.lib().ffb_mlp2_pipelined_eligible(W1.shape[1], W1.shape[0], W2.shape[0]) == 1
+        except Exception:
+            return False
 
     def _late_backward(self):
         """Second phase of the field backward (deferred by _render_backward when `self.late` is non-empty)."""

@@ -257,6 +257,14 @@ int ffb_mlp2_fwd(const float* x, const float* W1, const float* b1, const float* 
 int ffb_mlp2_bwd(const float* x, const float* gy, const float* W1, const float* b1, const float* W2,
                  const uint16_t* relu_mask, float* gx, float* gW1, float* gb1, float* gW2, int64_t n,
                  const int32_t* n_dev, int32_t K0, int32_t H, int32_t N, void* stream);
+/* ffb_mlp2_bwd for the SPARSE upstream gradient of the render path (shapes with ffb_mlp2_pipelined_eligible == 1): every
+ * sample has a density gradient, only the shaded ones (weight > threshold, :879-881) have feature gradients.
+ * gy[i, 0] = g0[i];  gy[i, 1:] = g_rows[row_slot[i], 1:] where row_slot[i] >= 0, zero elsewhere (g_rows [*, N]; its column
+ * 0 is ignored).  The dense [n, N] gradient (126 MB written and read per nerf.yaml step) is never materialised. */
+int ffb_mlp2p_bwd_sparse(const float* x, const float* g0, const int32_t* row_slot, const float* g_rows,
+                         const float* W1, const float* b1, const float* W2, const uint16_t* relu_mask, float* gx,
+                         float* gW1, float* gb1, float* gW2, int64_t n, const int32_t* n_dev, int32_t K0,
+                         int32_t H, int32_t N, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * get_coding + linear_mat as ONE kernel per direction (field_mlp.cu): FactorFields.py:425-533 followed by
@@ -290,6 +298,11 @@ int ffb_render_input_fwd(const float* feat, int32_t ld_feat, const float* rays, 
 int ffb_render_input_bwd(const float* feat, int32_t ld_feat, const int32_t* app_idx, const float* g_in,
                          int32_t ld_gin, float* g_feat, int64_t n, const int32_t* n_dev, int32_t C,
                          int32_t viewpe, int32_t feape, void* stream);
+/* Same, WRITING row j of the compact g_app [n, ld_app] (columns 1..C; column 0 untouched) instead of adding into row
+ * app_idx[j] of a dense gradient: the rows ffb_mlp2p_bwd_sparse consumes. */
+int ffb_render_input_bwd_compact(const float* feat, int32_t ld_feat, const int32_t* app_idx, const float* g_in,
+                                 int32_t ld_gin, float* g_app, int32_t ld_app, int64_t n, const int32_t* n_dev,
+                                 int32_t C, int32_t viewpe, int32_t feape, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused appearance MLP (MLPRender_Fea.forward, FactorFields.py:188-203, on the shaded samples of
@@ -390,6 +403,10 @@ int ffb_composite_weights(const ffb_composite_desc* h_desc, const float* feat0, 
 /* app_idx [Na]: indices (into the valid list) of shaded samples, in order. */
 int ffb_composite_app_fill(const float* weight, float weight_thres, const int32_t* offsets,
                            const int32_t* app_offsets, int64_t R, int32_t* app_idx, void* stream);
+/* Same, also writing the inverse map app_slot [Nv] (may be NULL): slot of sample i in app_idx, or -1 when it is not shaded. */
+int ffb_composite_app_fill_ex(const float* weight, float weight_thres, const int32_t* offsets,
+                              const int32_t* app_offsets, int64_t R, int32_t* app_idx, int32_t* app_slot,
+                              void* stream);
 /* Phase B: rgb_map [R,3] (clamped), acc [R], depth [R]; rgb [Na,3] in app order. pre_clamp [R,3]. */
 int ffb_composite_accum(const ffb_composite_desc* h_desc, const float* weight, const float* z,
                         const float* rgb, const int32_t* offsets, const int32_t* app_offsets, int64_t R,

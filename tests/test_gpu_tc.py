@@ -317,3 +317,55 @@ def test_fused_appearance_mlp_backward(n):
     rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max())
     for name, got, want in zip(['g_x', 'gW1', 'gb1', 'gW2', 'gb2', 'gW3'], [g_x, gW1, gb1, gW2, gb2, gW3], ref):
         assert rel(got, want) < 5e-5, (name, rel(got, want))
+
+
+@pytest.mark.parametrize('K0,N,cap,use_ndev', [(18, 32, 200077, False), (18, 32, 200077, True), (20, 8, 5000, True)])
+def test_pipelined_mlp2_backward_sparse_upstream_gradient(K0, N, cap, use_ndev):
+    """ffb_mlp2p_bwd_sparse (the render path's hand-off: a density gradient for every row, feature gradients only for the rows with
+    a slot in a compact table) against ffb_mlp2_bwd on the equivalent dense gradient — same operands, so the results agree to the
+    rounding of the cross-CTA accumulation; rows without a slot must not read the compact table."""
+    from ffb200 import native as nv
+    lib = nv.lib()
+    H = 64
+    assert lib.ffb_mlp2_pipelined_eligible(K0, H, N) == 1
+    torch.manual_seed(K0 + N + cap)
+    n = cap - 777 if use_ndev else cap
+    x = torch.randn(cap, K0, device='cuda')
+    W1 = torch.randn(H, K0, device='cuda') / K0 ** 0.5
+    b1 = torch.randn(H, device='cuda') * 0.3
+    W2 = torch.randn(N, H, device='cuda') / H ** 0.5
+    n_dev = torch.tensor([n], device='cuda', dtype=torch.int32) if use_ndev else None
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    s = nv.stream()
+    y = torch.empty(cap, N, device='cuda')
+    bits = torch.zeros(cap, H // 16, device='cuda', dtype=torch.int16)
+    nv.check(lib.ffb_mlp2_fwd(P(x), P(W1), P(b1), P(W2), P(y), P(bits), C.c_int64(cap), P(n_dev), K0, H, N, s))
+    # ~15 % of the rows carry feature gradients, in a shuffled compact table padded with NaN rows that nothing may read
+    shaded = torch.rand(cap, device='cuda') < 0.15
+    idx = torch.nonzero(shaded).flatten()
+    n_rows = idx.numel()
+    slot = torch.full((cap,), -1, device='cuda', dtype=torch.int32)
+    slot[idx] = torch.arange(n_rows, device='cuda', dtype=torch.int32)
+    rows = torch.full((n_rows + 64, N), float('nan'), device='cuda')
+    rows[:n_rows] = torch.randn(n_rows, N, device='cuda')
+    rows[:n_rows, 0] = float('nan')                       # column 0 of the compact rows is ignored
+    g0 = torch.randn(cap, device='cuda')
+    gy = torch.zeros(cap, N, device='cuda')
+    gy[idx] = rows[:n_rows]
+    gy[:, 0] = g0
+    out = []
+    for sparse in (False, True):
+        gx = torch.full((cap, K0), 7.0, device='cuda')
+        gW1, gb1, gW2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2)
+        if sparse:
+            nv.check(lib.ffb_mlp2p_bwd_sparse(P(x), P(g0), P(slot), P(rows), P(W1), P(b1), P(W2), P(bits), P(gx), P(gW1), P(gb1), P(gW2),
+                                              C.c_int64(cap), P(n_dev), K0, H, N, s))
+        else:
+            nv.check(lib.ffb_mlp2_bwd(P(x), P(gy), P(W1), P(b1), P(W2), P(bits), P(gx), P(gW1), P(gb1), P(gW2), C.c_int64(cap), P(n_dev),
+                                      K0, H, N, s))
+        out.append((gx, gW1, gb1, gW2))
+    assert torch.equal(out[0][0][:n], out[1][0][:n])                       # input gradient: row-local arithmetic, bit-identical
+    assert bool((out[1][0][n:] == 7.0).all())
+    for name, a, b in zip(('gW1', 'gb1', 'gW2'), out[0][1:], out[1][1:]):
+        assert bool(torch.isfinite(b).all()), name
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max()), name
