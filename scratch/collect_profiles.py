@@ -2,6 +2,7 @@
 SASS census.  usage: python scratch/collect_profiles.py   (from the repo root, after the record run has been merged back)"""
 import json, os, re, subprocess, sys
 
+PARTS = set(sys.argv[1:]) or {'bench', 'ncu', 'ncu_presets', 'launches', 'probes', 'sanitizer', 'sass'}    # which records to refresh
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
 G, P, T = 'gpurun_out', 'profiles', 'r2f'
@@ -26,7 +27,7 @@ def sh(cmd, out=None):
 # ---- bench lines
 names = {'bench': 'nerf', 'bench_ref': 'reference_arm', 'bench_nerf_vm': 'nerf_vm', 'bench_nerf_cp': 'nerf_cp', 'bench_image': 'image',
          'bench_sdf': 'sdf', 'bench_image_set': 'image_set', 'bench_nerf_eval': 'nerf_eval'}
-for src, dst in names.items():
+for src, dst in (names.items() if 'bench' in PARTS else ()):
     f = f'{G}/{T}_{src}.json'
     try:
         d = last_json_line(f)
@@ -39,7 +40,9 @@ for src, dst in names.items():
 
 # ---- ncu --set full summaries
 rep = f'{G}/{T}_prof_step.ncu-rep'
-if os.path.exists(rep):
+if 'ncu' not in PARTS:
+    pass
+elif os.path.exists(rep):
     subprocess.run([sys.executable, 'scratch/ncu_summary.py', rep, f'{P}/r02_ncu_step', f'Round 2: kernels of the nerf.yaml train step (build {rev}), ncu --set full, one launch each',
                     "ncu --set full --clock-control none --import-source on -k regex:'fast_fwd_kernel|fast_bwd_saved_agg|mlp2p_fwd|mlp2p_bwd|rgb_fwd_kernel|rgb_bwd_kernel' -s 36 -c 6 python scratch/prof_step.py"],
                    stdout=subprocess.DEVNULL)
@@ -54,7 +57,7 @@ if os.path.exists(rep):
 else:
     print('MISSING', rep)
 # the preset / regression captures were summarised on the box (scratch/r2_final.sh: the .ncu-rep files would exceed what gpurun brings back)
-for w in ('nerf_vm', 'nerf_cp', 'image', 'sdf', 'image_set'):
+for w in (('nerf_vm', 'nerf_cp', 'image', 'sdf', 'image_set') if 'ncu_presets' in PARTS else ()):
     ok = False
     for ext in ('md', 'json'):
         f = f'{G}/{T}_ncusum_{w}.{ext}'
@@ -67,8 +70,9 @@ for w in ('nerf_vm', 'nerf_cp', 'image', 'sdf', 'image_set'):
     print('ncu summary', w, 'ok' if ok else 'MISSING')
 
 # ---- launch lists
-for src, dst, cmd in (('launches', 'launches', 'python bench.py --steps 2 --warmup 3 --eager'),
-                      ('launches_graph', 'launches_graph', 'python bench.py --steps 4 --warmup 3   (the default CUDA-graph step: kernel nodes of the replayed graph)')):
+for src, dst, cmd in ((('launches', 'launches', 'python bench.py --steps 2 --warmup 3 --eager'),
+                       ('launches_graph', 'launches_graph', 'python bench.py --steps 4 --warmup 3   (the default CUDA-graph step: kernel nodes of the replayed graph)'))
+                      if 'launches' in PARTS else ()):
     f = f'{G}/{T}_{src}.csv'
     if os.path.exists(f) and os.path.getsize(f) > 1000:
         body = sh(f'{sys.executable} scratch/launch_summary.py {f}')
@@ -80,6 +84,8 @@ for src, dst, cmd in (('launches', 'launches', 'python bench.py --steps 2 --warm
 
 # ---- probes
 try:
+    if 'probes' not in PARTS:
+        raise KeyError('skipped')
     open(f'{P}/r02_probe_red.json', 'w').write(json.dumps(last_json_line(f'{G}/{T}_probe_red.json')) + '\n')
     txt = open(f'{G}/{T}_probe_mma.txt').read()
     open(f'{P}/r02_probe_mma.md', 'w').write('# tcgen05.mma issue / execution rate vs N (M = 128, K = 16, bf16, SWIZZLE_NONE smem operands), one elected thread per SM, B200\n\n'
@@ -100,7 +106,8 @@ for tool in ('memcheck', 'racecheck', 'initcheck'):
     summ = next((l.strip('= ').strip() for l in reversed(lines) if 'SUMMARY' in l), '?')
     rows.append(f'| {tool} | {rc} | {summ} |')
     tails += [f'[{tool}] {l}' for l in lines[-5:]]
-open(f'{P}/r02_sanitizer.md', 'w').write(
+if 'sanitizer' in PARTS:
+  open(f'{P}/r02_sanitizer.md', 'w').write(
     f'# compute-sanitizer over the shared-memory / vector-reduction / tensor-core kernels (round 2, build {rev})\n\n'
     'Command (per tool): `compute-sanitizer --tool <memcheck|racecheck|initcheck> --error-exitcode 1 python scratch/sanitize_case.py`\n'
     'on one B200.  The script renders 96 rays x 120 samples through `FactorFields.forward` + autograd twice (exact-sized and\n'
@@ -113,5 +120,6 @@ open(f'{P}/r02_sanitizer.md', 'w').write(
     '| tool | exit code | summary line |\n|---|---|---|\n' + '\n'.join(rows) + '\n\nLog tails:\n```\n' + '\n'.join(tails) + '\n```\n')
 
 # ---- SASS census (of the library that ran)
-sh('bash scratch/sass_census.sh', f'{P}/r02_sass_census.md')
+if 'sass' in PARTS:
+    sh('bash scratch/sass_census.sh', f'{P}/r02_sass_census.md')
 print('done; GPU tests:', open(f'{G}/{T}_gpu_tests.log').read().strip().splitlines()[-2:])

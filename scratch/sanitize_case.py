@@ -30,6 +30,15 @@ for lazy in (False, True):
     grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
     torch.cuda.synchronize()
     print('lazy', lazy, 'n_valid', int(m.last_stats['n_valid']), 'n_app', int(m.last_stats['n_app']), 'loss', float(loss))
+# the CUDA-graph step's launch sequence, run eagerly: device-side counts + the sparse hand-off of the compositor's gradient
+# (composite_app_fill's slot map, render_input_bwd's compact rows, mlp2p_bwd's sparse producer)
+from ffb200.train import TrainStep
+ts = TrainStep(m, m.get_optparam_groups(0.001, 0.02), batch=R, n_samples=S, lr_decay=0.999, use_graph=False)
+tgt = torch.rand(R, 3, device='cuda')
+for _ in range(2):
+    ts.step(rays, tgt, torch.rand(R, device='cuda'))
+torch.cuda.synchronize()
+print('train step (sparse gradient hand-off:', ts._sparse_ok(), ') loss', float(ts.loss_s))
 # the -CP / -vm preset kernels (field_lines.cu: TMA-staged lines + shared-memory-privatised accumulation; field_planes.cu)
 nv.check(nv.lib().ffb_set_tuning(b'field_level_parallel', 1))
 for ov in (['model.coeff_type=vec', 'model.basis_type=cp', 'model.freq_bands=[1.,1.,1.,1.,1.,1.]', 'model.basis_resos=[64,64,64,64,64,64]',
