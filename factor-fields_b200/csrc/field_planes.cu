@@ -5,10 +5,12 @@
 //
 // Same design as field_fast.cu (one thread per query, consecutive threads = consecutive samples of a ray, channels-last texels
 // read as float4 / float2, x-neighbour corners adjacent, scatter with red.global.add.v4/v2.f32), adapted to the factorisation:
-// the 3 x Cc coefficient row of a query is interpolated first and parked in shared memory (one column of a [W][threads] tile
-// per thread: conflict-free), because the re-ordering scatters the basis columns across it; every plane sample is then combined
-// with its coefficient, and in the backward pass REPLACED by the coefficient gradient in place, so one shared-memory row per
-// thread serves both directions.  The backward pass re-gathers (no saved rows: all factors are L2 resident).
+// the 3 x Cc coefficient row of a query is interpolated first and parked in shared memory, because the re-ordering scatters the
+// basis columns across it; every plane sample is then combined with its coefficient, and in the backward pass REPLACED by the
+// coefficient gradient in place.  Two generations: vm_fwd_kernel / vm_bwd_kernel (one column of a [W][threads] tile per thread,
+// per-lane row traffic to global memory) and — the default — vm_fwd2_kernel / vm_bwd2_kernel, which move whole 32-query WARP
+// TILES to / from global memory as coalesced 16-byte pieces (see below).  The plane texels are always re-gathered by the
+// backward pass (L2 resident); the coefficient row comes from the forward's output.
 #include "field_fast.cuh"
 
 namespace ffb {
