@@ -2,9 +2,11 @@
 
 Restatement of the reference's NeRF train step (grid coefficient x grid basis, bounded scene) with the SAME
 third-party operators the reference calls (torch CPU: F.grid_sample, nn.functional.linear, cumprod, autograd,
-Adam), so that timing it on the host cores reproduces the cost of the reference's CPU path.  The reference itself
-(pure Python) cannot travel to the GPU box; this file is what `bench.py`'s cpu_baseline leg and `--impl reference`
-time ("kind": "port").  Pinned against the golden vectors in tests/test_oracle_golden.py::test_torch_port.
+Adam), so that timing it on the host cores reproduces the cost of the reference's CPU path.  `bench.py`'s NeRF legs
+(cpu_baseline, `--impl reference`, the CUDA-eager bar) run the UNMODIFIED reference from the git-ignored copy under
+baseline/_ref/factor-fields ("kind": "reference"); this port is their fallback when that copy is absent ("kind": "port"),
+the CPU leg of the regression bench lines (the reference's regression loops live in notebooks), and the reference side of
+the PSNR-parity tests.  Pinned against the golden vectors in tests/test_oracle_golden.py::test_torch_port.
 
 Follows /root/reference/models/FactorFields.py (line numbers cited inline) and train_per_scene.py:149-171.
 """
